@@ -1,0 +1,152 @@
+/*
+ * yolopost_b200 - C-ABI of the B200-native YOLO detection post-processing path.
+ *
+ * Drop-in boundary.  The reference (Chriz122/ultralytics_pro, pure Python) has no
+ * FFI layer for this path: its boundary is Python attribute binding of
+ *     ultralytics/nn/modules/head.py:151   Detect._inference(self, x)            -> ypb_decode_dense
+ *     ultralytics/nn/modules/head.py:184   Detect.decode_bboxes(...)             -> ypb_decode_dense
+ *     ultralytics/nn/modules/head.py:1026  OBB.forward / :1040 OBB.decode_bboxes -> ypb_decode_dense (angle)
+ *     ultralytics/utils/nms.py:13          non_max_suppression(prediction, ...)  -> ypb_nms_from_dense
+ *     (head.py:151 + nms.py:13 back to back, the `postprocess` timer envelope)   -> ypb_nms_from_head
+ *     ultralytics/utils/nms.py:239/187/299 TorchNMS.nms / fast_nms / batched_nms -> ypb_nms_boxes
+ * The ctypes binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer except `ypb_*_desc*` / `ypb_nms_params*` (host structs) is a DEVICE pointer owned by the caller
+ *     (torch caching allocator); the library allocates nothing and frees nothing;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return value: 0 = OK, negative = error (see ypb_status); ypb_last_error_string() gives the text for the
+ *     calling thread;
+ *   - there is no CPU fallback: the library needs a CUDA device of compute capability 10.x.
+ */
+#ifndef YOLOPOST_B200_H_
+#define YOLOPOST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define YPB_API __attribute__((visibility("default")))
+#else
+#define YPB_API
+#endif
+
+#define YPB_ABI_VERSION 1
+#define YPB_MAX_LEVELS 8
+
+typedef enum { YPB_F32 = 0, YPB_F16 = 1, YPB_BF16 = 2 } ypb_dtype;
+
+typedef enum {
+  YPB_OK = 0,
+  YPB_ERR_INVALID_ARGUMENT = -1,
+  YPB_ERR_UNSUPPORTED = -2,
+  YPB_ERR_WORKSPACE_TOO_SMALL = -3,
+  YPB_ERR_CUDA = -4
+} ypb_status;
+
+/* Suppression rule (utils/nms.py). */
+typedef enum {
+  YPB_NMS_GREEDY = 0,       /* nms.py:239-296 == torchvision.ops.nms: suppress iff inter/(a_i+a_j-inter) > thr, no eps */
+  YPB_NMS_FAST_PROBIOU = 1, /* nms.py:187-236 with metrics.py:251 batch_probiou: drop j iff ANY higher-ranked i has piou >= thr */
+  YPB_NMS_FAST_BOXIOU = 2   /* nms.py:187-236 with metrics.py:54 box_iou (eps 1e-7 in the denominator), >= thr */
+} ypb_nms_rule;
+
+/* Detect-head raw output: L levels of (B, 4*reg_max+nc, H_l, W_l), anchors (H_l*W_l) contiguous.
+ * head.py:121-122 builds exactly these tensors; head.py:162 is the concat this library never materialises. */
+typedef struct {
+  int32_t num_levels;
+  int32_t batch;
+  int32_t nc;      /* classes */
+  int32_t reg_max; /* DFL bins per side (block.py:232); 1 = no DFL (raw ltrb) */
+  int32_t dtype;   /* ypb_dtype of the level tensors */
+  int32_t reserved;
+  const void* level_ptr[YPB_MAX_LEVELS];
+  int32_t level_h[YPB_MAX_LEVELS];
+  int32_t level_w[YPB_MAX_LEVELS];
+  int64_t level_batch_stride[YPB_MAX_LEVELS];   /* elements */
+  int64_t level_channel_stride[YPB_MAX_LEVELS]; /* elements; pixel stride must be 1 */
+  float level_stride[YPB_MAX_LEVELS];           /* model stride of the level (head.py:79 self.stride) */
+} ypb_head_desc;
+
+/* Decoded prediction tensor (B, 4+nc+extra, A) as consumed by nms.py:13 - any strides (models/nas/predict.py:54
+ * passes a permuted view). */
+typedef struct {
+  const void* ptr;
+  int32_t dtype;
+  int32_t batch;
+  int32_t channels; /* 4 + nc + extra */
+  int32_t anchors;
+  int64_t stride_b, stride_c, stride_a; /* elements */
+} ypb_dense_desc;
+
+/* Arguments of non_max_suppression (nms.py:13-29) that reach the device. */
+typedef struct {
+  float conf_thres;     /* already rounded to the prediction dtype by the caller (torch casts the scalar, nms.py:76) */
+  float iou_thres_eff;  /* GREEDY: largest float <= iou_thres (double compare in torchvision); FAST_*: (float)iou_thres */
+  int32_t nc;
+  int32_t extra;        /* channels after the class scores (mask coeffs, keypoints, angle) */
+  int32_t max_det;      /* nms.py:157 */
+  int32_t max_nms;      /* nms.py:137 */
+  float max_wh;         /* nms.py:143; 0 when agnostic */
+  int32_t multi_label;  /* nms.py:82,114 (already AND-ed with nc > 1) */
+  int32_t rule;         /* ypb_nms_rule; FAST_PROBIOU == rotated=True (boxes stay xywh + angle = last channel) */
+  int32_t rows_cap;     /* candidate rows reserved per image in the workspace (A, or A*nc for multi_label) */
+  const uint32_t* class_mask; /* device bitmask of allowed classes (nms.py:127-131) or NULL */
+} ypb_nms_params;
+
+/* Result buffers (device).  rows: (B, max_det, 6+extra) fp32 = x1,y1,x2,y2,conf,cls,extra... (xywh + angle when
+ * rotated); idx: (B, max_det) int64 anchor index of each kept row (nms.py:161 keepi) or NULL; count: (B) int32;
+ * cand_count: (B) int32 rows that passed the confidence filter before any cap (diagnostic) or NULL. */
+typedef struct {
+  float* rows;
+  int64_t* idx;
+  int32_t* count;
+  int32_t* cand_count;
+} ypb_nms_out;
+
+YPB_API int ypb_abi_version(void);
+YPB_API const char* ypb_last_error_string(void);
+
+/* Bytes of scratch needed by ypb_nms_from_head / ypb_nms_from_dense for this geometry. */
+YPB_API size_t ypb_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t rows_cap, int32_t max_det, int32_t max_nms,
+                               int32_t rule);
+
+/* Dense decode == Detect._inference (head.py:151-169): writes (B, 4+nc[+1], A) in `out_dtype`.
+ *   angle            : NULL, or (B, A) contiguous rotation channel of the OBB head (head.py:1028)
+ *   angle_is_logit   : 1 = raw cv4 output, the kernel applies (sigmoid-0.25)*pi (head.py:1031); 0 = already activated
+ *   append_angle     : 1 = also write the activated angle as channel 4+nc (head.py:1038)
+ *   xyxy             : 1 = corners instead of cx,cy,w,h (head.py:189 end2end / self.xyxy); ignored when angle != NULL */
+YPB_API int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t append_angle,
+                     int32_t xyxy, void* out, int32_t out_dtype, int64_t out_stride_b, int64_t out_stride_c,
+                     void* stream);
+
+/* Fused decode -> confidence filter -> sort/top-k -> suppression -> gather, reading the head once and never writing
+ * the dense tensor.  `value_dtype` is the dtype the dense tensor WOULD have had (scores and boxes are rounded to it
+ * so results are bit-identical to ypb_decode_dense followed by ypb_nms_from_dense). */
+YPB_API int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
+                      const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* non_max_suppression on an already decoded tensor (nms.py:13-166). */
+YPB_API int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, const ypb_nms_out* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* TorchNMS.nms / fast_nms on one box set (nms.py:187-296): boxes (n, 4|5) fp32 row-major, scores (n) fp32.
+ * keep: (n) int64 indices in descending-score order, keep_count: (1) int32.  Workspace: ypb_nms_boxes_workspace_bytes(n). */
+YPB_API size_t ypb_nms_boxes_workspace_bytes(int32_t n);
+YPB_API int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t box_dim, int32_t rule,
+                  float iou_thres_eff, int64_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Diagnostic: exhaustively checks that the device sigmoid used by the decode kernels is monotone non-decreasing
+ * over all finite fp32 inputs after rounding to `dtype`; writes the number of violations to *violations (device). */
+YPB_API int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOPOST_B200_H_ */

@@ -1,0 +1,314 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): decode within 1e-5 relative for fp32 (implemented as |d| <= 1e-5*|ref| + 1e-5*imgsz,
+SURVEY.md Appendix B-7) / 1e-2 for bf16; NMS kept indices, counts and row values bit-exact when both sides are fed
+the same decoded tensor.
+"""
+import pytest
+import torch
+
+from oracle.postproc_oracle import decode_oracle, nms_oracle, obb_forward_oracle
+from tests.helpers import assert_rows_equal, dense_from_oracle, make_scores_unique, small_cfg
+from ultralytics_pro_b200.synth import CONFIGS, make_head_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _to(dev, levels, ang=None):
+    return [lv.to(dev) for lv in levels], (ang.to(dev) if ang is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch", [("c1_v8n_640_b1", 1), ("c2_v8x_640_b64", 3), ("c4_p6_1280_b16", 2)])
+def test_decode_dense_fp32(cuda_device, name, batch):
+    from ultralytics_pro_b200.head import decode_head
+
+    cfg = CONFIGS[name]
+    levels, _ = make_head_batch(cfg, batch=batch, seed=11)
+    want = decode_oracle(levels, cfg.strides, cfg.nc)
+    got = decode_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc).cpu()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    tol = 1e-5 * want.abs() + 1e-5 * cfg.imgsz
+    bad = (got - want).abs() > tol
+    assert not bool(bad[:, :4].any()), f"box mismatch max {float((got - want)[:, :4].abs().max())}"
+    # scores and w/h are well conditioned: pure relative bound
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-30))
+    assert float(rel[:, 4:].max()) < 1e-5, f"score rel err {float(rel[:, 4:].max())}"
+    assert float(rel[:, 2:4].max()) < 1e-5, f"wh rel err {float(rel[:, 2:4].max())}"
+
+
+def test_decode_dense_xyxy(cuda_device):
+    from ultralytics_pro_b200.head import decode_head
+
+    cfg = small_cfg(batch=2)
+    levels, _ = make_head_batch(cfg, seed=5)
+    want = decode_oracle(levels, cfg.strides, cfg.nc, xyxy=True)
+    got = decode_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc, xyxy=True).cpu()
+    assert float((got - want).abs().max()) <= 1e-5 * cfg.imgsz
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_decode_dense_half(cuda_device, dtype):
+    from ultralytics_pro_b200.head import decode_head
+
+    cfg = CONFIGS["c2_v8x_640_b64"]
+    levels, _ = make_head_batch(cfg, batch=2, seed=13, dtype=dtype)
+    got = decode_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc).cpu()
+    assert got.dtype == dtype
+    exact = decode_oracle([lv.float() for lv in levels], cfg.strides, cfg.nc)  # fp32 math on the same (rounded) inputs
+    ref = decode_oracle(levels, cfg.strides, cfg.nc).float()                   # the reference's own low-precision chain
+    tol = 1e-2 * exact.abs() + 1e-2
+    err_ours = (got.float() - exact).abs()
+    assert not bool((err_ours > tol).any()), f"max err {float(err_ours.max())}"
+    # never worse than the reference's own per-op-rounded chain, in aggregate
+    assert float(err_ours.mean()) <= float((ref - exact).abs().mean()) * 1.05 + 1e-6
+
+
+def test_decode_obb(cuda_device):
+    from ultralytics_pro_b200.head import decode_head
+
+    cfg = CONFIGS["c5_obb_1024_b16"]
+    levels, ang = make_head_batch(cfg, batch=2, seed=17)
+    want = obb_forward_oracle(levels, ang, cfg.strides, cfg.nc)
+    dl, da = _to(cuda_device, levels, ang)
+    got = decode_head(dl, cfg.strides, cfg.nc, angle=da, angle_is_logit=True, append_angle=True).cpu()
+    assert got.shape == want.shape
+    tol = 1e-5 * want.abs() + 1e-5 * cfg.imgsz
+    assert not bool(((got - want).abs() > tol).any()), f"max {float((got - want).abs().max())}"
+
+
+def test_decode_scalar_path_odd_grid(cuda_device):
+    """Level sizes that are not multiples of the vector width take the VEC=1 kernel."""
+    from ultralytics_pro_b200.head import decode_head
+
+    torch.manual_seed(3)
+    nc = 7
+    levels = [torch.randn(2, 64 + nc, 9, 7), torch.randn(2, 64 + nc, 5, 3)]
+    want = decode_oracle(levels, (8, 16), nc)
+    got = decode_head(_to(cuda_device, levels)[0], (8, 16), nc).cpu()
+    assert float((got - want).abs().max()) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# non_max_suppression on the same decoded tensor: bit-exact
+# ------------------------------------------------------------------------------------------------------------------
+CASES = [
+    # name, batch, overrides
+    ("c2_v8x_640_b64", 4, {}),
+    ("c2_v8x_640_b64", 2, {"agnostic": True}),
+    ("c2_v8x_640_b64", 2, {"classes": [0, 3, 17, 42, 79]}),
+    ("c2_v8x_640_b64", 2, {"max_det": 20}),
+    ("c2_v8x_640_b64", 2, {"conf": 0.05, "iou": 0.45}),
+    ("c4_p6_1280_b16", 2, {}),
+    ("c4_p6_1280_b16", 2, {"agnostic": True}),
+    ("c3_val_stress_b32", 2, {}),
+    ("c3_val_stress_b32", 1, {"max_nms": 5000}),
+]
+
+
+@pytest.mark.parametrize("name,batch,over", CASES)
+def test_nms_from_dense_bitexact(cuda_device, name, batch, over):
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    cfg = CONFIGS[name]
+    _, _, y = dense_from_oracle(cfg, batch, seed=21)
+    kw = dict(conf=cfg.conf, iou=cfg.iou, multi_label=cfg.multi_label, agnostic=cfg.agnostic, max_det=cfg.max_det,
+              max_nms=cfg.max_nms, classes=None)
+    kw.update(over)
+    if kw["max_nms"] < 30000:
+        y = make_scores_unique(y, cfg.nc, kw["conf"])
+    want, want_idx = nms_oracle(y, kw["conf"], kw["iou"], classes=kw["classes"], agnostic=kw["agnostic"],
+                                multi_label=kw["multi_label"], max_det=kw["max_det"], nc=cfg.nc, max_nms=kw["max_nms"])
+    got, got_idx = non_max_suppression(y.to(cuda_device), kw["conf"], kw["iou"], classes=kw["classes"],
+                                       agnostic=kw["agnostic"], multi_label=kw["multi_label"], max_det=kw["max_det"],
+                                       nc=cfg.nc, max_nms=kw["max_nms"], return_idxs=True)
+    assert sum(w.shape[0] for w in want) > 0
+    assert_rows_equal(got, got_idx, want, want_idx, f"{name} {over}")
+
+
+def test_nms_rotated_matches_oracle(cuda_device):
+    """ProbIoU goes through cos/sin/log/exp whose last ulp differs between libm (CPU) and CUDA: kept sets must match
+    except for pairs within 1e-6 of the threshold; here we demand equality and report the margin."""
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    cfg = CONFIGS["c5_obb_1024_b16"]
+    _, _, y = dense_from_oracle(cfg, 3, seed=23)
+    y = make_scores_unique(y, cfg.nc, cfg.conf)
+    want, want_idx = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc, rotated=True)
+    got, got_idx = non_max_suppression(y.to(cuda_device), cfg.conf, cfg.iou, nc=cfg.nc, rotated=True, return_idxs=True)
+    assert_rows_equal(got, got_idx, want, want_idx, "obb")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_nms_from_dense_half_inputs(cuda_device, dtype):
+    """Low-precision predictions: threshold cast, in-dtype xywh->xyxy and fp32 promotion of the rows (nms.py:76,86,116)."""
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    cfg = CONFIGS["c2_v8x_640_b64"]
+    _, _, y = dense_from_oracle(cfg, 2, seed=29)
+    y = y.to(dtype)
+    want, want_idx = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc)
+    got, got_idx = non_max_suppression(y.to(cuda_device), cfg.conf, cfg.iou, nc=cfg.nc, return_idxs=True)
+    assert got[0].dtype == torch.float32
+    assert_rows_equal(got, got_idx, want, want_idx, str(dtype))
+
+
+def test_nms_extras_and_noncontiguous(cuda_device):
+    """Mask-coefficient style extras ride through (nms.py:74,112) and permuted inputs work (models/nas/predict.py:54)."""
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    cfg = small_cfg(imgsz=320, batch=3)
+    _, _, y = dense_from_oracle(cfg, 3, seed=31)
+    torch.manual_seed(1)
+    y = torch.cat((y, torch.randn(3, 32, y.shape[2])), 1)
+    want, want_idx = nms_oracle(y, 0.25, 0.7, nc=cfg.nc)
+    yd = y.to(cuda_device).permute(0, 2, 1).contiguous().permute(0, 2, 1)  # (B, C, A) view with stride_a = C
+    assert not yd.is_contiguous()
+    got, got_idx = non_max_suppression(yd, 0.25, 0.7, nc=cfg.nc, return_idxs=True)
+    assert got[0].shape[1] == 6 + 32
+    assert_rows_equal(got, got_idx, want, want_idx, "extras")
+
+
+def test_nms_empty_and_edge(cuda_device):
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    y = torch.zeros(2, 84, 64, device=cuda_device)
+    out, idx = non_max_suppression(y, 0.25, 0.7, return_idxs=True)
+    assert [o.shape for o in out] == [(0, 6), (0, 6)] and all(i.numel() == 0 for i in idx)
+    # one image empty, one with a single box; tuple input accepted (nms.py:61)
+    y[1, :4, 5] = torch.tensor([50.0, 60.0, 20.0, 10.0], device=cuda_device)
+    y[1, 4 + 3, 5] = 0.9
+    out = non_max_suppression((y, None), 0.25, 0.7)
+    assert out[0].shape == (0, 6) and out[1].shape == (1, 6)
+    assert out[1][0].tolist() == [40.0, 55.0, 60.0, 65.0, pytest.approx(0.9), 3.0]
+    with pytest.raises(AssertionError):
+        non_max_suppression(y, 1.5, 0.7)
+    with pytest.raises(RuntimeError):
+        non_max_suppression(y.cpu(), 0.25, 0.7)
+
+
+def test_nms_iou_equal_threshold_and_degenerate(cuda_device):
+    """IoU == thr keeps both (strict >, nms.py:292-294); zero-area duplicates are both kept (0/0 = NaN); thr=0.6 hits the
+    float-vs-double threshold corner (torchvision CPU suppresses IoU == float32(0.6))."""
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    def run(boxes_xyxy, scores, thr):
+        n = len(scores)
+        y = torch.zeros(1, 5, n)
+        b = torch.tensor(boxes_xyxy, dtype=torch.float32)
+        y[0, 0], y[0, 1] = (b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2
+        y[0, 2], y[0, 3] = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+        y[0, 4] = torch.tensor(scores)
+        want, _ = nms_oracle(y, 0.1, thr, nc=1)
+        got = non_max_suppression(y.to(cuda_device), 0.1, thr, nc=1)
+        assert_rows_equal(got, None, want, None, f"thr={thr}")
+        return got[0].shape[0]
+
+    assert run([[0, 0, 2, 2], [0, 0, 2, 1]], [0.9, 0.8], 0.5) == 2
+    assert run([[1, 1, 1, 1], [1, 1, 1, 1]], [0.9, 0.8], 0.5) == 2
+    assert run([[0, 0, 10, 10], [0, 0, 10, 6]], [0.9, 0.8], 0.6) == 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused path == dense decode followed by NMS, bit for bit
+# ------------------------------------------------------------------------------------------------------------------
+FUSED = [
+    ("c2_v8x_640_b64", 4, torch.float32),
+    ("c2_v8x_640_b64", 2, torch.bfloat16),
+    ("c2_v8x_640_b64", 2, torch.float16),
+    ("c3_val_stress_b32", 2, torch.float32),
+    ("c4_p6_1280_b16", 2, torch.float32),
+    ("c5_obb_1024_b16", 2, torch.float32),
+]
+
+
+@pytest.mark.parametrize("name,batch,dtype", FUSED)
+def test_fused_equals_two_call(cuda_device, name, batch, dtype):
+    from ultralytics_pro_b200.head import decode_head, postprocess_from_head
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    cfg = CONFIGS[name]
+    levels, ang = make_head_batch(cfg, batch=batch, seed=37, dtype=dtype)
+    dl, da = _to(cuda_device, levels, ang)
+    if cfg.rotated:
+        y = decode_head(dl, cfg.strides, cfg.nc, angle=da, angle_is_logit=True, append_angle=True)
+    else:
+        y = decode_head(dl, cfg.strides, cfg.nc)
+    two, two_idx = non_max_suppression(y, cfg.conf, cfg.iou, nc=cfg.nc, multi_label=cfg.multi_label,
+                                       rotated=cfg.rotated, return_idxs=True)
+    one, one_idx = postprocess_from_head(dl, cfg.strides, cfg.nc, cfg.conf, cfg.iou, multi_label=cfg.multi_label,
+                                         angle_logits=da, return_idxs=True)
+    assert sum(t.shape[0] for t in two) > 0
+    assert_rows_equal(one, one_idx, [t.cpu() for t in two], [t.cpu() for t in two_idx], f"fused {name} {dtype}")
+
+
+def test_fused_against_oracle_end_to_end(cuda_device):
+    """decode+NMS against the oracle's decode+NMS: kept anchors identical on tie-free, margin-free data; values within
+    the decode tolerance."""
+    from ultralytics_pro_b200.head import postprocess_from_head
+
+    cfg = CONFIGS["c2_v8x_640_b64"]
+    levels, _ = make_head_batch(cfg, batch=4, seed=41)
+    y = decode_oracle(levels, cfg.strides, cfg.nc)
+    want, want_idx = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc)
+    got, got_idx = postprocess_from_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc, cfg.conf, cfg.iou, return_idxs=True)
+    same = 0
+    for b in range(4):
+        gi, wi = got_idx[b].cpu(), want_idx[b]
+        if gi.shape == wi.shape and torch.equal(gi, wi):
+            same += 1
+            assert float((got[b].cpu() - want[b]).abs().max()) <= 1e-5 * cfg.imgsz + 1e-5 * float(want[b].abs().max())
+    assert same >= 3, "kept sets diverge beyond borderline effects"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TorchNMS mirror, self tests
+# ------------------------------------------------------------------------------------------------------------------
+def test_torchnms_mirror(cuda_device):
+    from oracle.postproc_oracle import fast_nms, greedy_nms
+    from ultralytics_pro_b200.nms import TorchNMS, batch_probiou, box_iou
+
+    torch.manual_seed(7)
+    n = 700
+    xy = torch.rand(n, 2) * 300
+    wh = torch.rand(n, 2) * 80 + 4
+    boxes = torch.cat((xy, xy + wh), 1)
+    scores = torch.rand(n)
+    want = greedy_nms(boxes, scores, 0.5, "plain")
+    got = TorchNMS.nms(boxes.to(cuda_device), scores.to(cuda_device), 0.5).cpu()
+    assert torch.equal(got, want)
+    want = fast_nms(boxes, scores, 0.5, "boxiou")
+    got = TorchNMS.fast_nms(boxes.to(cuda_device), scores.to(cuda_device), 0.5, iou_func=box_iou).cpu()
+    assert torch.equal(got, want)
+    obb = torch.cat((xy, wh, (torch.rand(n, 1) - 0.25) * 3.14159), 1)
+    want = fast_nms(obb, scores, 0.3, "probiou")
+    got = TorchNMS.fast_nms(obb.to(cuda_device), scores.to(cuda_device), 0.3, iou_func=batch_probiou).cpu()
+    assert torch.equal(got, want)
+    idxs = torch.randint(0, 5, (n,))
+    got = TorchNMS.batched_nms(boxes.to(cuda_device), scores.to(cuda_device), idxs.to(cuda_device), 0.5).cpu()
+    off = idxs.to(boxes) * (boxes.max() + 1)
+    want = greedy_nms(boxes + off[:, None], scores, 0.5, "plain")
+    assert torch.equal(got, want)
+    # large n: radix-sort + multi-chunk path
+    n = 9000
+    xy = torch.rand(n, 2) * 2000
+    wh = torch.rand(n, 2) * 60 + 4
+    boxes = torch.cat((xy, xy + wh), 1)
+    scores = torch.rand(n)
+    want = greedy_nms(boxes, scores, 0.5, "torchvision")
+    got = TorchNMS.nms(boxes.to(cuda_device), scores.to(cuda_device), 0.5).cpu()
+    assert torch.equal(got, want)
+    assert TorchNMS.nms(torch.zeros(0, 4, device=cuda_device), torch.zeros(0, device=cuda_device), 0.5).numel() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_sigmoid_monotone_selftest(cuda_device, dtype):
+    """The single-label fast filter relies on round_T(sigmoid(x)) being monotone: checked over all 2^32 inputs."""
+    from ultralytics_pro_b200 import _cabi
+
+    lib = _cabi.load()
+    v = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    _cabi.check(lib.ypb_selftest_sigmoid_monotone(_cabi.dtype_code(dtype), v.data_ptr(), _cabi.stream_ptr(cuda_device)), "selftest")
+    assert int(v.item()) == 0

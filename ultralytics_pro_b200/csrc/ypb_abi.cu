@@ -1,0 +1,250 @@
+// extern "C" surface of libyolopost_b200 (declared in include/yolopost_b200.h): argument validation, geometry,
+// workspace carve-up and kernel sequencing.  Nothing here allocates, frees or synchronises.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ypb_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  return fail(YPB_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+
+size_t dtype_size(int dt) { return dt == YPB_F32 ? 4 : 2; }
+bool dtype_ok(int dt) { return dt == YPB_F32 || dt == YPB_F16 || dt == YPB_BF16; }
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Validates the head and fills the device-side geometry.  `vec` = anchors per thread (widest that every level,
+// stride and pointer allows: 16-byte accesses, else scalar).
+int build_geom(const ypb_head_desc* h, ypb::HeadGeom* g, int* vec_out, const void* extra_ptr_a, const void* extra_ptr_b,
+               long long extra_stride_a, long long extra_stride_b) {
+  if (!h) return fail(YPB_ERR_INVALID_ARGUMENT, "head descriptor is NULL");
+  if (h->num_levels < 1 || h->num_levels > YPB_MAX_LEVELS)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "num_levels=%d outside [1,%d]", h->num_levels, YPB_MAX_LEVELS);
+  if (h->batch < 0 || h->nc < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d nc=%d invalid", h->batch, h->nc);
+  if (!dtype_ok(h->dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", h->dtype);
+  if (h->reg_max != 16)
+    return fail(YPB_ERR_UNSUPPORTED, "reg_max=%d: only 16 is built (every head in the reference bundle, head.py:89)", h->reg_max);
+  const int wide = 16 / static_cast<int>(dtype_size(h->dtype));
+  int vec = wide;
+  long long anchors = 0;
+  for (int l = 0; l < h->num_levels; ++l) {
+    if (!h->level_ptr[l] && h->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "level %d pointer is NULL", l);
+    if (h->level_h[l] < 1 || h->level_w[l] < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "level %d has empty grid", l);
+    const long long hw = static_cast<long long>(h->level_h[l]) * h->level_w[l];
+    if (h->level_channel_stride[l] < hw) return fail(YPB_ERR_INVALID_ARGUMENT, "level %d channel stride < H*W", l);
+    anchors += hw;
+    if (hw % wide || h->level_channel_stride[l] % wide || h->level_batch_stride[l] % wide || !aligned(h->level_ptr[l], 16))
+      vec = 1;
+  }
+  if (anchors > 0x7fffffffLL / (h->nc > 1 ? h->nc : 1))
+    return fail(YPB_ERR_UNSUPPORTED, "anchors*nc does not fit the 31-bit row id");
+  if (extra_ptr_a && !aligned(extra_ptr_a, 16)) vec = 1;
+  if (extra_ptr_b && !aligned(extra_ptr_b, 16)) vec = 1;
+  if (extra_stride_a % wide || extra_stride_b % wide) vec = 1;
+  std::memset(g, 0, sizeof(*g));
+  g->num_levels = h->num_levels;
+  g->batch = h->batch;
+  g->nc = h->nc;
+  g->reg_max = h->reg_max;
+  int as = 0, gs = 0;
+  for (int l = 0; l < h->num_levels; ++l) {
+    g->ptr[l] = h->level_ptr[l];
+    g->h[l] = h->level_h[l];
+    g->w[l] = h->level_w[l];
+    g->bstride[l] = h->level_batch_stride[l];
+    g->cstride[l] = h->level_channel_stride[l];
+    g->stride[l] = h->level_stride[l];
+    g->anchor_start[l] = as;
+    g->group_start[l] = gs;
+    as += h->level_h[l] * h->level_w[l];
+    gs += h->level_h[l] * h->level_w[l] / vec;
+  }
+  for (int l = h->num_levels; l <= YPB_MAX_LEVELS; ++l) {
+    g->anchor_start[l] = as;
+    g->group_start[l] = gs;
+  }
+  g->anchors = as;
+  *vec_out = vec;
+  return YPB_OK;
+}
+
+int check_params(const ypb_nms_params* p, const ypb_nms_out* out) {
+  if (!p || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "params/out is NULL");
+  if (p->nc < 1 || p->extra < 0 || p->max_det < 1 || p->max_nms < 1 || p->rows_cap < 1)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "nc=%d extra=%d max_det=%d max_nms=%d rows_cap=%d invalid", p->nc, p->extra,
+                p->max_det, p->max_nms, p->rows_cap);
+  if (p->rule < YPB_NMS_GREEDY || p->rule > YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown rule %d", p->rule);
+  if (!(p->conf_thres >= 0.f) || !(p->iou_thres_eff >= 0.f) || p->iou_thres_eff > 1.f)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "conf/iou threshold outside [0,1] (nms.py:59-60)");
+  if (!out->rows || !out->count) return fail(YPB_ERR_INVALID_ARGUMENT, "out.rows / out.count is NULL");
+  return YPB_OK;
+}
+
+ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out, const ypb::Workspace& w, int batch,
+                                int anchors) {
+  ypb::SuppressArgs s{};
+  s.batch = batch; s.anchors = anchors; s.nc = p->nc; s.extra = p->extra; s.max_det = p->max_det; s.max_nms = p->max_nms;
+  s.rule = p->rule; s.rows_cap = p->rows_cap; s.multi_label = p->multi_label;
+  s.iou_thr = p->iou_thres_eff; s.max_wh = p->max_wh;
+  s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
+  s.cand_ang = p->rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
+  s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
+  s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_cand = out->cand_count;
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ypb_abi_version(void) { return YPB_ABI_VERSION; }
+
+const char* ypb_last_error_string(void) { return g_err; }
+
+size_t ypb_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t rows_cap, int32_t max_det, int32_t max_nms,
+                               int32_t rule) {
+  if (batch < 0 || anchors < 0 || rows_cap < 0 || max_det < 0 || max_nms < 0) return 0;
+  return ypb::carve_workspace(nullptr, batch, anchors, rows_cap, max_det, max_nms, rule).bytes + 256;
+}
+
+int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t append_angle,
+                     int32_t xyxy, void* out, int32_t out_dtype, int64_t out_stride_b, int64_t out_stride_c,
+                     void* stream) {
+  ypb::HeadGeom g;
+  int vec;
+  int rc = build_geom(head, &g, &vec, angle, out, out_stride_b, out_stride_c);
+  if (rc) return rc;
+  if (!out) return fail(YPB_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (out_dtype != head->dtype)
+    return fail(YPB_ERR_UNSUPPORTED, "out dtype %d != head dtype %d (Detect._inference keeps the dtype, head.py:169)", out_dtype, head->dtype);
+  if (out_stride_c < g.anchors) return fail(YPB_ERR_INVALID_ARGUMENT, "out channel stride < anchors");
+  if (head->batch == 0) return YPB_OK;
+  cudaError_t e = ypb::launch_decode_dense(g, head->dtype, angle, angle_is_logit, append_angle, xyxy, out, out_dtype,
+                                           out_stride_b, out_stride_c, vec, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_decode_dense");
+  return YPB_OK;
+}
+
+int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
+                      const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  ypb::HeadGeom g;
+  int vec;
+  int rc = build_geom(head, &g, &vec, nullptr, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = check_params(p, out);
+  if (rc) return rc;
+  if (p->nc != head->nc) return fail(YPB_ERR_INVALID_ARGUMENT, "params.nc=%d != head.nc=%d", p->nc, head->nc);
+  if (value_dtype != head->dtype) return fail(YPB_ERR_UNSUPPORTED, "value dtype must equal the head dtype");
+  const bool rotated = p->rule == YPB_NMS_FAST_PROBIOU;
+  if (rotated && !angle) return fail(YPB_ERR_INVALID_ARGUMENT, "rotated rule needs the angle channel");
+  if (!rotated && angle) return fail(YPB_ERR_INVALID_ARGUMENT, "angle given but rule is not FAST_PROBIOU");
+  if (p->extra != (rotated ? 1 : 0)) return fail(YPB_ERR_INVALID_ARGUMENT, "fused path carries extra=%d only", rotated ? 1 : 0);
+  if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
+  ypb::Workspace w = ypb::carve_workspace(workspace, head->batch, g.anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
+  if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
+    return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
+  if (head->batch == 0) return YPB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * head->batch, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+  ypb::FilterArgs f{};
+  f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
+  f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+  e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, st);
+  if (e != cudaSuccess) return cuda_fail(e, "filter_from_head");
+  ypb::SuppressArgs s = suppress_args(p, out, w, head->batch, g.anchors);
+  e = ypb::launch_sort_suppress(s, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  return YPB_OK;
+}
+
+int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, const ypb_nms_out* out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!pred) return fail(YPB_ERR_INVALID_ARGUMENT, "prediction descriptor is NULL");
+  int rc = check_params(p, out);
+  if (rc) return rc;
+  if (!dtype_ok(pred->dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", pred->dtype);
+  if (pred->batch < 0 || pred->anchors < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d anchors=%d invalid", pred->batch, pred->anchors);
+  if (pred->channels != 4 + p->nc + p->extra)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "channels=%d != 4+nc+extra=%d (nms.py:73-75)", pred->channels, 4 + p->nc + p->extra);
+  if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
+  const bool rotated = p->rule == YPB_NMS_FAST_PROBIOU;
+  if (rotated && p->extra < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "rotated rule needs the angle as last channel (nms.py:146)");
+  if (static_cast<long long>(pred->anchors) > 0x7fffffffLL / p->nc)
+    return fail(YPB_ERR_UNSUPPORTED, "anchors*nc does not fit the 31-bit row id");
+  if (!pred->ptr && pred->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "prediction pointer is NULL");
+  ypb::Workspace w = ypb::carve_workspace(workspace, pred->batch, pred->anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
+  if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
+    return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
+  if (pred->batch == 0) return YPB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * pred->batch, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+  ypb::FilterArgs f{};
+  f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
+  f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+  e = ypb::launch_filter_from_dense(*pred, f, st);
+  if (e != cudaSuccess) return cuda_fail(e, "filter_from_dense");
+  ypb::SuppressArgs s = suppress_args(p, out, w, pred->batch, pred->anchors);
+  s.pred = pred->ptr; s.pred_dtype = pred->dtype; s.pred_sb = pred->stride_b; s.pred_sc = pred->stride_c; s.pred_sa = pred->stride_a;
+  e = ypb::launch_sort_suppress(s, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  return YPB_OK;
+}
+
+size_t ypb_nms_boxes_workspace_bytes(int32_t n) {
+  if (n < 0) return 0;
+  const int m = n > 0 ? n : 1;
+  return ypb::carve_workspace(nullptr, 1, m, m, m, m, YPB_NMS_FAST_PROBIOU).bytes + 256;
+}
+
+int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t box_dim, int32_t rule,
+                  float iou_thres_eff, int64_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (n < 0 || (box_dim != 4 && box_dim != 5)) return fail(YPB_ERR_INVALID_ARGUMENT, "n=%d box_dim=%d invalid", n, box_dim);
+  if (rule < YPB_NMS_GREEDY || rule > YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown rule %d", rule);
+  if ((rule == YPB_NMS_FAST_PROBIOU) != (box_dim == 5)) return fail(YPB_ERR_INVALID_ARGUMENT, "box_dim 5 <=> FAST_PROBIOU");
+  if (!keep || !keep_count) return fail(YPB_ERR_INVALID_ARGUMENT, "keep / keep_count is NULL");
+  if (n > 0 && (!boxes || !scores)) return fail(YPB_ERR_INVALID_ARGUMENT, "boxes / scores is NULL");
+  const int m = n > 0 ? n : 1;
+  ypb::Workspace w = ypb::carve_workspace(workspace, 1, m, m, m, m, YPB_NMS_FAST_PROBIOU);
+  if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
+    return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = ypb::launch_boxes_prep(boxes, scores, n, box_dim, w.keys_a, w.cand_box, w.cand_ang, w.row_count, st);
+  if (e != cudaSuccess) return cuda_fail(e, "boxes_prep");
+  ypb::SuppressArgs s{};
+  s.batch = 1; s.anchors = m; s.nc = 1; s.extra = 0; s.max_det = m; s.max_nms = m; s.rule = rule; s.rows_cap = m;
+  s.iou_thr = iou_thres_eff; s.max_wh = 0.f;
+  s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
+  s.cand_ang = rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
+  s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
+  s.out_rows = nullptr; s.out_idx = reinterpret_cast<long long*>(keep); s.out_count = keep_count; s.idx_as_row = 1;
+  e = ypb::launch_sort_suppress(s, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  return YPB_OK;
+}
+
+int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream) {
+  if (!violations || !dtype_ok(dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "bad arguments");
+  cudaError_t e = ypb::launch_sigmoid_selftest(dtype, violations, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "sigmoid selftest");
+  return YPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// Shared device helpers and the internal launch interface of libyolopost_b200.
+// sm_100a only; no CPU path.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/yolopost_b200.h"
+
+namespace ypb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// dtype traits: storage type, widening to fp32 and "round an fp32 value through the storage type" (what a torch op
+// on a T tensor does to its fp32 opmath result).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT> struct DType;
+template <> struct DType<YPB_F32> {
+  using type = float;
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }
+};
+template <> struct DType<YPB_F16> {
+  using type = __half;
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+};
+template <> struct DType<YPB_BF16> {
+  using type = __nv_bfloat16;
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+
+// A VEC-wide, naturally aligned group of T moved with one LDG/STG (128-bit for fp32 x4 / 16-bit x8).
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> load_pack(const T* p) {
+  // streaming read-once data: bypass L1 allocation so the class/box rows do not evict each other
+  if constexpr (sizeof(T) * VEC == 16) {
+    Pack<T, VEC> r;
+    int4 raw = __ldcs(reinterpret_cast<const int4*>(p));
+    *reinterpret_cast<int4*>(&r) = raw;
+    return r;
+  } else if constexpr (sizeof(T) * VEC == 8) {
+    Pack<T, VEC> r;
+    int2 raw = __ldcs(reinterpret_cast<const int2*>(p));
+    *reinterpret_cast<int2*>(&r) = raw;
+    return r;
+  } else if constexpr (sizeof(T) * VEC == 4) {
+    Pack<T, VEC> r;
+    int raw = __ldcs(reinterpret_cast<const int*>(p));
+    *reinterpret_cast<int*>(&r) = raw;
+    return r;
+  } else {
+    Pack<T, VEC> r;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = p[i];
+    return r;
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& r) {
+  if constexpr (sizeof(T) * VEC == 16) {
+    __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(&r));
+  } else if constexpr (sizeof(T) * VEC == 8) {
+    __stcs(reinterpret_cast<int2*>(p), *reinterpret_cast<const int2*>(&r));
+  } else if constexpr (sizeof(T) * VEC == 4) {
+    __stcs(reinterpret_cast<int*>(p), *reinterpret_cast<const int*>(&r));
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// math of the decode (head.py:151-169, block.py:250-253, tal.py:367-403), fp32 opmath.
+// The SAME functions are used by the dense kernel and by the fused filter so the two agree bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// torch max semantics: NaN is sticky.
+__device__ __forceinline__ float nanmax(float m, float v) { return (v > m || v != v) ? v : m; }
+
+// Expectation of the softmax over REG bins (DFL).  v[k] = logit of bin k.
+template <int REG>
+__device__ __forceinline__ float dfl_expect(const float (&v)[REG]) {
+  float m = v[0];
+#pragma unroll
+  for (int k = 1; k < REG; ++k) m = fmaxf(m, v[k]);
+  float den = 0.f, num = 0.f;
+#pragma unroll
+  for (int k = 0; k < REG; ++k) {
+    float e = __expf(v[k] - m);
+    den += e;
+    num = fmaf(static_cast<float>(k), e, num);
+  }
+  return __fdividef(num, den);
+}
+
+struct BoxXYWH { float cx, cy, w, h; };
+
+// tal.py:367-376 (dist2bbox, xywh) then head.py:168 (x stride).  ax, ay: anchor centre in grid units.
+__device__ __forceinline__ BoxXYWH decode_axis_aligned(float dl, float dt, float dr, float db, float ax, float ay,
+                                                       float stride, bool xyxy) {
+  float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;
+  BoxXYWH o;
+  if (xyxy) {
+    o.cx = x1 * stride; o.cy = y1 * stride; o.w = x2 * stride; o.h = y2 * stride;
+  } else {
+    o.cx = (x1 + x2) * 0.5f * stride; o.cy = (y1 + y2) * 0.5f * stride;
+    o.w = (x2 - x1) * stride; o.h = (y2 - y1) * stride;
+  }
+  return o;
+}
+
+// tal.py:385-403 (dist2rbox) then head.py:168.
+__device__ __forceinline__ BoxXYWH decode_rotated(float dl, float dt, float dr, float db, float theta, float ax,
+                                                  float ay, float stride) {
+  float s, c;
+  sincosf(theta, &s, &c);
+  float xf = (dr - dl) * 0.5f, yf = (db - dt) * 0.5f;
+  BoxXYWH o;
+  // explicit _rn intrinsics: no FMA contraction, so every inlining context rounds identically
+  o.cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(xf, c), __fmul_rn(yf, s)), ax), stride);
+  o.cy = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf, s), __fmul_rn(yf, c)), ay), stride);
+  o.w = (dl + dr) * stride;
+  o.h = (dt + db) * stride;
+  return o;
+}
+
+// head.py:1031: (sigmoid(t) - 0.25) * pi
+__device__ __forceinline__ float activate_angle(float t) { return (sigmoid_f(t) - 0.25f) * 3.14159265358979323846f; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// sort keys: 64-bit, unique per image.  hi = ~orderable(score), lo = row id (anchor * nc + cls), so an ascending
+// sort is "score descending, then lower row first" == torchvision's stable descending sort (Ties).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t orderable_bits(float f) {
+  if (f == 0.0f) f = 0.0f;  // -0 -> +0
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable_bits(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return (static_cast<uint64_t>(~orderable_bits(score)) << 32) | row;
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return from_orderable_bits(~static_cast<uint32_t>(k >> 32)); }
+__device__ __forceinline__ uint32_t key_row(uint64_t k) { return static_cast<uint32_t>(k); }
+constexpr uint64_t KEY_SENTINEL = ~0ull;
+
+// ---------------------------------------------------------------------------------------------------------------
+// workspace carve-up (all offsets 256-byte aligned)
+// ---------------------------------------------------------------------------------------------------------------
+struct Workspace {
+  int32_t* row_count;  // [B]            rows emitted by the filter (atomic)
+  uint64_t* keys_a;    // [B][rows_cap]
+  uint64_t* keys_b;    // [B][rows_cap]  radix ping-pong
+  float4* cand_box;    // [B][A]         box of each candidate anchor (xyxy, or xywh when rotated), un-offset
+  float* cand_ang;     // [B][A]         angle of each candidate anchor (rotated only)
+  float4* kept_box;    // [B][max_det]   class-offset boxes of rows already kept (greedy rule)
+  float* kept_area;    // [B][max_det]
+  uint64_t* kept_key;  // [B][max_det]
+  float* rec;          // [B][min(rows_cap,max_nms)][8]  per-rank records (fast rules only)
+  size_t bytes;
+};
+
+__host__ inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+__host__ inline Workspace carve_workspace(void* base, int batch, int anchors, int rows_cap, int max_det, int max_nms,
+                                          int rule) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  size_t B = static_cast<size_t>(batch);
+  w.row_count = reinterpret_cast<int32_t*>(take(B * sizeof(int32_t)));
+  w.keys_a = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
+  w.keys_b = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
+  w.cand_box = reinterpret_cast<float4*>(take(B * anchors * sizeof(float4)));
+  w.cand_ang = reinterpret_cast<float*>(take(B * anchors * sizeof(float)));
+  w.kept_box = reinterpret_cast<float4*>(take(B * max_det * sizeof(float4)));
+  w.kept_area = reinterpret_cast<float*>(take(B * max_det * sizeof(float)));
+  w.kept_key = reinterpret_cast<uint64_t*>(take(B * max_det * sizeof(uint64_t)));
+  size_t m = static_cast<size_t>(rows_cap < max_nms ? rows_cap : max_nms);
+  w.rec = reinterpret_cast<float*>(take(rule == YPB_NMS_GREEDY ? 0 : B * m * 8 * sizeof(float)));
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// internal launch interface (defined in ypb_decode.cu / ypb_nms.cu, called from ypb_abi.cu)
+// ---------------------------------------------------------------------------------------------------------------
+struct HeadGeom {  // device-side view of ypb_head_desc, passed by value
+  int num_levels, batch, nc, reg_max;
+  const void* ptr[YPB_MAX_LEVELS];
+  int h[YPB_MAX_LEVELS], w[YPB_MAX_LEVELS];
+  long long bstride[YPB_MAX_LEVELS], cstride[YPB_MAX_LEVELS];
+  float stride[YPB_MAX_LEVELS];
+  int anchor_start[YPB_MAX_LEVELS + 1];  // prefix of H*W
+  int group_start[YPB_MAX_LEVELS + 1];   // prefix of H*W/VEC
+  int anchors;
+};
+
+struct FilterArgs {
+  float conf;
+  int nc, multi_label, rotated, rows_cap;
+  const uint32_t* class_mask;
+  int32_t* row_count;
+  uint64_t* keys;
+  float4* cand_box;
+  float* cand_ang;
+};
+
+struct SuppressArgs {
+  int batch, anchors, nc, extra, max_det, max_nms, rule, rows_cap, multi_label;
+  float iou_thr, max_wh;
+  int32_t* row_count;
+  uint64_t* keys_a;
+  uint64_t* keys_b;
+  const float4* cand_box;
+  const float* cand_ang;
+  float4* kept_box;
+  float* kept_area;
+  uint64_t* kept_key;
+  float* rec;
+  // extras gather source (dense path) - may be null
+  const void* pred;
+  int pred_dtype;
+  long long pred_sb, pred_sc, pred_sa;
+  // outputs
+  float* out_rows;
+  long long* out_idx;
+  int32_t* out_count;
+  int32_t* out_cand;
+  int idx_as_row;  // ypb_nms_boxes: write the row id itself
+};
+
+cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
+                                int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
+                                int vec, cudaStream_t st);
+cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_dtype, const void* angle,
+                                    int angle_is_logit, const FilterArgs& f, int vec, cudaStream_t st);
+cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st);
+cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
+cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,
+                              float4* cand_box, float* cand_ang, int32_t* row_count, cudaStream_t st);
+cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st);
+
+}  // namespace ypb

@@ -1,0 +1,505 @@
+// Decode-side kernels of libyolopost_b200 (sm_100a):
+//   decode_dense_kernel       Detect._inference drop-in (head.py:151-169, OBB head.py:1026-1042)
+//   filter_from_head_kernel   fused decode + confidence filter + compaction (head.py:151-169 + nms.py:76-131)
+//   filter_from_dense_kernel  confidence filter + compaction of an already decoded tensor (nms.py:76-131)
+//
+// Layout facts the mapping is built on: every head level is (B, 4*reg_max+nc, H, W) with the H*W anchors contiguous,
+// so lanes map to ANCHORS (coalesced, 128-bit per lane) and the 16 DFL bins / nc classes of an anchor are walked by
+// the owning thread down the channel stride.  The bins sit on the slow axis, so the softmax is an in-register
+// reduction; warp shuffles are used where lanes really cooperate (the compaction scan).
+#include "ypb_common.cuh"
+
+namespace ypb {
+
+constexpr int DEC_THREADS = 128;
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_level(const HeadGeom& g, int grp) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+    if (i < g.num_levels && grp >= g.group_start[i]) l = i;
+  return l;
+}
+
+__device__ __forceinline__ bool class_allowed(const uint32_t* mask, int c) {
+  return mask == nullptr || ((mask[c >> 5] >> (c & 31)) & 1u);
+}
+
+// Exclusive scan of one int per thread over a DEC_THREADS block; `total` is returned to every thread.
+__device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
+  __shared__ int warp_sum[DEC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sum[warp] = inc;
+  __syncthreads();
+  int before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < DEC_THREADS / 32; ++w) {
+    int s = warp_sum[w];
+    if (w < warp) before += s;
+    tot += s;
+  }
+  total = tot;
+  return before + inc - v;
+}
+
+// Reserve `total` rows of image b for this block; every thread gets the block base.
+__device__ __forceinline__ int reserve_rows(int32_t* row_count, int b, int total) {
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = total > 0 ? atomicAdd(&row_count[b], total) : 0;
+  __syncthreads();
+  return base_s;
+}
+
+// xywh (T-rounded) -> corners in T arithmetic, exactly ops.py:281-283 evaluated on a T tensor.
+template <int DT>
+__device__ __forceinline__ float4 corners_in_dtype(float cx, float cy, float w, float h) {
+  using D = DType<DT>;
+  float hw = D::rnd(w * 0.5f), hh = D::rnd(h * 0.5f);
+  return make_float4(D::rnd(__fsub_rn(cx, hw)), D::rnd(__fsub_rn(cy, hh)), D::rnd(__fadd_rn(cx, hw)),
+                     D::rnd(__fadd_rn(cy, hh)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense decode
+// ---------------------------------------------------------------------------------------------------------------
+enum { MODE_XYWH = 0, MODE_XYXY = 1, MODE_ROT = 2 };
+
+template <int DT_IN, int VEC, int REG>
+__device__ __forceinline__ void load_ltrb(const typename DType<DT_IN>::type* src, long long cs, float (&d)[4][VEC]) {
+  using TI = typename DType<DT_IN>::type;
+#pragma unroll
+  for (int side = 0; side < 4; ++side) {
+    Pack<TI, VEC> raw[REG];
+#pragma unroll
+    for (int k = 0; k < REG; ++k) raw[k] = load_pack<TI, VEC>(src + static_cast<long long>(side * REG + k) * cs);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float v[REG];
+#pragma unroll
+      for (int k = 0; k < REG; ++k) v[k] = DType<DT_IN>::to_f(raw[k].v[i]);
+      d[side][i] = dfl_expect<REG>(v);
+    }
+  }
+}
+
+template <int DT_IN, int DT_OUT, int VEC, int REG, int MODE>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                    int append_angle, void* __restrict__ out_v, long long osb, long long osc) {
+  using TI = typename DType<DT_IN>::type;
+  using TO = typename DType<DT_OUT>::type;
+  const int grp = blockIdx.x * DEC_THREADS + threadIdx.x;
+  const int b = blockIdx.y;
+  if (grp >= g.group_start[g.num_levels]) return;
+  const int l = find_level(g, grp);
+  const int a_local = (grp - g.group_start[l]) * VEC;
+  const int a_glob = g.anchor_start[l] + a_local;
+  const long long cs = g.cstride[l];
+  const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+  TO* out = static_cast<TO*>(out_v) + static_cast<long long>(b) * osb + a_glob;
+  const int nc = g.nc;
+
+  // ---- boxes: DFL expectation per side, then dist2bbox / dist2rbox, x stride -------------------------------------
+  float d[4][VEC];
+  load_ltrb<DT_IN, VEC, REG>(src, cs, d);
+
+  float theta[VEC];
+  if constexpr (MODE == MODE_ROT) {
+    const TI* ang = static_cast<const TI*>(angle_v) + static_cast<long long>(b) * g.anchors + a_glob;
+    Pack<TI, VEC> pa = load_pack<TI, VEC>(ang);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float t = DType<DT_IN>::to_f(pa.v[i]);
+      theta[i] = angle_is_logit ? DType<DT_OUT>::rnd(activate_angle(t)) : t;
+    }
+  }
+
+  const int W = g.w[l];
+  const float stride = g.stride[l];
+  int gy = a_local / W, gx = a_local - gy * W;
+  Pack<TO, VEC> o0, o1, o2, o3;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+    BoxXYWH bx;
+    if constexpr (MODE == MODE_ROT)
+      bx = decode_rotated(d[0][i], d[1][i], d[2][i], d[3][i], theta[i], ax, ay, stride);
+    else
+      bx = decode_axis_aligned(d[0][i], d[1][i], d[2][i], d[3][i], ax, ay, stride, MODE == MODE_XYXY);
+    o0.v[i] = DType<DT_OUT>::from_f(bx.cx);
+    o1.v[i] = DType<DT_OUT>::from_f(bx.cy);
+    o2.v[i] = DType<DT_OUT>::from_f(bx.w);
+    o3.v[i] = DType<DT_OUT>::from_f(bx.h);
+    if (++gx == W) { gx = 0; ++gy; }
+  }
+  store_pack<TO, VEC>(out, o0);
+  store_pack<TO, VEC>(out + osc, o1);
+  store_pack<TO, VEC>(out + 2 * osc, o2);
+  store_pack<TO, VEC>(out + 3 * osc, o3);
+
+  // ---- class scores: sigmoid, streamed ---------------------------------------------------------------------------
+  const TI* csrc = src + static_cast<long long>(4 * REG) * cs;
+  TO* cdst = out + 4 * osc;
+#pragma unroll 8
+  for (int c = 0; c < nc; ++c) {
+    Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+    Pack<TO, VEC> q;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) q.v[i] = DType<DT_OUT>::from_f(sigmoid_f(DType<DT_IN>::to_f(p.v[i])));
+    store_pack<TO, VEC>(cdst + static_cast<long long>(c) * osc, q);
+  }
+  if constexpr (MODE == MODE_ROT) {
+    if (append_angle) {
+      Pack<TO, VEC> q;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) q.v[i] = DType<DT_OUT>::from_f(theta[i]);
+      store_pack<TO, VEC>(out + static_cast<long long>(4 + nc) * osc, q);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused decode + filter + compaction
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT_IN, int DT_VAL, int VEC, int REG, bool ROT, bool MULTI>
+__global__ void __launch_bounds__(DEC_THREADS)
+filter_from_head_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                        const __grid_constant__ FilterArgs f) {
+  using TI = typename DType<DT_IN>::type;
+  using DV = DType<DT_VAL>;
+  const int grp = blockIdx.x * DEC_THREADS + threadIdx.x;
+  const int b = blockIdx.y;
+  const bool active = grp < g.group_start[g.num_levels];
+  const int nc = g.nc;
+  const float conf = f.conf;
+
+  int l = 0, a_local = 0, a_glob = 0;
+  long long cs = 0;
+  const TI* src = nullptr;
+  const TI* csrc = nullptr;
+  int rows[VEC];    // rows this anchor emits
+  float best[VEC];  // single-label: max score (T-rounded)
+  int bcls[VEC];    // single-label: first argmax
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { rows[i] = 0; best[i] = 0.f; bcls[i] = 0; }
+
+  if (active) {
+    l = find_level(g, grp);
+    a_local = (grp - g.group_start[l]) * VEC;
+    a_glob = g.anchor_start[l] + a_local;
+    cs = g.cstride[l];
+    src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+    csrc = src + static_cast<long long>(4 * REG) * cs;
+
+    if constexpr (MULTI) {
+      // nms.py:76 + :115: every (anchor, class) whose score > conf; an anchor with a NaN score is dropped (amax -> NaN).
+      bool has_nan[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) has_nan[i] = false;
+#pragma unroll 8
+      for (int c = 0; c < nc; ++c) {
+        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+        const bool ok = class_allowed(f.class_mask, c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          float v = DType<DT_IN>::to_f(p.v[i]);
+          float s = DV::rnd(sigmoid_f(v));
+          has_nan[i] |= (v != v);
+          rows[i] += (s > conf && ok) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (has_nan[i]) rows[i] = 0;
+    } else {
+      // nms.py:76: candidate iff max_c score > conf.  sigmoid_f is monotone after rounding (ypb_selftest_sigmoid_
+      // monotone), so max_c score == score(max_c logit): one sigmoid per anchor instead of nc.
+      float mx[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) mx[i] = -INFINITY;
+#pragma unroll 8
+      for (int c = 0; c < nc; ++c) {
+        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) mx[i] = nanmax(mx[i], DType<DT_IN>::to_f(p.v[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (DV::rnd(sigmoid_f(mx[i])) > conf) {
+          // nms.py:120: conf, j = cls.max(1) -> first index of the maximal SCORE (ties between distinct logits that
+          // round to the same score resolve to the lower class), then re-filter (:121) and class filter (:127-131).
+          float bs = -1.f;
+          int bc = 0;
+          for (int c = 0; c < nc; ++c) {
+            float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
+            if (s > bs) { bs = s; bc = c; }
+          }
+          best[i] = bs;
+          bcls[i] = bc;
+          rows[i] = (bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;
+        }
+      }
+    }
+  }
+
+  int my_rows = 0;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) my_rows += rows[i];
+
+  // ---- decode only what survived (head.py:167-168 restricted to candidate anchors) ---------------------------------
+  if (my_rows > 0) {
+    float d[4][VEC];
+    load_ltrb<DT_IN, VEC, REG>(src, cs, d);
+    const int W = g.w[l];
+    const float stride = g.stride[l];
+    int gy = a_local / W, gx = a_local - gy * W;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (rows[i] > 0) {
+        const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+        const long long slot = static_cast<long long>(b) * g.anchors + a_glob + i;
+        if constexpr (ROT) {
+          float t = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
+          float theta = angle_is_logit ? DV::rnd(activate_angle(t)) : t;
+          BoxXYWH bx = decode_rotated(d[0][i], d[1][i], d[2][i], d[3][i], theta, ax, ay, stride);
+          f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
+          f.cand_ang[slot] = theta;
+        } else {
+          BoxXYWH bx = decode_axis_aligned(d[0][i], d[1][i], d[2][i], d[3][i], ax, ay, stride, false);
+          f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
+        }
+      }
+      if (++gx == W) { gx = 0; ++gy; }
+    }
+  }
+
+  // ---- compaction: one atomic per block, rows land in arbitrary order (the 64-bit keys are unique) -----------------
+  int total;
+  int off = block_exclusive_scan(my_rows, total);
+  if (total == 0) return;  // uniform
+  const int base = reserve_rows(f.row_count, b, total);
+  if (my_rows == 0) return;
+  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+  int pos = base + off;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (rows[i] == 0) continue;
+    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) * static_cast<uint32_t>(nc);
+    if constexpr (MULTI) {
+      for (int c = 0; c < nc; ++c) {
+        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
+        if (s > conf && class_allowed(f.class_mask, c)) {
+          if (pos < f.rows_cap) keys[pos] = make_key(s, row0 + c);
+          ++pos;
+        }
+      }
+    } else {
+      if (pos < f.rows_cap) keys[pos] = make_key(best[i], row0 + bcls[i]);
+      ++pos;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// filter + compaction of an already decoded (B, 4+nc+extra, A) tensor with arbitrary strides (nms.py:76-131)
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT, bool ROT, bool MULTI>
+__global__ void __launch_bounds__(DEC_THREADS)
+filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_constant__ FilterArgs f) {
+  using T = typename DType<DT>::type;
+  using D = DType<DT>;
+  const int a = blockIdx.x * DEC_THREADS + threadIdx.x;
+  const int b = blockIdx.y;
+  const int nc = f.nc;
+  const float conf = f.conf;
+  const bool active = a < d.anchors;
+  const T* p = static_cast<const T*>(d.ptr) + static_cast<long long>(b) * d.stride_b + static_cast<long long>(a) * d.stride_a;
+  const T* pc = p + 4 * d.stride_c;
+  const long long sc = d.stride_c;
+
+  int my_rows = 0, bcls = 0;
+  float best = 0.f;
+  if (active) {
+    if constexpr (MULTI) {
+      bool has_nan = false;
+#pragma unroll 8
+      for (int c = 0; c < nc; ++c) {
+        float s = D::to_f(pc[c * sc]);
+        has_nan |= (s != s);
+        my_rows += (s > conf && class_allowed(f.class_mask, c)) ? 1 : 0;
+      }
+      if (has_nan) my_rows = 0;
+    } else {
+      // torch max: NaN wins; otherwise first index of the maximum (nms.py:120)
+      float bs = -INFINITY;
+      int bc = 0;
+      bool has_nan = false;
+#pragma unroll 8
+      for (int c = 0; c < nc; ++c) {
+        float s = D::to_f(pc[c * sc]);
+        has_nan |= (s != s);
+        if (s > bs) { bs = s; bc = c; }
+      }
+      best = bs;
+      bcls = bc;
+      my_rows = (!has_nan && bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;
+    }
+    if (my_rows > 0) {
+      const long long slot = static_cast<long long>(b) * d.anchors + a;
+      float cx = D::to_f(p[0]), cy = D::to_f(p[sc]), w = D::to_f(p[2 * sc]), h = D::to_f(p[3 * sc]);
+      if constexpr (ROT) {
+        f.cand_box[slot] = make_float4(cx, cy, w, h);
+        f.cand_ang[slot] = D::to_f(p[static_cast<long long>(d.channels - 1) * sc]);  // nms.py:146 x[:, -1:]
+      } else {
+        f.cand_box[slot] = corners_in_dtype<DT>(cx, cy, w, h);  // nms.py:86
+      }
+    }
+  }
+
+  int total;
+  int off = block_exclusive_scan(my_rows, total);
+  if (total == 0) return;
+  const int base = reserve_rows(f.row_count, b, total);
+  if (my_rows == 0) return;
+  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+  int pos = base + off;
+  const uint32_t row0 = static_cast<uint32_t>(a) * static_cast<uint32_t>(nc);
+  if constexpr (MULTI) {
+    for (int c = 0; c < nc; ++c) {
+      float s = D::to_f(pc[c * sc]);
+      if (s > conf && class_allowed(f.class_mask, c)) {
+        if (pos < f.rows_cap) keys[pos] = make_key(s, row0 + c);
+        ++pos;
+      }
+    }
+  } else {
+    if (pos < f.rows_cap) keys[pos] = make_key(best, row0 + bcls);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// exhaustive monotonicity check of round_T(sigmoid_f(x)) over every finite fp32 x
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void sigmoid_monotone_kernel(unsigned long long* violations) {
+  const unsigned long long total = 0xffffffffull;  // pairs (o, o+1) in orderable space
+  unsigned long long bad = 0;
+  for (unsigned long long o = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; o < total;
+       o += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    float x = from_orderable_bits(static_cast<uint32_t>(o));
+    float y = from_orderable_bits(static_cast<uint32_t>(o + 1));
+    if (!isfinite(x) || !isfinite(y)) continue;
+    float sx = DType<DT>::rnd(sigmoid_f(x)), sy = DType<DT>::rnd(sigmoid_f(y));
+    if (!(sx <= sy)) ++bad;
+  }
+  if (bad) atomicAdd(violations, bad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT_IN, int DT_OUT, int VEC>
+static cudaError_t decode_dense_dispatch(const HeadGeom& g, const void* angle, int angle_is_logit, int append_angle,
+                                         int xyxy, void* out, long long osb, long long osc, cudaStream_t st) {
+  const int groups = g.group_start[g.num_levels];
+  dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
+  if (angle)
+    decode_dense_kernel<DT_IN, DT_OUT, VEC, 16, MODE_ROT><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+  else if (xyxy)
+    decode_dense_kernel<DT_IN, DT_OUT, VEC, 16, MODE_XYXY><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+  else
+    decode_dense_kernel<DT_IN, DT_OUT, VEC, 16, MODE_XYWH><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
+                                int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
+                                int vec, cudaStream_t st) {
+  if (in_dtype != out_dtype) return cudaErrorInvalidValue;  // Detect._inference returns the input dtype (head.py:169)
+#define YPB_DD(DT, V) return decode_dense_dispatch<DT, DT, V>(g, angle, angle_is_logit, append_angle, xyxy, out, osb, osc, st)
+  if (in_dtype == YPB_F32) {
+    if (vec == 4) YPB_DD(YPB_F32, 4);
+    if (vec == 1) YPB_DD(YPB_F32, 1);
+  } else if (in_dtype == YPB_BF16) {
+    if (vec == 8) YPB_DD(YPB_BF16, 8);
+    if (vec == 1) YPB_DD(YPB_BF16, 1);
+  } else if (in_dtype == YPB_F16) {
+    if (vec == 8) YPB_DD(YPB_F16, 8);
+    if (vec == 1) YPB_DD(YPB_F16, 1);
+  }
+#undef YPB_DD
+  return cudaErrorInvalidValue;
+}
+
+template <int DT_IN, int DT_VAL, int VEC>
+static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, int angle_is_logit, const FilterArgs& f,
+                                        cudaStream_t st) {
+  const int groups = g.group_start[g.num_levels];
+  dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
+#define YPB_FH(R, M) filter_from_head_kernel<DT_IN, DT_VAL, VEC, 16, R, M><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
+  if (f.rotated) { if (f.multi_label) YPB_FH(true, true); else YPB_FH(true, false); }
+  else           { if (f.multi_label) YPB_FH(false, true); else YPB_FH(false, false); }
+#undef YPB_FH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_dtype, const void* angle,
+                                    int angle_is_logit, const FilterArgs& f, int vec, cudaStream_t st) {
+  if (in_dtype != value_dtype) return cudaErrorInvalidValue;
+#define YPB_FD(DT, V) return filter_head_dispatch<DT, DT, V>(g, angle, angle_is_logit, f, st)
+  if (in_dtype == YPB_F32) {
+    if (vec == 4) YPB_FD(YPB_F32, 4);
+    if (vec == 1) YPB_FD(YPB_F32, 1);
+  } else if (in_dtype == YPB_BF16) {
+    if (vec == 8) YPB_FD(YPB_BF16, 8);
+    if (vec == 1) YPB_FD(YPB_BF16, 1);
+  } else if (in_dtype == YPB_F16) {
+    if (vec == 8) YPB_FD(YPB_F16, 8);
+    if (vec == 1) YPB_FD(YPB_F16, 1);
+  }
+#undef YPB_FD
+  return cudaErrorInvalidValue;
+}
+
+template <int DT>
+static cudaError_t filter_dense_dispatch(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st) {
+  dim3 grid((d.anchors + DEC_THREADS - 1) / DEC_THREADS, d.batch);
+#define YPB_FDN(R, M) filter_from_dense_kernel<DT, R, M><<<grid, DEC_THREADS, 0, st>>>(d, f)
+  if (f.rotated) { if (f.multi_label) YPB_FDN(true, true); else YPB_FDN(true, false); }
+  else           { if (f.multi_label) YPB_FDN(false, true); else YPB_FDN(false, false); }
+#undef YPB_FDN
+  return cudaGetLastError();
+}
+
+cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st) {
+  switch (d.dtype) {
+    case YPB_F32: return filter_dense_dispatch<YPB_F32>(d, f, st);
+    case YPB_F16: return filter_dense_dispatch<YPB_F16>(d, f, st);
+    case YPB_BF16: return filter_dense_dispatch<YPB_BF16>(d, f, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(violations, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  const int blocks = 148 * 16;
+  switch (dtype) {
+    case YPB_F32: sigmoid_monotone_kernel<YPB_F32><<<blocks, 256, 0, st>>>(violations); break;
+    case YPB_F16: sigmoid_monotone_kernel<YPB_F16><<<blocks, 256, 0, st>>>(violations); break;
+    case YPB_BF16: sigmoid_monotone_kernel<YPB_BF16><<<blocks, 256, 0, st>>>(violations); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ypb

@@ -1,0 +1,445 @@
+// Sort + suppression + gather kernel of libyolopost_b200 (sm_100a): one CTA per image.
+//
+//   stage 1  rank the candidate rows of the image by their unique 64-bit key (score desc, row asc):
+//            <= SORT_SMEM_MAX rows -> bitonic network in shared memory; more -> 8-bit LSD radix passes in global
+//            memory (ping-pong), skipping digit positions that are constant over the image.       (nms.py:137-141)
+//   stage 2  walk the ranks in chunks of CH: each rank is first tested against the rows already kept (<= max_det,
+//            the only ones that can still matter), then the chunk resolves its internal order dependence with a
+//            bitmask fix-point; stops as soon as max_det rows are kept (nms.py:157 keeps only those).  Fast-NMS rules
+//            (rotated ProbIoU, box_iou) have no dependence: a rank is tested against every higher rank. (nms.py:143-156)
+//   stage 3  gather the kept rows (nms.py:159-161).
+//
+// All IoU arithmetic uses explicit round-to-nearest intrinsics in the reference's operation order (no FMA
+// contraction), so kept sets are bit-exact against torchvision.ops.nms / TorchNMS (SURVEY.md section 7 "Hard parts").
+#include "ypb_common.cuh"
+
+namespace ypb {
+
+constexpr int NT = 512;              // threads per CTA
+constexpr int NW = NT / 32;          // warps per CTA
+constexpr int CH = NT;               // ranks per chunk
+constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
+
+struct __align__(16) Smem {
+  union {
+    uint64_t keys[SORT_SMEM_MAX];  // small path: sorted keys live here for the whole kernel
+    struct {
+      uint32_t hist[256];
+      uint32_t wc[NW * 256];
+    } rx;
+  } u;
+  uint32_t mask[NW * CH];  // mask[w * CH + t]: bit i set iff rank (w*32+i) of the chunk suppresses rank t
+  union {
+    struct {
+      float4 box[CH];
+      float area[CH];
+    } g;
+    float rec[CH * 8];
+  } c;
+  uint32_t alive_bits[NW];
+  uint32_t kept_bits[NW];
+  uint32_t undec_bits[NW];
+  unsigned long long red_and, red_or;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// pair predicates
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+// torchvision nms_kernel_impl / nms.py:276-294: inter / (area_i + area_j - inter) > thr, no eps.
+__device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+  float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  float inter = __fmul_rn(w, h);
+  if (inter == 0.f) return false;  // quotient is +-0 or NaN: never > thr (thr >= 0)
+  float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return iou > thr;
+}
+
+// metrics.py:54-75 with eps in the denominator, rule ">= thr" (nms.py:223).
+__device__ __forceinline__ bool boxiou_suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+  float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  float inter = __fmul_rn(w, h);
+  float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-7f));
+  return iou >= thr;
+}
+
+struct ObbRec { float x, y, a, b, c, det; };
+
+// metrics.py:187-203 on one xywhr box (+ the per-box factor of metrics.py:279).
+__device__ __forceinline__ ObbRec obb_record(float x, float y, float w, float h, float r) {
+  ObbRec o;
+  o.x = x; o.y = y;
+  float a = __fdiv_rn(__fmul_rn(w, w), 12.f), b = __fdiv_rn(__fmul_rn(h, h), 12.f);
+  float co = cosf(r), si = sinf(r);
+  float c2 = __fmul_rn(co, co), s2 = __fmul_rn(si, si);
+  o.a = __fadd_rn(__fmul_rn(a, c2), __fmul_rn(b, s2));
+  o.b = __fadd_rn(__fmul_rn(a, s2), __fmul_rn(b, c2));
+  o.c = __fmul_rn(__fmul_rn(__fsub_rn(a, b), co), si);
+  o.det = fmaxf(__fsub_rn(__fmul_rn(o.a, o.b), __fmul_rn(o.c, o.c)), 0.f);
+  return o;
+}
+
+// metrics.py:251-284, p = higher-ranked row (obb1), q = lower-ranked (obb2); rule ">= thr" (nms.py:223).
+__device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec& q, float thr) {
+  const float eps = 1e-7f;
+  float sa = __fadd_rn(p.a, q.a), sb = __fadd_rn(p.b, q.b), sc = __fadd_rn(p.c, q.c);
+  float dy = __fsub_rn(p.y, q.y), dx = __fsub_rn(p.x, q.x);
+  float den = __fsub_rn(__fmul_rn(sa, sb), __fmul_rn(sc, sc));
+  float dene = __fadd_rn(den, eps);
+  float t1 = __fmul_rn(__fdiv_rn(__fadd_rn(__fmul_rn(sa, __fmul_rn(dy, dy)), __fmul_rn(sb, __fmul_rn(dx, dx))), dene), 0.25f);
+  float t2 = __fmul_rn(__fdiv_rn(__fmul_rn(__fmul_rn(sc, __fsub_rn(q.x, p.x)), dy), dene), 0.5f);
+  float root = sqrtf(__fmul_rn(p.det, q.det));
+  float t3 = __fmul_rn(logf(__fadd_rn(__fdiv_rn(den, __fadd_rn(__fmul_rn(4.f, root), eps)), eps)), 0.5f);
+  float bd = __fadd_rn(__fadd_rn(t1, t2), t3);
+  bd = bd != bd ? bd : fminf(fmaxf(bd, eps), 100.f);
+  float hd = sqrtf(__fadd_rn(__fsub_rn(1.0f, expf(-bd)), eps));
+  return __fsub_rn(1.0f, hd) >= thr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 1: ranking
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_smem(uint64_t* s, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += NT) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int l = i | j;
+        bool up = (i & k) == 0;
+        uint64_t a = s[i], c = s[l];
+        if ((a > c) == up) { s[i] = c; s[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One stable 8-bit LSD pass src -> dst over n keys.
+__device__ void radix_pass(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int n, int shift, Smem& sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* hist = sm.u.rx.hist;
+  uint32_t* wc = sm.u.rx.wc;
+  for (int i = threadIdx.x; i < 256; i += NT) hist[i] = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += NT) {
+    const int i = base + threadIdx.x;
+    const bool act = i < n;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const uint32_t d = static_cast<uint32_t>(src[i] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(am, d);
+      if ((peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 256 bins
+    uint32_t v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = hist[lane * 8 + k]; s += v[k]; }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    uint32_t run = inc - s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { hist[lane * 8 + k] = run; run += v[k]; }
+  }
+  __syncthreads();
+  for (int base = 0; base < n; base += NT) {
+    for (int k = threadIdx.x; k < NW * 256; k += NT) wc[k] = 0;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    const bool act = i < n;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    uint64_t key = 0;
+    uint32_t d = 0, rank = 0;
+    if (act) {
+      key = src[i];
+      d = static_cast<uint32_t>(key >> shift) & 255u;
+      const unsigned peers = __match_any_sync(am, d);
+      rank = __popc(peers & lt_mask);
+      if (rank == 0) wc[warp * 256 + d] = __popc(peers);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      uint32_t run = hist[threadIdx.x];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t c = wc[w * 256 + threadIdx.x];
+        wc[w * 256 + threadIdx.x] = run;
+        run += c;
+      }
+      hist[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (act) dst[wc[warp * 256 + d] + rank] = key;
+    __syncthreads();
+  }
+}
+
+// Full ascending sort of n keys in global memory; returns the buffer holding the result.
+__device__ const uint64_t* radix_sort_global(uint64_t* a, uint64_t* b, int n, Smem& sm) {
+  // digit positions that are constant over the image need no pass
+  unsigned long long vand = ~0ull, vor = 0ull;
+  for (int i = threadIdx.x; i < n; i += NT) { uint64_t k = a[i]; vand &= k; vor |= k; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+  }
+  if (threadIdx.x == 0) { sm.red_and = ~0ull; sm.red_or = 0ull; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { atomicAnd(&sm.red_and, vand); atomicOr(&sm.red_or, vor); }
+  __syncthreads();
+  const unsigned long long varying = sm.red_and ^ sm.red_or;
+  uint64_t* src = a;
+  uint64_t* dst = b;
+  for (int shift = 0; shift < 64; shift += 8) {
+    if (((varying >> shift) & 255ull) == 0) continue;  // uniform branch
+    radix_pass(src, dst, n, shift, sm);
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ float load_as_float(const void* p, long long off) {
+  return DType<DT>::to_f(static_cast<const typename DType<DT>::type*>(p)[off]);
+}
+__device__ __forceinline__ float load_pred(const void* p, int dt, long long off) {
+  if (dt == YPB_F32) return load_as_float<YPB_F32>(p, off);
+  if (dt == YPB_F16) return load_as_float<YPB_F16>(p, off);
+  return load_as_float<YPB_BF16>(p, off);
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant__ SuppressArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  const int emitted = a.row_count[b];
+  const int n = min(emitted, a.rows_cap);
+  if (tid == 0 && a.out_cand) a.out_cand[b] = emitted;
+
+  uint64_t* ka = a.keys_a + static_cast<long long>(b) * a.rows_cap;
+  uint64_t* kb = a.keys_b + static_cast<long long>(b) * a.rows_cap;
+
+  // ---- stage 1 ---------------------------------------------------------------------------------------------------
+  const uint64_t* sorted;
+  if (n <= SORT_SMEM_MAX) {
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += NT) sm.u.keys[i] = i < n ? ka[i] : KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_smem(sm.u.keys, P);
+    sorted = sm.u.keys;
+  } else {
+    sorted = radix_sort_global(ka, kb, n, sm);
+  }
+  const int m = min(n, a.max_nms);
+
+  // ---- stage 2 ---------------------------------------------------------------------------------------------------
+  const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
+  const float* cand_ang = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
+  float4* kept_box = a.kept_box + static_cast<long long>(b) * a.max_det;
+  float* kept_area = a.kept_area + static_cast<long long>(b) * a.max_det;
+  uint64_t* kept_key = a.kept_key + static_cast<long long>(b) * a.max_det;
+  float* rec_g = RULE == YPB_NMS_GREEDY ? nullptr : a.rec + static_cast<long long>(b) * min(a.rows_cap, a.max_nms) * 8;
+  const float thr = a.iou_thr;
+  const uint32_t nc = static_cast<uint32_t>(a.nc);
+
+  int kept_n = 0;
+  for (int c0 = 0; c0 < m && kept_n < a.max_det; c0 += CH) {
+    const int r = c0 + tid;
+    const bool valid = r < m;
+    uint64_t key = 0;
+    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    float area = 0.f;
+    ObbRec me{};
+    bool alive = valid;
+    if (valid) {
+      key = sorted[r];
+      const uint32_t row = key_row(key);
+      const uint32_t anchor = row / nc, cls = row - anchor * nc;
+      const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
+      const float4 bx = cand_box[anchor];
+      if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+        me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, cand_ang[anchor]);  // nms.py:146
+      } else {
+        ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // nms.py:149
+        area = box_area(ob);
+      }
+    }
+
+    if constexpr (RULE == YPB_NMS_GREEDY) {
+      // (a) against rows kept in earlier chunks
+      if (alive) {
+        for (int k = 0; k < kept_n; ++k) {
+          if (greedy_suppresses(kept_box[k], kept_area[k], ob, area, thr)) { alive = false; break; }
+        }
+      }
+      sm.c.g.box[tid] = ob;
+      sm.c.g.area[tid] = area;
+      const unsigned ab = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) sm.alive_bits[warp] = ab;
+      __syncthreads();
+      // (b) who inside the chunk could suppress me
+      if (alive) {
+        for (int w = 0; w <= warp; ++w) {
+          uint32_t cand = sm.alive_bits[w];
+          if (w == warp) cand &= lt_mask;
+          uint32_t word = 0;
+          while (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int idx = w * 32 + i;
+            if (greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, thr)) word |= 1u << i;
+          }
+          sm.mask[w * CH + tid] = word;
+        }
+      }
+      // (c) fix-point: kept iff no kept suppressor; dead iff some kept suppressor; wait while a suppressor is undecided
+      int status = alive ? 0 : 2;  // 0 undecided, 1 kept, 2 dead
+      while (true) {
+        const unsigned ub = __ballot_sync(0xffffffffu, status == 0);
+        const unsigned kbits = __ballot_sync(0xffffffffu, status == 1);
+        if (lane == 0) { sm.undec_bits[warp] = ub; sm.kept_bits[warp] = kbits; }
+        if (!__syncthreads_or(status == 0)) break;
+        if (status == 0) {
+          bool hit_kept = false, hit_undec = false;
+          for (int w = 0; w <= warp; ++w) {
+            const uint32_t mw = sm.mask[w * CH + tid];
+            hit_kept |= (mw & sm.kept_bits[w]) != 0;
+            hit_undec |= (mw & sm.undec_bits[w]) != 0;
+          }
+          if (hit_kept) status = 2;
+          else if (!hit_undec) status = 1;
+        }
+        __syncthreads();
+      }
+      alive = status == 1;
+    } else {
+      // Fast-NMS: test against EVERY higher rank (kept or not), nms.py:221-223
+      float* my = sm.c.rec + tid * 8;
+      if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+        my[0] = me.x; my[1] = me.y; my[2] = me.a; my[3] = me.b; my[4] = me.c; my[5] = me.det;
+      } else {
+        my[0] = ob.x; my[1] = ob.y; my[2] = ob.z; my[3] = ob.w; my[4] = area;
+      }
+      if (valid) {
+        float* gr = rec_g + static_cast<long long>(r) * 8;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gr[k] = my[k];
+      }
+      __syncthreads();
+      if (valid) {
+        for (int i = 0; i < r && alive; ++i) {
+          const float* q = i < c0 ? rec_g + static_cast<long long>(i) * 8 : sm.c.rec + (i - c0) * 8;
+          if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+            ObbRec hi{q[0], q[1], q[2], q[3], q[4], q[5]};
+            if (probiou_suppresses(hi, me, thr)) alive = false;
+          } else {
+            float4 hb = make_float4(q[0], q[1], q[2], q[3]);
+            if (boxiou_suppresses(hb, q[4], ob, area, thr)) alive = false;
+          }
+        }
+      }
+      const unsigned kbits = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) sm.kept_bits[warp] = kbits;
+      __syncthreads();
+    }
+
+    // (d) append the chunk's kept rows in rank order
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int pc = __popc(sm.kept_bits[w]);
+      if (w < warp) before += pc;
+      total += pc;
+    }
+    if (alive) {
+      const int pos = kept_n + before + __popc(sm.kept_bits[warp] & lt_mask);
+      if (pos < a.max_det) {
+        kept_key[pos] = key;
+        if constexpr (RULE == YPB_NMS_GREEDY) { kept_box[pos] = ob; kept_area[pos] = area; }
+      }
+    }
+    kept_n = min(a.max_det, kept_n + total);
+    __syncthreads();  // kept_* visible to the block, smem reusable
+  }
+
+  // ---- stage 3 ---------------------------------------------------------------------------------------------------
+  if (tid == 0) a.out_count[b] = kept_n;
+  const int cols = 6 + a.extra;
+  for (int k = tid; k < kept_n; k += NT) {
+    const uint64_t key = kept_key[k];
+    const uint32_t row = key_row(key);
+    const uint32_t anchor = row / nc, cls = row - anchor * nc;
+    if (a.out_idx) a.out_idx[static_cast<long long>(b) * a.max_det + k] = a.idx_as_row ? row : anchor;
+    if (a.out_rows) {
+      float* o = a.out_rows + (static_cast<long long>(b) * a.max_det + k) * cols;
+      const float4 bx = cand_box[anchor];
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+      o[4] = key_score(key);
+      o[5] = static_cast<float>(cls);
+      if (a.pred) {
+        const long long base = static_cast<long long>(b) * a.pred_sb + static_cast<long long>(anchor) * a.pred_sa;
+        for (int e = 0; e < a.extra; ++e)
+          o[6 + e] = load_pred(a.pred, a.pred_dtype, base + static_cast<long long>(4 + a.nc + e) * a.pred_sc);
+      } else if (a.extra == 1 && cand_ang) {
+        o[6] = cand_ang[anchor];
+      }
+    }
+  }
+}
+
+__global__ void boxes_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, int box_dim,
+                                  uint64_t* keys, float4* cand_box, float* cand_ang, int32_t* row_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) row_count[0] = n;
+  if (i >= n) return;
+  keys[i] = make_key(scores[i], static_cast<uint32_t>(i));
+  const float* p = boxes + static_cast<long long>(i) * box_dim;
+  cand_box[i] = make_float4(p[0], p[1], p[2], p[3]);
+  if (box_dim == 5) cand_ang[i] = p[4];
+}
+
+cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(Smem);
+  cudaError_t e;
+#define YPB_SS(R)                                                                                              \
+  do {                                                                                                         \
+    e = cudaFuncSetAttribute(sort_suppress_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                            \
+    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(a);                                                     \
+  } while (0)
+  switch (a.rule) {
+    case YPB_NMS_GREEDY: YPB_SS(YPB_NMS_GREEDY); break;
+    case YPB_NMS_FAST_PROBIOU: YPB_SS(YPB_NMS_FAST_PROBIOU); break;
+    case YPB_NMS_FAST_BOXIOU: YPB_SS(YPB_NMS_FAST_BOXIOU); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef YPB_SS
+  return cudaGetLastError();
+}
+
+cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,
+                              float4* cand_box, float* cand_ang, int32_t* row_count, cudaStream_t st) {
+  const int blocks = n > 0 ? (n + 255) / 256 : 1;
+  boxes_prep_kernel<<<blocks, 256, 0, st>>>(boxes, scores, n, box_dim, keys, cand_box, cand_ang, row_count);
+  return cudaGetLastError();
+}
+
+}  // namespace ypb

@@ -1,0 +1,162 @@
+"""Host-side sequencing shared by the drop-in functions: descriptors, scratch reuse, result views.
+
+Everything here is plumbing around the C-ABI calls; no arithmetic of the path is done in Python/PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import torch
+
+from . import _cabi
+
+_tls = threading.local()
+
+
+def _scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(thread, device, stream) scratch buffer, grown geometrically; 256-byte aligned by the caching allocator."""
+    pool = getattr(_tls, "pool", None)
+    if pool is None:
+        pool = _tls.pool = {}
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = pool.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        pool[key] = buf
+    return buf
+
+
+def _pinned_counts(n: int) -> torch.Tensor:
+    buf = getattr(_tls, "pinned", None)
+    if buf is None or buf.numel() < n:
+        buf = _tls.pinned = torch.empty(max(n, 256), dtype=torch.int32, pin_memory=True)
+    return buf[:n]
+
+
+_class_masks: dict = {}
+
+
+def class_mask_tensor(classes, nc: int, device: torch.device):
+    """Device bitmask of the `classes` filter (nms.py:62-63,127-131); cached per (classes, nc, device)."""
+    if classes is None:
+        return None
+    if isinstance(classes, torch.Tensor):
+        classes = classes.tolist()
+    key = (tuple(int(c) for c in classes), nc, device.index)
+    t = _class_masks.get(key)
+    if t is None:
+        words = [0] * ((nc + 31) // 32)
+        for c in key[0]:
+            if 0 <= c < nc:
+                words[c >> 5] |= 1 << (c & 31)
+        # uint32 words stored as their int32 bit patterns
+        t = torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in words], dtype=torch.int32, device=device)
+        _class_masks[key] = t
+    return t
+
+
+def head_desc(levels, strides, nc: int, reg_max: int):
+    """Build the ypb_head_desc for a list of (B, 4*reg_max+nc, H, W) level tensors (head.py:121-122)."""
+    if not levels:
+        raise ValueError("no head levels given")
+    if len(levels) > _cabi.MAX_LEVELS:
+        raise ValueError(f"{len(levels)} levels > {_cabi.MAX_LEVELS}")
+    dev, dt = levels[0].device, levels[0].dtype
+    b = levels[0].shape[0]
+    no = 4 * reg_max + nc
+    d = _cabi.HeadDesc()
+    d.num_levels, d.batch, d.nc, d.reg_max, d.dtype = len(levels), b, nc, reg_max, _cabi.dtype_code(dt)
+    keep = []
+    anchors = 0
+    for i, lv in enumerate(levels):
+        _cabi.require_cuda(lv, "head level")
+        if lv.device != dev or lv.dtype != dt:
+            raise ValueError("head levels must share device and dtype")
+        if lv.dim() != 4 or lv.shape[0] != b or lv.shape[1] != no:
+            raise ValueError(f"level {i}: expected (B={b}, {no}, H, W), got {tuple(lv.shape)}")
+        h, w = lv.shape[2], lv.shape[3]
+        if h * w and (lv.stride(3) != 1 or lv.stride(2) != w):
+            lv = lv.contiguous()  # channels_last or sliced maps: anchors must be contiguous
+        keep.append(lv)
+        d.level_ptr[i] = lv.data_ptr()
+        d.level_h[i], d.level_w[i] = h, w
+        d.level_batch_stride[i] = lv.stride(0)
+        d.level_channel_stride[i] = lv.stride(1)
+        d.level_stride[i] = float(strides[i])
+        anchors += h * w
+    return d, keep, anchors
+
+
+@dataclass
+class NmsPlan:
+    """Geometry-dependent pieces of one non_max_suppression call."""
+    params: _cabi.NmsParams
+    out: _cabi.NmsOut
+    rows: torch.Tensor
+    idx: torch.Tensor
+    count: torch.Tensor
+    cand: torch.Tensor
+    scratch: torch.Tensor
+    keep_alive: tuple
+
+
+def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
+              max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None) -> NmsPlan:
+    rows_cap = anchors * nc if multi_label else anchors
+    rows_cap = max(rows_cap, 1)
+    max_nms = max(1, min(int(max_nms), rows_cap))
+    max_det = max(1, min(int(max_det), max_nms))
+    lib = _cabi.load()
+    nbytes = lib.ypb_nms_workspace_bytes(batch, anchors, rows_cap, max_det, max_nms, rule)
+    scratch = _scratch(device, nbytes)
+    cols = 6 + extra
+    rows = torch.empty((batch, max_det, cols), dtype=torch.float32, device=device)
+    idx = torch.empty((batch, max_det), dtype=torch.int64, device=device)
+    count = torch.empty((batch,), dtype=torch.int32, device=device)
+    cand = torch.empty((batch,), dtype=torch.int32, device=device)
+    mask = class_mask_tensor(classes, nc, device)
+    p = _cabi.NmsParams()
+    p.conf_thres, p.iou_thres_eff = conf_t, iou_eff
+    p.nc, p.extra, p.max_det, p.max_nms = nc, extra, max_det, max_nms
+    p.max_wh, p.multi_label, p.rule, p.rows_cap = float(max_wh), int(bool(multi_label)), rule, rows_cap
+    p.class_mask = mask.data_ptr() if mask is not None else None
+    o = _cabi.NmsOut()
+    o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
+    return NmsPlan(p, o, rows, idx, count, cand, scratch, (mask,))
+
+
+def fetch_counts(count: torch.Tensor) -> list:
+    """The one device->host transfer of the path: per-image kept counts."""
+    host = _pinned_counts(count.numel())
+    host.copy_(count, non_blocking=True)
+    torch.cuda.current_stream(count.device).synchronize()
+    return host.tolist()
+
+
+def split_results(plan: NmsPlan, return_idxs: bool):
+    counts = fetch_counts(plan.count)
+    out = [plan.rows[b, :n] for b, n in enumerate(counts)]
+    if return_idxs:
+        return out, [plan.idx[b, :n] for b, n in enumerate(counts)]
+    return out
+
+
+def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:
+    d = _cabi.DenseDesc()
+    d.ptr, d.dtype = pred.data_ptr(), _cabi.dtype_code(pred.dtype)
+    d.batch, d.channels, d.anchors = pred.shape
+    d.stride_b, d.stride_c, d.stride_a = pred.stride()
+    lib = _cabi.load()
+    rc = lib.ypb_nms_from_dense(C.byref(d), C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
+                                plan.scratch.numel(), _cabi.stream_ptr(pred.device))
+    _cabi.check(rc, "ypb_nms_from_dense")
+
+
+def run_from_head(desc, angle, angle_is_logit: bool, plan: NmsPlan, device) -> None:
+    lib = _cabi.load()
+    rc = lib.ypb_nms_from_head(C.byref(desc), angle.data_ptr() if angle is not None else None, int(angle_is_logit),
+                               desc.dtype, C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
+                               plan.scratch.numel(), _cabi.stream_ptr(device))
+    _cabi.check(rc, "ypb_nms_from_head")

@@ -1,0 +1,104 @@
+"""Drop-ins for the Detect-family decode (``ultralytics/nn/modules/head.py``) and the fused post-process call.
+
+  detect_inference(self, x)      bound as ``Detect._inference`` (head.py:151-169; identical copies :340,:535,:724)
+  decode_head(...)               the same decode as a free function on raw level tensors
+  postprocess_from_head(...)     decode + non_max_suppression in one pass over the head (never writes the dense
+                                 tensor) - the `postprocess` envelope of predictor.py:335 / validator.py:221
+
+All arithmetic runs in libyolopost_b200; PyTorch allocates the output and provides the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi, engine
+from .nms import _greedy_threshold
+
+
+def _anchor_cache(levels, strides, dtype, device):
+    """anchors (2, A) / strides (1, A) exactly as head.py:163-165 caches them (Pose.kpts_decode and
+    BaseModel._apply read these attributes).  Built once per input shape with index arithmetic only."""
+    pts, srow = [], []
+    for lv, s in zip(levels, strides):
+        h, w = lv.shape[2], lv.shape[3]
+        gx = torch.arange(w, device=device, dtype=dtype) + 0.5
+        gy = torch.arange(h, device=device, dtype=dtype) + 0.5
+        yy, xx = torch.meshgrid(gy, gx, indexing="ij")
+        pts.append(torch.stack((xx, yy), -1).view(-1, 2))
+        srow.append(torch.full((h * w, 1), float(s), dtype=dtype, device=device))
+    return torch.cat(pts).transpose(0, 1), torch.cat(srow).transpose(0, 1)
+
+
+def decode_head(levels, strides, nc: int, reg_max: int = 16, angle: torch.Tensor | None = None,
+                angle_is_logit: bool = False, append_angle: bool = False, xyxy: bool = False) -> torch.Tensor:
+    """Dense decode of raw Detect-head levels -> (B, 4+nc[+1], A) in the input dtype.
+
+    levels: list of (B, 4*reg_max+nc, H_i, W_i) CUDA tensors; strides: per-level model stride (head.py:79);
+    angle: optional (B, 1, A) OBB channel - raw cv4 logits when ``angle_is_logit`` else already
+    ``(sigmoid-0.25)*pi`` (head.py:1031) - selecting the rotated decode (tal.py:385-403).
+    """
+    desc, keep, anchors = engine.head_desc(levels, strides, nc, reg_max)
+    lv0 = keep[0]
+    b = lv0.shape[0]
+    ch = 4 + nc + (1 if (angle is not None and append_angle) else 0)
+    out = torch.empty((b, ch, anchors), dtype=lv0.dtype, device=lv0.device)
+    ang_ptr = None
+    if angle is not None:
+        _cabi.require_cuda(angle, "angle")
+        if angle.dtype != lv0.dtype:
+            angle = angle.to(lv0.dtype)
+        angle = angle.reshape(b, anchors).contiguous()
+        ang_ptr = angle.data_ptr()
+    lib = _cabi.load()
+    rc = lib.ypb_decode_dense(C.byref(desc), ang_ptr, int(angle_is_logit), int(append_angle), int(xyxy),
+                              out.data_ptr(), desc.dtype, out.stride(0), out.stride(1), _cabi.stream_ptr(lv0.device))
+    _cabi.check(rc, "ypb_decode_dense")
+    return out
+
+
+def detect_inference(self, x: list) -> torch.Tensor:
+    """``Detect._inference`` drop-in (head.py:151-169).  Reads the same module attributes, keeps caching
+    ``self.anchors/self.strides/self.shape`` and returns the dense (B, 4+nc, A) tensor in the input dtype."""
+    shape = x[0].shape  # BCHW
+    if self.dynamic or self.shape != shape:
+        self.anchors, self.strides = _anchor_cache(x, self.stride, x[0].dtype, x[0].device)
+        self.shape = shape
+    angle = getattr(self, "angle", None) if hasattr(self, "ne") and hasattr(self, "cv4") else None  # OBB family
+    return decode_head(x, [float(s) for s in self.stride], self.nc, self.reg_max, angle=angle, angle_is_logit=False,
+                       append_angle=False, xyxy=bool(self.end2end or self.xyxy))
+
+
+def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
+                          agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
+                          max_wh: int = 7680, reg_max: int = 16, angle_logits: torch.Tensor | None = None,
+                          return_idxs: bool = False, sync: bool = True):
+    """Fused ``Detect._inference`` + ``non_max_suppression`` (head.py:151-169 then nms.py:13-166).
+
+    Bit-identical to ``non_max_suppression(decode_head(levels, ...), ...)`` but reads the head once and never writes
+    the (B, 4+nc, A) tensor.  ``angle_logits`` (B, 1, A) switches to the OBB path (rotated decode + ProbIoU Fast-NMS).
+    With ``sync=False`` returns the device-resident plan (rows/idx/count tensors) without any host transfer.
+    """
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    desc, keep, anchors = engine.head_desc(levels, strides, nc, reg_max)
+    lv0 = keep[0]
+    b = lv0.shape[0]
+    rotated = angle_logits is not None
+    multi_label = bool(multi_label) and nc > 1
+    conf_t = _cabi.round_to_dtype(float(conf_thres), lv0.dtype)
+    if rotated:
+        rule, iou_eff = _cabi.RULE_FAST_PROBIOU, _cabi.f32_round(float(iou_thres))
+        angle_logits = angle_logits.to(lv0.dtype).reshape(b, anchors).contiguous()
+    else:
+        rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(iou_thres)
+    plan = engine.make_plan(lv0.device, b, anchors, nc, 1 if rotated else 0, conf_t, iou_eff, max_det, max_nms,
+                            0.0 if agnostic else float(max_wh), multi_label, rule, classes)
+    if b:
+        engine.run_from_head(desc, angle_logits, True, plan, lv0.device)
+    else:
+        plan.count.zero_()
+    if not sync:
+        return plan
+    return engine.split_results(plan, return_idxs)
