@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the detection post-processing hot path (BASELINE.json: post-process imgs/s, decode+NMS, B=64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f32|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the fused decode+filter+sort+suppress path over one batch of synthetic yolov8x-shaped head
+outputs (configs[1] of BASELINE.json) per GPU.  Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "post-process imgs/s (decode+NMS) @B=64"
+UNIT = "imgs/s"
+WORKLOAD = "c2_v8x_640_b64"
+WORKLOAD_DESC = ("c2: yolov8x detect head outputs (3 levels 80/40/20, 144 ch, 8400 anchors, 80 classes, reg_max 16), "
+                 "batch 64 per GPU at 640x640, predict mode conf=0.25 iou=0.7 max_det=300, clustered-object synthetic logits")
+FALLBACK_HBM_GBS = 6650.0
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                uuid = torch.cuda.get_device_properties(index).uuid
+            except Exception:
+                pass
+            self.nv = pynvml
+            self.h = None
+            if uuid is not None:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
+                self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for name, bit in {**self.BAD, **self.NOTE}.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        self.sample()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port (torch CPU restatement of the reference's own operators) on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_step_fn(cfg, images: int, seed: int = 99):
+    from oracle.postproc_oracle import decode_oracle, nms_oracle
+    from ultralytics_pro_b200.synth import make_head_batch
+
+    levels, _ = make_head_batch(cfg, batch=images, seed=seed)
+
+    def step():
+        y = decode_oracle(levels, cfg.strides, cfg.nc, cfg.reg_max)
+        out, _ = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc, multi_label=cfg.multi_label, max_det=cfg.max_det)
+        return out
+
+    return step
+
+
+def cpu_baseline(cfg, budget_s: float = 15.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = _cpu_step_fn(cfg, cfg.batch)
+    step()  # warm-up (imports torchvision)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or reps >= 50:
+            break
+    all_cores = cfg.batch * reps / el
+    torch.set_num_threads(1)
+    t1 = time.perf_counter()
+    step()
+    one = cfg.batch / (time.perf_counter() - t1)
+    torch.set_num_threads(cores)
+    return {"value": all_cores, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} passes over one {cfg.batch}-image batch of the same workload (decode_oracle + nms_oracle, "
+                      f"torchvision.ops.nms branch), torch threads={cores}",
+            "single_thread_value": one}
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return 0
+    from ultralytics_pro_b200.synth import CONFIGS
+
+    cfg = CONFIGS[WORKLOAD]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe = _cpu_step_fn(cfg, 8)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    t_img = (time.perf_counter() - t0) / 8
+    total_steps = args.steps + args.warmup
+    sample = int(max(1, min(cfg.batch, 120.0 / max(t_img * total_steps, 1e-9))))
+    step = _cpu_step_fn(cfg, sample)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = sample * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC, "batch_per_step": sample, "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images of the workload per step (bounded so the run ends in minutes); "
+                                   f"oracle port = the reference's torch CPU operators incl. torchvision.ops.nms"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from ultralytics_pro_b200 import dist as ypb_dist
+    from ultralytics_pro_b200.head import postprocess_from_head
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+    from ultralytics_pro_b200.synth import CONFIGS, make_head_batch
+
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[WORKLOAD]
+    dtype = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
+    B, K, W = cfg.batch, args.steps, max(args.warmup, 3)
+    esize = 4 if dtype == torch.float32 else 2
+    in_bytes_img = cfg.no * cfg.anchors * esize  # algorithmic bytes per image of the fused path
+
+    # ---- synthetic inputs, resident in HBM before any timing; NSETS x 310 MB > 126 MB L2 ---------------------------
+    NSETS = 3
+    sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B)[0]
+            for s in range(NSETS)]
+    post = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
+    use_graph = not args.no_graph
+    graphs = [post.capture(lv) for lv in sets] if use_graph else None
+    plan = post.enqueue(sets[0])  # builds the plan / result buffers (also when graphs are off)
+
+    def step(i):
+        if use_graph:
+            graphs[i % NSETS].replay()
+        else:
+            post.enqueue(sets[i % NSETS])
+
+    # result gather across ranks (counts + rows, one packed all_gather) on a side stream, overlapped with the next step
+    gather_stream = torch.cuda.Stream(dev) if world > 1 else None
+    gather_buf = None
+    if world > 1:
+        per = B
+        gather_buf = [torch.empty((world * per, 1 + plan.rows.shape[1] * plan.rows.shape[2]), dtype=torch.float32, device=dev)
+                      for _ in range(2)]
+
+    def gather(i):
+        if world == 1:
+            return
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(gather_stream):
+            gather_stream.wait_event(done)
+            packed = ypb_dist.pack_results(plan.rows, plan.count)
+            dist.all_gather_into_tensor(gather_buf[i % 2], packed)
+        # the next step overwrites plan.rows: it must not start before `packed` was built
+        packed_done = torch.cuda.Event()
+        packed_done.record(gather_stream)
+        torch.cuda.current_stream(dev).wait_event(packed_done)
+
+    for i in range(W):
+        step(i)
+        gather(i)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step(i)
+        gather(i)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(gather_stream)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * B * K / (total_ms * 1e-3)
+    kept = plan.count.sum().item()
+    cand = plan.cand.sum().item()
+
+    # ---- per-kernel timing with CUDA events on the launching stream (roofline of the dominant kernel) ---------------
+    KI = min(K, 200)
+    e = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KI)]
+    for i in range(3):
+        post.enqueue(sets[i % NSETS], stage=1)
+        post.enqueue(sets[i % NSETS], stage=2)
+    torch.cuda.synchronize(dev)
+    for i in range(KI):
+        e[i][0].record()
+        post.enqueue(sets[i % NSETS], stage=1)
+        e[i][1].record()
+        post.enqueue(sets[i % NSETS], stage=2)
+        e[i][2].record()
+    torch.cuda.synchronize(dev)
+    t_filter = sum(a.elapsed_time(b) for a, b, _ in e) / KI  # ms: memset + fused decode/filter kernel
+    t_suppr = sum(b.elapsed_time(c) for _, b, c in e) / KI   # ms: sort + suppress + gather kernel
+    peak, peak_src = _peaks()
+    algo_bytes = B * in_bytes_img
+    achieved = algo_bytes / (t_filter * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "filter_from_head_kernel (fused DFL decode + sigmoid + confidence filter + compaction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "launch_ms": t_filter, "other_kernels_ms": {"sort_suppress_kernel": t_suppr}}
+
+    # ---- dense decode kernel alone (the Detect._inference drop-in), same inputs --------------------------------------
+    from ultralytics_pro_b200.head import decode_head
+
+    for i in range(3):
+        y = decode_head(sets[i % NSETS], cfg.strides, cfg.nc)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    KD = min(K, 50)
+    torch.cuda.synchronize(dev)
+    d0.record()
+    for i in range(KD):
+        y = decode_head(sets[i % NSETS], cfg.strides, cfg.nc)
+    d1.record()
+    torch.cuda.synchronize(dev)
+    t_dense = d0.elapsed_time(d1) / KD
+    dense_bytes = B * (in_bytes_img + (4 + cfg.nc) * cfg.anchors * esize)
+    dense = {"launch_ms": t_dense, "achieved": dense_bytes / (t_dense * 1e-3) / 1e9, "unit": "GB/s",
+             "frac": dense_bytes / (t_dense * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": dense_bytes}
+    del y
+
+    # ---- end to end through the public API with HOST buffers: H2D of the head, decode+NMS, D2H of rows+counts ---------
+    KE = min(K, 30)
+    host_sets = [[lv.cpu().pin_memory() for lv in s] for s in sets[:2]]
+    dev_in = [torch.empty_like(lv) for lv in sets[0]]
+    host_rows = torch.empty(plan.rows.shape, dtype=torch.float32).pin_memory()
+    h2d = sum(lv.numel() * lv.element_size() for lv in dev_in)
+    d2h = host_rows.numel() * 4 + B * 4
+
+    def e2e_step(i):
+        for dst, src in zip(dev_in, host_sets[i % 2]):
+            dst.copy_(src, non_blocking=True)
+        p = postprocess_from_head(dev_in, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det, sync=False)
+        host_rows.copy_(p.rows, non_blocking=True)
+        from ultralytics_pro_b200.engine import fetch_counts
+
+        return fetch_counts(p.count)  # D2H + stream synchronize: the result is usable on the host here
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(KE):
+        e2e_step(i)
+    g1.record()
+    torch.cuda.synchronize(dev)
+    ems = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * KE / (float(ems.item()) * 1e-3)
+
+    # ---- p50 latency at B=1 through the public API (device-resident input, result counts on host) ---------------------
+    one = [lv[:1].contiguous() for lv in sets[0]]
+    lat = []
+    for i in range(20):
+        postprocess_from_head(one, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det)
+    for i in range(200):
+        t0 = time.perf_counter()
+        postprocess_from_head(one, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC, "batch_per_gpu": B, "global_batch": B * world,
+                       "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
+                       "cuda_graph": use_graph,
+                       "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
+                                      "of counts+rows per step on a side stream" if world > 1 else "single GPU"},
+            "clocks": sampler.summary(),
+            "gpu_launches": 2 * K,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
+                    "note": "postprocess_from_head on pinned HOST head tensors: H2D + decode+NMS + D2H of rows and counts, "
+                            "synchronised every step"},
+            "roofline": roofline,
+            "decode_dense": dense,
+            "latency_b1_ms_p50": lat[len(lat) // 2],
+            "latency_b1_ms_p90": lat[int(len(lat) * 0.9)],
+            "detections_last_step": {"kept": int(kept), "candidates": int(cand)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -26,6 +26,7 @@ EXPORTS = (
     "ypb_nms_workspace_bytes",
     "ypb_decode_dense",
     "ypb_nms_from_head",
+    "ypb_nms_from_head_stage",
     "ypb_nms_from_dense",
     "ypb_nms_boxes_workspace_bytes",
     "ypb_nms_boxes",
@@ -117,6 +118,8 @@ def load():
     lib.ypb_nms_from_head.restype = C.c_int
     lib.ypb_nms_from_head.argtypes = [C.POINTER(HeadDesc), C.c_void_p, C.c_int32, C.c_int32, C.POINTER(NmsParams),
                                       C.POINTER(NmsOut), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ypb_nms_from_head_stage.restype = C.c_int
+    lib.ypb_nms_from_head_stage.argtypes = lib.ypb_nms_from_head.argtypes + [C.c_int32]
     lib.ypb_nms_from_dense.restype = C.c_int
     lib.ypb_nms_from_dense.argtypes = [C.POINTER(DenseDesc), C.POINTER(NmsParams), C.POINTER(NmsOut), C.c_void_p,
                                        C.c_size_t, C.c_void_p]

@@ -87,20 +87,48 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.
 // torch max semantics: NaN is sticky.
 __device__ __forceinline__ float nanmax(float m, float v) { return (v > m || v != v) ? v : m; }
 
-// Expectation of the softmax over REG bins (DFL).  v[k] = logit of bin k.
+// Expectation of the softmax over 16 bins (DFL, block.py:250-253).  v[k] = logit of bin k.
+// The two sums use a FIXED butterfly association order (k ^ 8, ^ 4, ^ 2, ^ 1) with separately rounded products, so the
+// in-register version (dense kernel, one thread per anchor) and the warp-shuffle version (fused filter, 16 lanes per
+// side) are bit-identical.
+__device__ __forceinline__ float tree16(const float (&v)[16]) {
+  float a[8], b[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(v[i], v[i + 8]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = __fadd_rn(a[i], a[i + 4]);
+  return __fadd_rn(__fadd_rn(b[0], b[2]), __fadd_rn(b[1], b[3]));
+}
+
 template <int REG>
 __device__ __forceinline__ float dfl_expect(const float (&v)[REG]) {
+  static_assert(REG == 16, "only reg_max = 16 is built");
   float m = v[0];
 #pragma unroll
   for (int k = 1; k < REG; ++k) m = fmaxf(m, v[k]);
-  float den = 0.f, num = 0.f;
+  float e[REG], p[REG];
 #pragma unroll
   for (int k = 0; k < REG; ++k) {
-    float e = __expf(v[k] - m);
-    den += e;
-    num = fmaf(static_cast<float>(k), e, num);
+    e[k] = __expf(__fsub_rn(v[k], m));
+    p[k] = __fmul_rn(static_cast<float>(k), e[k]);
   }
-  return __fdividef(num, den);
+  return __fdividef(tree16(p), tree16(e));
+}
+
+// Same expectation with the 16 bins spread over 16 consecutive lanes (lane & 15 = bin); every lane of the segment
+// returns the result.  Butterfly order matches tree16.
+__device__ __forceinline__ float dfl_expect_lanes16(float v, int bin) {
+  float m = v;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float e = __expf(__fsub_rn(v, m));
+  float p = __fmul_rn(static_cast<float>(bin), e);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    e = __fadd_rn(e, __shfl_xor_sync(0xffffffffu, e, o));
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o));
+  }
+  return __fdividef(p, e);
 }
 
 struct BoxXYWH { float cx, cy, w, h; };

@@ -169,142 +169,194 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------------
 // fused decode + filter + compaction
+//
+//   phase A  (thread = VEC consecutive anchors)  stream the nc class rows with 128-bit loads, keep the max logit per
+//            anchor; candidate iff round_T(sigmoid(max)) > conf  (nms.py:76; sigmoid_f is monotone, see selftest).
+//   phase B  block-level compaction of the candidate anchors into shared memory (shuffle scan).
+//   phase C  (warp = one candidate anchor, lanes = classes / DFL bins)  exact first-argmax of the rounded scores
+//            (nms.py:120) or the multi-label row count (nms.py:115); the 4x16-bin DFL softmax expectation with
+//            16-lane shuffle butterflies, dist2bbox/dist2rbox, x stride (head.py:167-168) - only for survivors.
+//   phase D  one atomicAdd per block reserves the rows; 64-bit keys are written (unique, so order is irrelevant).
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT_IN, int DT_VAL, int VEC, int REG, bool ROT, bool MULTI>
+template <int DT_IN, int DT_VAL, int VEC, bool ROT, bool MULTI>
 __global__ void __launch_bounds__(DEC_THREADS)
 filter_from_head_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
                         const __grid_constant__ FilterArgs f) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  const int grp = blockIdx.x * DEC_THREADS + threadIdx.x;
+  constexpr int MAXC = DEC_THREADS * VEC;  // candidate anchors a block can hold
+  __shared__ int s_anchor[MAXC];           // global anchor index of each candidate
+  __shared__ float s_score[MAXC];          // single-label: best (rounded) score
+  __shared__ int s_cls[MAXC];              // single-label: its class
+  __shared__ int s_rows[MAXC];             // rows emitted by the candidate, later their exclusive offsets
+  __shared__ int s_ncand;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = blockIdx.x * DEC_THREADS + tid;
   const int b = blockIdx.y;
-  const bool active = grp < g.group_start[g.num_levels];
   const int nc = g.nc;
   const float conf = f.conf;
 
-  int l = 0, a_local = 0, a_glob = 0;
-  long long cs = 0;
-  const TI* src = nullptr;
-  const TI* csrc = nullptr;
-  int rows[VEC];    // rows this anchor emits
-  float best[VEC];  // single-label: max score (T-rounded)
-  int bcls[VEC];    // single-label: first argmax
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) { rows[i] = 0; best[i] = 0.f; bcls[i] = 0; }
-
-  if (active) {
-    l = find_level(g, grp);
-    a_local = (grp - g.group_start[l]) * VEC;
+  // ---- phase A ---------------------------------------------------------------------------------------------------
+  uint32_t flags = 0;
+  int a_glob = 0;
+  if (grp < g.group_start[g.num_levels]) {
+    const int l = find_level(g, grp);
+    const int a_local = (grp - g.group_start[l]) * VEC;
     a_glob = g.anchor_start[l] + a_local;
-    cs = g.cstride[l];
-    src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
-    csrc = src + static_cast<long long>(4 * REG) * cs;
-
-    if constexpr (MULTI) {
-      // nms.py:76 + :115: every (anchor, class) whose score > conf; an anchor with a NaN score is dropped (amax -> NaN).
-      bool has_nan[VEC];
+    const long long cs = g.cstride[l];
+    const TI* csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local + 64 * cs;
+    float mx[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) has_nan[i] = false;
+    for (int i = 0; i < VEC; ++i) mx[i] = -INFINITY;
 #pragma unroll 8
-      for (int c = 0; c < nc; ++c) {
-        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
-        const bool ok = class_allowed(f.class_mask, c);
+    for (int c = 0; c < nc; ++c) {
+      Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          float v = DType<DT_IN>::to_f(p.v[i]);
-          float s = DV::rnd(sigmoid_f(v));
-          has_nan[i] |= (v != v);
-          rows[i] += (s > conf && ok) ? 1 : 0;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i)
-        if (has_nan[i]) rows[i] = 0;
-    } else {
-      // nms.py:76: candidate iff max_c score > conf.  sigmoid_f is monotone after rounding (ypb_selftest_sigmoid_
-      // monotone), so max_c score == score(max_c logit): one sigmoid per anchor instead of nc.
-      float mx[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) mx[i] = -INFINITY;
-#pragma unroll 8
-      for (int c = 0; c < nc; ++c) {
-        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) mx[i] = nanmax(mx[i], DType<DT_IN>::to_f(p.v[i]));
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        if (DV::rnd(sigmoid_f(mx[i])) > conf) {
-          // nms.py:120: conf, j = cls.max(1) -> first index of the maximal SCORE (ties between distinct logits that
-          // round to the same score resolve to the lower class), then re-filter (:121) and class filter (:127-131).
-          float bs = -1.f;
-          int bc = 0;
-          for (int c = 0; c < nc; ++c) {
-            float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
-            if (s > bs) { bs = s; bc = c; }
-          }
-          best[i] = bs;
-          bcls[i] = bc;
-          rows[i] = (bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;
-        }
-      }
+      for (int i = 0; i < VEC; ++i) mx[i] = nanmax(mx[i], DType<DT_IN>::to_f(p.v[i]));
     }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      if (DV::rnd(sigmoid_f(mx[i])) > conf) flags |= 1u << i;  // NaN max -> false: the anchor is dropped (amax -> NaN)
   }
 
-  int my_rows = 0;
+  // ---- phase B ---------------------------------------------------------------------------------------------------
+  int total;
+  int off = block_exclusive_scan(__popc(flags), total);
+  if (total == 0) return;  // uniform
+  if (tid == 0) s_ncand = total;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) my_rows += rows[i];
+  for (int i = 0; i < VEC; ++i)
+    if (flags & (1u << i)) s_anchor[off++] = a_glob + i;
+  __syncthreads();
+  const int ncand = total;
 
-  // ---- decode only what survived (head.py:167-168 restricted to candidate anchors) ---------------------------------
-  if (my_rows > 0) {
-    float d[4][VEC];
-    load_ltrb<DT_IN, VEC, REG>(src, cs, d);
-    const int W = g.w[l];
-    const float stride = g.stride[l];
-    int gy = a_local / W, gx = a_local - gy * W;
+  // ---- phase C ---------------------------------------------------------------------------------------------------
+  for (int ci = warp; ci < ncand; ci += DEC_THREADS / 32) {
+    const int a = s_anchor[ci];
+    int l = 0;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      if (rows[i] > 0) {
+    for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+      if (i < g.num_levels && a >= g.anchor_start[i]) l = i;
+    const int a_local = a - g.anchor_start[l];
+    const long long cs = g.cstride[l];
+    const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+    const TI* csrc = src + 64 * cs;
+    int rows;
+    if constexpr (MULTI) {
+      int cnt = 0;
+      for (int c = lane; c < nc; c += 32) {
+        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
+        cnt += (s > conf && class_allowed(f.class_mask, c)) ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      rows = cnt;
+    } else {
+      // first index of the maximal rounded score (nms.py:120), then the re-filter (:121) and class filter (:127-131)
+      float bs = -1.f;
+      int bc = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {
+        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
+        if (s > bs) { bs = s; bc = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (os > bs || (os == bs && oc < bc)) { bs = os; bc = oc; }
+      }
+      rows = (bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;
+      if (lane == 0) { s_score[ci] = bs; s_cls[ci] = bc; }
+    }
+    if (lane == 0) s_rows[ci] = rows;
+    if (rows > 0) {  // warp-uniform
+      // lanes 0-15: side l (ch 0-15) and side r (ch 32-47); lanes 16-31: side t (ch 16-31) and side b (ch 48-63)
+      const float v0 = DType<DT_IN>::to_f(src[static_cast<long long>(lane) * cs]);
+      const float v1 = DType<DT_IN>::to_f(src[static_cast<long long>(lane + 32) * cs]);
+      const float e0 = dfl_expect_lanes16(v0, lane & 15);
+      const float e1 = dfl_expect_lanes16(v1, lane & 15);
+      const float dl = __shfl_sync(0xffffffffu, e0, 0), dt = __shfl_sync(0xffffffffu, e0, 16);
+      const float dr = __shfl_sync(0xffffffffu, e1, 0), db = __shfl_sync(0xffffffffu, e1, 16);
+      if (lane == 0) {
+        const int W = g.w[l];
+        const int gy = a_local / W, gx = a_local - gy * W;
         const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-        const long long slot = static_cast<long long>(b) * g.anchors + a_glob + i;
+        const float stride = g.stride[l];
+        const long long slot = static_cast<long long>(b) * g.anchors + a;
         if constexpr (ROT) {
           float t = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
           float theta = angle_is_logit ? DV::rnd(activate_angle(t)) : t;
-          BoxXYWH bx = decode_rotated(d[0][i], d[1][i], d[2][i], d[3][i], theta, ax, ay, stride);
+          BoxXYWH bx = decode_rotated(dl, dt, dr, db, theta, ax, ay, stride);
           f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
           f.cand_ang[slot] = theta;
         } else {
-          BoxXYWH bx = decode_axis_aligned(d[0][i], d[1][i], d[2][i], d[3][i], ax, ay, stride, false);
+          BoxXYWH bx = decode_axis_aligned(dl, dt, dr, db, ax, ay, stride, false);
           f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
         }
       }
-      if (++gx == W) { gx = 0; ++gy; }
     }
   }
+  __syncthreads();
 
-  // ---- compaction: one atomic per block, rows land in arbitrary order (the 64-bit keys are unique) -----------------
-  int total;
-  int off = block_exclusive_scan(my_rows, total);
-  if (total == 0) return;  // uniform
-  const int base = reserve_rows(f.row_count, b, total);
-  if (my_rows == 0) return;
-  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
-  int pos = base + off;
+  // ---- phase D ---------------------------------------------------------------------------------------------------
+  int mine[VEC], my_rows = 0;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    if (rows[i] == 0) continue;
-    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) * static_cast<uint32_t>(nc);
-    if constexpr (MULTI) {
-      for (int c = 0; c < nc; ++c) {
-        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
-        if (s > conf && class_allowed(f.class_mask, c)) {
-          if (pos < f.rows_cap) keys[pos] = make_key(s, row0 + c);
-          ++pos;
-        }
+    const int ci = tid * VEC + i;
+    mine[i] = ci < ncand ? s_rows[ci] : 0;
+    my_rows += mine[i];
+  }
+  int roff = block_exclusive_scan(my_rows, total);
+  if (total == 0) return;  // uniform
+  const int base = reserve_rows(f.row_count, b, total);
+  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+  if constexpr (!MULTI) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int ci = tid * VEC + i;
+      if (mine[i]) {
+        const int pos = base + roff;
+        if (pos < f.rows_cap)
+          keys[pos] = make_key(s_score[ci], static_cast<uint32_t>(s_anchor[ci]) * static_cast<uint32_t>(nc) + static_cast<uint32_t>(s_cls[ci]));
+        ++roff;
       }
-    } else {
-      if (pos < f.rows_cap) keys[pos] = make_key(best[i], row0 + bcls[i]);
-      ++pos;
+    }
+  } else {
+    __syncthreads();  // everyone has read s_rows
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int ci = tid * VEC + i;
+      if (ci < ncand) s_rows[ci] = base + roff;
+      roff += mine[i];
+    }
+    __syncthreads();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int ci = warp; ci < ncand; ci += DEC_THREADS / 32) {
+      const int a = s_anchor[ci];
+      int l = 0;
+#pragma unroll
+      for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+        if (i < g.num_levels && a >= g.anchor_start[i]) l = i;
+      const long long cs = g.cstride[l];
+      const TI* csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + (a - g.anchor_start[l]) + 64 * cs;
+      int pos = s_rows[ci];
+      const uint32_t row0 = static_cast<uint32_t>(a) * static_cast<uint32_t>(nc);
+      for (int c0 = 0; c0 < nc; c0 += 32) {  // class-minor order inside the anchor
+        const int c = c0 + lane;
+        float s = 0.f;
+        bool pass = false;
+        if (c < nc) {
+          s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
+          pass = s > conf && class_allowed(f.class_mask, c);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+          const int p = pos + __popc(bal & lt_mask);
+          if (p < f.rows_cap) keys[p] = make_key(s, row0 + c);
+        }
+        pos += __popc(bal);
+      }
     }
   }
 }
@@ -445,7 +497,7 @@ static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, in
                                         cudaStream_t st) {
   const int groups = g.group_start[g.num_levels];
   dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
-#define YPB_FH(R, M) filter_from_head_kernel<DT_IN, DT_VAL, VEC, 16, R, M><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
+#define YPB_FH(R, M) filter_from_head_kernel<DT_IN, DT_VAL, VEC, R, M><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
   if (f.rotated) { if (f.multi_label) YPB_FH(true, true); else YPB_FH(true, false); }
   else           { if (f.multi_label) YPB_FH(false, true); else YPB_FH(false, false); }
 #undef YPB_FH

@@ -17,8 +17,11 @@ namespace ypb {
 
 constexpr int NT = 512;              // threads per CTA
 constexpr int NW = NT / 32;          // warps per CTA
-constexpr int CH = NT;               // ranks per chunk
+constexpr int CH = 128;              // ranks per chunk
+constexpr int CW = CH / 32;          // mask words per rank of a chunk
+constexpr int PARTS = NT / CH;       // threads cooperating on one rank (== CW: part q owns mask word q)
 constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
+static_assert(PARTS == CW, "one thread per (rank, mask word)");
 
 struct __align__(16) Smem {
   union {
@@ -28,7 +31,7 @@ struct __align__(16) Smem {
       uint32_t wc[NW * 256];
     } rx;
   } u;
-  uint32_t mask[NW * CH];  // mask[w * CH + t]: bit i set iff rank (w*32+i) of the chunk suppresses rank t
+  uint32_t mask[CW * CH];  // mask[w * CH + t]: bit i set iff rank (w*32+i) of the chunk suppresses rank t
   union {
     struct {
       float4 box[CH];
@@ -36,9 +39,10 @@ struct __align__(16) Smem {
     } g;
     float rec[CH * 8];
   } c;
-  uint32_t alive_bits[NW];
-  uint32_t kept_bits[NW];
-  uint32_t undec_bits[NW];
+  int dead[CH];  // rank already suppressed by a row outside the chunk
+  uint32_t alive_bits[CW];
+  uint32_t kept_bits[CW];
+  uint32_t undec_bits[CW];
   unsigned long long red_and, red_or;
 };
 
@@ -260,15 +264,18 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   const float thr = a.iou_thr;
   const uint32_t nc = static_cast<uint32_t>(a.nc);
 
+  // thread (t, q): rank t of the chunk, part q.  A warp holds 32 consecutive ranks of ONE part, so the row it tests
+  // against (kept row k, or chunk rank i) is the same for all lanes: shared/L1 broadcast loads, no divergence.
+  const int t = tid & (CH - 1);
+  const int q = tid / CH;
   int kept_n = 0;
   for (int c0 = 0; c0 < m && kept_n < a.max_det; c0 += CH) {
-    const int r = c0 + tid;
+    const int r = c0 + t;
     const bool valid = r < m;
     uint64_t key = 0;
     float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
     float area = 0.f;
     ObbRec me{};
-    bool alive = valid;
     if (valid) {
       key = sorted[r];
       const uint32_t row = key_row(key);
@@ -276,51 +283,60 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
       const float4 bx = cand_box[anchor];
       if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
-        me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, cand_ang[anchor]);  // nms.py:146
+        if (q == 0) me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, cand_ang[anchor]);  // nms.py:146
       } else {
         ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // nms.py:149
         area = box_area(ob);
       }
     }
+    if (q == 0) sm.dead[t] = valid ? 0 : 1;
+    bool alive;
 
     if constexpr (RULE == YPB_NMS_GREEDY) {
-      // (a) against rows kept in earlier chunks
-      if (alive) {
-        for (int k = 0; k < kept_n; ++k) {
-          if (greedy_suppresses(kept_box[k], kept_area[k], ob, area, thr)) { alive = false; break; }
-        }
-      }
-      sm.c.g.box[tid] = ob;
-      sm.c.g.area[tid] = area;
-      const unsigned ab = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) sm.alive_bits[warp] = ab;
+      if (q == 0) { sm.c.g.box[t] = ob; sm.c.g.area[t] = area; }
       __syncthreads();
-      // (b) who inside the chunk could suppress me
-      if (alive) {
-        for (int w = 0; w <= warp; ++w) {
-          uint32_t cand = sm.alive_bits[w];
-          if (w == warp) cand &= lt_mask;
-          uint32_t word = 0;
-          while (cand) {
-            const int i = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const int idx = w * 32 + i;
-            if (greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, thr)) word |= 1u << i;
-          }
-          sm.mask[w * CH + tid] = word;
-        }
+      // (a) against the rows kept in earlier chunks: part q takes every PARTS-th kept row (no early exit: ILP)
+      bool hit = false;
+      if (valid) {
+#pragma unroll 4
+        for (int k = q; k < kept_n; k += PARTS) hit |= greedy_suppresses(kept_box[k], kept_area[k], ob, area, thr);
       }
-      // (c) fix-point: kept iff no kept suppressor; dead iff some kept suppressor; wait while a suppressor is undecided
-      int status = alive ? 0 : 2;  // 0 undecided, 1 kept, 2 dead
+      if (hit) sm.dead[t] = 1;
+      __syncthreads();
+      alive = sm.dead[t] == 0;
+      if (q == 0) {
+        const unsigned ab = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) sm.alive_bits[warp] = ab;
+      }
+      __syncthreads();
+      // (b) mask word q of rank t: which alive ranks 32q..32q+31 of this chunk (ranked above t) would suppress t
+      const int tw = t >> 5;
+      if (alive && q <= tw) {
+        uint32_t word = 0;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int idx = q * 32 + i;
+          if (greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, thr)) word |= 1u << i;
+        }
+        word &= sm.alive_bits[q];
+        if (q == tw) word &= lt_mask;
+        sm.mask[q * CH + t] = word;
+      }
+      __syncthreads();
+      // (c) fix-point over the chunk (ranks owned by part 0): kept iff no kept suppressor; dead iff some kept suppressor;
+      //     wait while a possible suppressor is still undecided.  The lowest undecided rank always decides.
+      int status = (q == 0 && alive) ? 0 : 2;  // 0 undecided, 1 kept, 2 dead
       while (true) {
-        const unsigned ub = __ballot_sync(0xffffffffu, status == 0);
-        const unsigned kbits = __ballot_sync(0xffffffffu, status == 1);
-        if (lane == 0) { sm.undec_bits[warp] = ub; sm.kept_bits[warp] = kbits; }
+        if (q == 0) {
+          const unsigned ub = __ballot_sync(0xffffffffu, status == 0);
+          const unsigned kbits = __ballot_sync(0xffffffffu, status == 1);
+          if (lane == 0) { sm.undec_bits[warp] = ub; sm.kept_bits[warp] = kbits; }
+        }
         if (!__syncthreads_or(status == 0)) break;
         if (status == 0) {
           bool hit_kept = false, hit_undec = false;
-          for (int w = 0; w <= warp; ++w) {
-            const uint32_t mw = sm.mask[w * CH + tid];
+          for (int w = 0; w <= tw; ++w) {
+            const uint32_t mw = sm.mask[w * CH + t];
             hit_kept |= (mw & sm.kept_bits[w]) != 0;
             hit_undec |= (mw & sm.undec_bits[w]) != 0;
           }
@@ -331,46 +347,54 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       }
       alive = status == 1;
     } else {
-      // Fast-NMS: test against EVERY higher rank (kept or not), nms.py:221-223
-      float* my = sm.c.rec + tid * 8;
-      if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
-        my[0] = me.x; my[1] = me.y; my[2] = me.a; my[3] = me.b; my[4] = me.c; my[5] = me.det;
-      } else {
-        my[0] = ob.x; my[1] = ob.y; my[2] = ob.z; my[3] = ob.w; my[4] = area;
-      }
-      if (valid) {
-        float* gr = rec_g + static_cast<long long>(r) * 8;
+      // Fast-NMS: a rank is dropped iff ANY higher rank (kept or not) overlaps it >= thr, nms.py:221-223.
+      float* my = sm.c.rec + t * 8;
+      if (q == 0) {
+        if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+          my[0] = me.x; my[1] = me.y; my[2] = me.a; my[3] = me.b; my[4] = me.c; my[5] = me.det;
+        } else {
+          my[0] = ob.x; my[1] = ob.y; my[2] = ob.z; my[3] = ob.w; my[4] = area; my[5] = 0.f;
+        }
+        if (valid) {
+          float* gr = rec_g + static_cast<long long>(r) * 8;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) gr[k] = my[k];
+          for (int k = 0; k < 6; ++k) gr[k] = my[k];
+        }
       }
       __syncthreads();
+      if constexpr (RULE == YPB_NMS_FAST_PROBIOU) me = ObbRec{my[0], my[1], my[2], my[3], my[4], my[5]};
+      bool hit = false;
       if (valid) {
-        for (int i = 0; i < r && alive; ++i) {
-          const float* q = i < c0 ? rec_g + static_cast<long long>(i) * 8 : sm.c.rec + (i - c0) * 8;
+        for (int i = q; i < r; i += PARTS) {
+          const float* o = i < c0 ? rec_g + static_cast<long long>(i) * 8 : sm.c.rec + (i - c0) * 8;
           if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
-            ObbRec hi{q[0], q[1], q[2], q[3], q[4], q[5]};
-            if (probiou_suppresses(hi, me, thr)) alive = false;
+            ObbRec hi{o[0], o[1], o[2], o[3], o[4], o[5]};
+            hit |= probiou_suppresses(hi, me, thr);
           } else {
-            float4 hb = make_float4(q[0], q[1], q[2], q[3]);
-            if (boxiou_suppresses(hb, q[4], ob, area, thr)) alive = false;
+            hit |= boxiou_suppresses(make_float4(o[0], o[1], o[2], o[3]), o[4], ob, area, thr);
           }
         }
       }
-      const unsigned kbits = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) sm.kept_bits[warp] = kbits;
+      if (hit) sm.dead[t] = 1;
+      __syncthreads();
+      alive = q == 0 && sm.dead[t] == 0;
+      if (q == 0) {
+        const unsigned kbits = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) sm.kept_bits[warp] = kbits;
+      }
       __syncthreads();
     }
 
-    // (d) append the chunk's kept rows in rank order
+    // (d) append the chunk's kept rows in rank order (part 0 owns the ranks)
     int before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
+    for (int w = 0; w < CW; ++w) {
       const int pc = __popc(sm.kept_bits[w]);
-      if (w < warp) before += pc;
+      if (w < (t >> 5)) before += pc;
       total += pc;
     }
-    if (alive) {
-      const int pos = kept_n + before + __popc(sm.kept_bits[warp] & lt_mask);
+    if (q == 0 && alive) {
+      const int pos = kept_n + before + __popc(sm.kept_bits[t >> 5] & lt_mask);
       if (pos < a.max_det) {
         kept_key[pos] = key;
         if constexpr (RULE == YPB_NMS_GREEDY) { kept_box[pos] = ob; kept_area[pos] = area; }
@@ -418,12 +442,20 @@ __global__ void boxes_prep_kernel(const float* __restrict__ boxes, const float* 
 
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
   const size_t smem = sizeof(Smem);
-  cudaError_t e;
-#define YPB_SS(R)                                                                                              \
-  do {                                                                                                         \
-    e = cudaFuncSetAttribute(sort_suppress_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                            \
-    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(a);                                                     \
+  // opt in to > 48 KB dynamic shared memory once per (device, rule); not a stream operation, safe under graph capture
+  static bool configured[64][3] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (a.rule < 0 || a.rule > 2) return cudaErrorInvalidValue;
+  const bool need_cfg = dev < 0 || dev >= 64 || !configured[dev][a.rule];
+#define YPB_SS(R)                                                                                                \
+  do {                                                                                                           \
+    if (need_cfg) {                                                                                              \
+      e = cudaFuncSetAttribute(sort_suppress_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(a);                                                       \
   } while (0)
   switch (a.rule) {
     case YPB_NMS_GREEDY: YPB_SS(YPB_NMS_GREEDY); break;
@@ -432,6 +464,7 @@ cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
     default: return cudaErrorInvalidValue;
   }
 #undef YPB_SS
+  if (dev >= 0 && dev < 64) configured[dev][a.rule] = true;
   return cudaGetLastError();
 }
 

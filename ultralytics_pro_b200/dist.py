@@ -1,0 +1,64 @@
+"""Batch sharding over the GPUs of one node and the result gather.
+
+Images are independent (the reference loops over them, nms.py:91), so each rank post-processes a contiguous slice of
+the batch with no exchange during compute - the same partition the reference's DDP validation uses
+(data/build.py:171-188 ``ContiguousDistributedSampler``).  The only collective is the gather of the per-image counts
+and the fixed-stride detection rows, mirroring ``dist.gather_object(stats)`` in models/yolo/detect/val.py:226-240 but
+as ONE packed all_gather (<= B*(max_det*(6+extra)+1)*4 bytes) instead of pickled Python objects.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch: int, rank: int, world: int):
+    """Contiguous [lo, hi) slice of the batch for `rank`; the remainder goes to the first ranks."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_results(rows: torch.Tensor, count: torch.Tensor, pad_batch: int | None = None) -> torch.Tensor:
+    """(b, max_det, cols) fp32 rows + (b,) int32 counts -> one (pad_batch, 1 + max_det*cols) fp32 buffer.
+
+    The count travels bit-cast in column 0, so one collective moves everything."""
+    b, max_det, cols = rows.shape
+    pb = b if pad_batch is None else pad_batch
+    packed = torch.zeros((pb, 1 + max_det * cols), dtype=torch.float32, device=rows.device)
+    packed[:b, 0] = count.view(torch.float32)
+    packed[:b, 1:] = rows.reshape(b, -1)
+    return packed
+
+
+def unpack_results(packed: torch.Tensor, max_det: int, cols: int):
+    count = packed[:, 0].contiguous().view(torch.int32)
+    rows = packed[:, 1:].reshape(packed.shape[0], max_det, cols)
+    return rows, count
+
+
+def gather_results(rows: torch.Tensor, count: torch.Tensor, batch: int, group=None, out: torch.Tensor | None = None,
+                   async_op: bool = False):
+    """all_gather the per-rank shards into the full-batch (B, max_det, cols) rows and (B,) counts on every rank.
+
+    rows/count are this rank's shard (shard_range order).  Returns (rows, count) or, with async_op, (work, finish)
+    where finish() -> (rows, count).
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    _, max_det, cols = rows.shape
+    per = -(-batch // world)  # padded shard size
+    packed = pack_results(rows, count, per)
+    full = out if out is not None else torch.empty((world * per, packed.shape[1]), dtype=torch.float32, device=rows.device)
+    work = dist.all_gather_into_tensor(full, packed, group=group, async_op=async_op)
+
+    def finish():
+        pieces = []
+        for r in range(world):
+            lo, hi = shard_range(batch, r, world)
+            pieces.append(full[r * per: r * per + (hi - lo)])
+        return unpack_results(torch.cat(pieces, 0), max_det, cols)
+
+    if async_op:
+        return work, finish
+    return finish()

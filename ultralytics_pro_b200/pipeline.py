@@ -1,0 +1,86 @@
+"""Fixed-geometry post-processor: descriptors, scratch and result buffers built once, optional CUDA-graph replay.
+
+``postprocess_from_head`` rebuilds its plan on every call (fine for a predictor loop).  A serving loop that sees the
+same head geometry every step uses this class instead: one C-ABI call (or one graph launch) per batch, no host
+allocation, no host synchronisation until ``results()``.  One instance serves one stream at a time (its result
+buffers and scratch are reused from call to call).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi, engine
+from .nms import _greedy_threshold
+
+
+class HeadPostProcessor:
+    def __init__(self, nc: int, strides, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
+                 agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
+                 max_wh: int = 7680, reg_max: int = 16, rotated: bool = False):
+        assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+        assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+        self.nc, self.strides, self.reg_max = nc, tuple(float(s) for s in strides), reg_max
+        self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
+        self.classes, self.agnostic, self.multi_label = classes, agnostic, bool(multi_label) and nc > 1
+        self.max_det, self.max_nms, self.max_wh, self.rotated = max_det, max_nms, max_wh, rotated
+        self._plans = {}
+        self.last = None
+
+    def _plan_for(self, levels, anchors):
+        lv0 = levels[0]
+        key = (lv0.device.index, lv0.dtype, lv0.shape[0], anchors)
+        plan = self._plans.get(key)
+        if plan is None:
+            conf_t = _cabi.round_to_dtype(self.conf_thres, lv0.dtype)
+            if self.rotated:
+                rule, iou_eff = _cabi.RULE_FAST_PROBIOU, _cabi.f32_round(self.iou_thres)
+            else:
+                rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(self.iou_thres)
+            plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
+                                    iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
+                                    self.multi_label, rule, self.classes)
+            # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
+            nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
+                                                          plan.params.max_det, plan.params.max_nms, plan.params.rule)
+            plan.scratch = torch.empty(nbytes, dtype=torch.uint8, device=lv0.device)
+            self._plans[key] = plan
+        return plan
+
+    def enqueue(self, levels, angle_logits=None, stage: int = 0):
+        """Launch decode+NMS for one batch on the current stream; returns the device-resident plan (no sync)."""
+        desc, keep, anchors = engine.head_desc(levels, self.strides, self.nc, self.reg_max)
+        plan = self._plan_for(keep, anchors)
+        ang = None
+        if self.rotated:
+            if angle_logits is None:
+                raise ValueError("rotated post-processor needs angle_logits")
+            ang = angle_logits.reshape(keep[0].shape[0], anchors)
+            if not ang.is_contiguous() or ang.dtype != keep[0].dtype:
+                ang = ang.to(keep[0].dtype).contiguous()
+        lib = _cabi.load()
+        dev = keep[0].device
+        rc = lib.ypb_nms_from_head_stage(C.byref(desc), ang.data_ptr() if ang is not None else None, 1, desc.dtype,
+                                         C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
+                                         plan.scratch.numel(), _cabi.stream_ptr(dev), stage)
+        _cabi.check(rc, "ypb_nms_from_head_stage")
+        self.last = plan
+        return plan
+
+    def capture(self, levels, angle_logits=None) -> "torch.cuda.CUDAGraph":
+        """Capture one batch's launches into a CUDA graph bound to these input tensors (static addresses)."""
+        self.enqueue(levels, angle_logits)  # warm: attributes set, plan built, scratch allocated
+        torch.cuda.current_stream(levels[0].device).synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.enqueue(levels, angle_logits)
+        return graph
+
+    def __call__(self, levels, angle_logits=None, return_idxs: bool = False):
+        return engine.split_results(self.enqueue(levels, angle_logits), return_idxs)
+
+    def results(self, return_idxs: bool = False):
+        if self.last is None:
+            raise RuntimeError("nothing enqueued yet")
+        return engine.split_results(self.last, return_idxs)
