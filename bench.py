@@ -39,6 +39,15 @@ def _peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _traffic(dtype):
+    """dram bytes per launch of the roofline kernel from the committed ncu capture (profiles/roofline_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh).get(dtype)
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -284,27 +293,29 @@ def run_ours(args):
 
     # ---- per-kernel timing with CUDA events on the launching stream (roofline of the dominant kernel) ---------------
     KI = min(K, 200)
-    e = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KI)]
+    e = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(KI)]
     for i in range(3):
-        post.enqueue(sets[i % NSETS], stage=1)
-        post.enqueue(sets[i % NSETS], stage=2)
+        for stage in (1, 2, 4):
+            post.enqueue(sets[i % NSETS], stage=stage)
     torch.cuda.synchronize(dev)
     for i in range(KI):
-        e[i][0].record()
-        post.enqueue(sets[i % NSETS], stage=1)
-        e[i][1].record()
-        post.enqueue(sets[i % NSETS], stage=2)
-        e[i][2].record()
+        for j, stage in enumerate((1, 2, 4)):
+            e[i][j].record()
+            post.enqueue(sets[i % NSETS], stage=stage)
+        e[i][3].record()
     torch.cuda.synchronize(dev)
-    t_filter = sum(a.elapsed_time(b) for a, b, _ in e) / KI  # ms: memset + fused decode/filter kernel
-    t_suppr = sum(b.elapsed_time(c) for _, b, c in e) / KI   # ms: sort + suppress + gather kernel
+    t_scan = sum(ev[0].elapsed_time(ev[1]) for ev in e) / KI    # ms: counter memset + class-scan/filter kernel
+    t_decode = sum(ev[1].elapsed_time(ev[2]) for ev in e) / KI  # ms: survivor box-decode kernel
+    t_suppr = sum(ev[2].elapsed_time(ev[3]) for ev in e) / KI   # ms: sort + suppress + gather kernel
     peak, peak_src = _peaks()
-    algo_bytes = B * in_bytes_img
-    achieved = algo_bytes / (t_filter * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "filter_from_head_kernel (fused DFL decode + sigmoid + confidence filter + compaction)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                "launch_ms": t_filter, "other_kernels_ms": {"sort_suppress_kernel": t_suppr}}
+    scan_bytes = B * cfg.nc * cfg.anchors * esize  # the class rows: what this kernel must read
+    achieved = scan_bytes / (t_scan * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "scan_classes_kernel (class scan + sigmoid/confidence filter + compaction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(args.dtype),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
+                "algorithmic_bytes_full_head": B * in_bytes_img,
+                "launch_ms": t_scan,
+                "other_kernels_ms": {"decode_candidates_kernel": t_decode, "sort_suppress_kernel": t_suppr}}
 
     # ---- dense decode kernel alone (the Detect._inference drop-in), same inputs --------------------------------------
     from ultralytics_pro_b200.head import decode_head
@@ -381,7 +392,7 @@ def run_ours(args):
                        "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
                                       "of counts+rows per step on a side stream" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
-            "gpu_launches": 2 * K,
+            "gpu_launches": 3 * K,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
                     "note": "postprocess_from_head on pinned HOST head tensors: H2D + decode+NMS + D2H of rows and counts, "
                             "synchronised every step"},

@@ -131,9 +131,10 @@ YPB_API int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int3
                       const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
                       void* stream);
 
-/* Same call restricted to one stage, for per-kernel timing with CUDA events (bench.py roofline) and profiling:
- * stage 1 = clear counters + fused decode/filter/compaction kernel; stage 2 = sort + suppression + gather kernel on the
- * candidates a previous stage-1 call left in `workspace`; stage 0 = both (== ypb_nms_from_head). */
+/* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
+ * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
+ * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);
+ * 0 or 7 = all three (== ypb_nms_from_head). */
 YPB_API int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit,
                                     int32_t value_dtype, const ypb_nms_params* p, const ypb_nms_out* out,
                                     void* workspace, size_t workspace_bytes, void* stream, int32_t stage);

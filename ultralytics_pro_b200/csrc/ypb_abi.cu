@@ -148,7 +148,8 @@ int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int32_t angl
 int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
                             const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
                             void* stream, int32_t stage) {
-  if (stage < 0 || stage > 2) return fail(YPB_ERR_INVALID_ARGUMENT, "stage=%d outside [0,2]", stage);
+  if (stage < 0 || stage > 7) return fail(YPB_ERR_INVALID_ARGUMENT, "stage mask=%d outside [0,7]", stage);
+  if (stage == 0) stage = 7;
   ypb::HeadGeom g;
   int vec;
   int rc = build_geom(head, &g, &vec, nullptr, nullptr, 0, 0);
@@ -168,16 +169,25 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
   if (head->batch == 0) return YPB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (stage != 2) {
-    e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * head->batch, st);
+  if (stage & 1) {
+    e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * 2 * head->batch, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+    ypb::FilterArgs f{};
+    f.anchor_count = w.row_count + head->batch; f.anchor_list = w.anchor_list;
+    f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
+    f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+    e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "scan_classes");
+  }
+  if (stage & 2) {
     ypb::FilterArgs f{};
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-    e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, st);
-    if (e != cudaSuccess) return cuda_fail(e, "filter_from_head");
+    f.anchor_count = w.row_count + head->batch; f.anchor_list = w.anchor_list;
+    e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
+    if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }
-  if (stage != 1) {
+  if (stage & 4) {
     ypb::SuppressArgs s = suppress_args(p, out, w, head->batch, g.anchors);
     e = ypb::launch_sort_suppress(s, st);
     if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");

@@ -189,7 +189,8 @@ constexpr uint64_t KEY_SENTINEL = ~0ull;
 // workspace carve-up (all offsets 256-byte aligned)
 // ---------------------------------------------------------------------------------------------------------------
 struct Workspace {
-  int32_t* row_count;  // [B]            rows emitted by the filter (atomic)
+  int32_t* row_count;  // [2B]           [0,B): rows emitted by the filter (atomic); [B,2B): candidate anchors
+  int32_t* anchor_list;  // [B][A]       anchors whose box the fused path must decode
   uint64_t* keys_a;    // [B][rows_cap]
   uint64_t* keys_b;    // [B][rows_cap]  radix ping-pong
   float4* cand_box;    // [B][A]         box of each candidate anchor (xyxy, or xywh when rotated), un-offset
@@ -213,7 +214,8 @@ __host__ inline Workspace carve_workspace(void* base, int batch, int anchors, in
     return p;
   };
   size_t B = static_cast<size_t>(batch);
-  w.row_count = reinterpret_cast<int32_t*>(take(B * sizeof(int32_t)));
+  w.row_count = reinterpret_cast<int32_t*>(take(2 * B * sizeof(int32_t)));
+  w.anchor_list = reinterpret_cast<int32_t*>(take(B * anchors * sizeof(int32_t)));
   w.keys_a = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
   w.keys_b = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
   w.cand_box = reinterpret_cast<float4*>(take(B * anchors * sizeof(float4)));
@@ -246,6 +248,8 @@ struct FilterArgs {
   int nc, multi_label, rotated, rows_cap;
   const uint32_t* class_mask;
   int32_t* row_count;
+  int32_t* anchor_count;
+  int32_t* anchor_list;
   uint64_t* keys;
   float4* cand_box;
   float* cand_ang;
@@ -278,8 +282,9 @@ struct SuppressArgs {
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
                                 int vec, cudaStream_t st);
+// which: 1 = class scan + compaction kernel, 2 = survivor box-decode kernel
 cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_dtype, const void* angle,
-                                    int angle_is_logit, const FilterArgs& f, int vec, cudaStream_t st);
+                                    int angle_is_logit, const FilterArgs& f, int vec, int which, cudaStream_t st);
 cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st);
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,

@@ -1,12 +1,13 @@
 // Decode-side kernels of libyolopost_b200 (sm_100a):
 //   decode_dense_kernel       Detect._inference drop-in (head.py:151-169, OBB head.py:1026-1042)
-//   filter_from_head_kernel   fused decode + confidence filter + compaction (head.py:151-169 + nms.py:76-131)
+//   scan_classes_kernel       fused path 1/2: class scan + confidence filter + compaction (nms.py:76-131)
+//   decode_candidates_kernel  fused path 2/2: DFL box decode of the survivors only, warp-shuffle softmax (head.py:167-168)
 //   filter_from_dense_kernel  confidence filter + compaction of an already decoded tensor (nms.py:76-131)
 //
 // Layout facts the mapping is built on: every head level is (B, 4*reg_max+nc, H, W) with the H*W anchors contiguous,
 // so lanes map to ANCHORS (coalesced, 128-bit per lane) and the 16 DFL bins / nc classes of an anchor are walked by
-// the owning thread down the channel stride.  The bins sit on the slow axis, so the softmax is an in-register
-// reduction; warp shuffles are used where lanes really cooperate (the compaction scan).
+// the owning thread down the channel stride when a kernel touches EVERY anchor (dense decode, class scan).  The sparse
+// survivor decode instead puts the 16 DFL bins on 16 lanes and reduces with shuffle butterflies.
 #include "ypb_common.cuh"
 
 namespace ypb {
@@ -168,122 +169,185 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused decode + filter + compaction
+// fused path, kernel 1: class scan + confidence filter + compaction (nms.py:76-131 evaluated on head.py:169's scores
+// without ever materialising them)
 //
-//   phase A  (thread = VEC consecutive anchors)  stream the nc class rows with 128-bit loads, keep the max logit per
-//            anchor; candidate iff round_T(sigmoid(max)) > conf  (nms.py:76; sigmoid_f is monotone, see selftest).
-//   phase B  block-level compaction of the candidate anchors into shared memory (shuffle scan).
-//   phase C  (warp = one candidate anchor, lanes = classes / DFL bins)  exact first-argmax of the rounded scores
-//            (nms.py:120) or the multi-label row count (nms.py:115); the 4x16-bin DFL softmax expectation with
-//            16-lane shuffle butterflies, dist2bbox/dist2rbox, x stride (head.py:167-168) - only for survivors.
-//   phase D  one atomicAdd per block reserves the rows; 64-bit keys are written (unique, so order is irrelevant).
+//   thread = VEC consecutive anchors; the nc class rows are streamed once with 128-bit loads.
+//   single-label: track per anchor the max logit m, its first index and the runner-up m2.  sigmoid_f is monotone after
+//     rounding (ypb_selftest_sigmoid_monotone), so  max_c score == round_T(sigmoid(m))  and, unless the runner-up rounds
+//     to the same score, the first argmax of the scores (nms.py:120) is the first argmax of the logits.  The rare tie is
+//     resolved by re-reading the anchor's classes.  One sigmoid per ANCHOR instead of per (anchor, class).
+//   multi-label: every (anchor, class) with score > conf is a row (nms.py:115): count in the streaming pass, then
+//     re-read the survivors' classes to write the keys.
+//   Output: unique 64-bit sort keys (row order irrelevant) + the list of anchors whose box must be decoded.
+//   One atomicAdd pair per block.
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT_IN, int DT_VAL, int VEC, bool ROT, bool MULTI>
+template <int DT_IN, int DT_VAL, int VEC, bool MULTI>
 __global__ void __launch_bounds__(DEC_THREADS)
-filter_from_head_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
-                        const __grid_constant__ FilterArgs f) {
+scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ FilterArgs f) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  constexpr int MAXC = DEC_THREADS * VEC;  // candidate anchors a block can hold
-  __shared__ int s_anchor[MAXC];           // global anchor index of each candidate
-  __shared__ float s_score[MAXC];          // single-label: best (rounded) score
-  __shared__ int s_cls[MAXC];              // single-label: its class
-  __shared__ int s_rows[MAXC];             // rows emitted by the candidate, later their exclusive offsets
-  __shared__ int s_ncand;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_base[2];
+  const int tid = threadIdx.x;
   const int grp = blockIdx.x * DEC_THREADS + tid;
   const int b = blockIdx.y;
   const int nc = g.nc;
   const float conf = f.conf;
 
-  // ---- phase A ---------------------------------------------------------------------------------------------------
-  uint32_t flags = 0;
+  int rows[VEC];
+  float score[VEC];
+  int cls[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { rows[i] = 0; score[i] = 0.f; cls[i] = 0; }
   int a_glob = 0;
+  long long cs = 0;
+  const TI* csrc = nullptr;
+
   if (grp < g.group_start[g.num_levels]) {
     const int l = find_level(g, grp);
     const int a_local = (grp - g.group_start[l]) * VEC;
     a_glob = g.anchor_start[l] + a_local;
-    const long long cs = g.cstride[l];
-    const TI* csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local + 64 * cs;
-    float mx[VEC];
+    cs = g.cstride[l];
+    csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local + 64 * cs;
+    if constexpr (MULTI) {
+      bool has_nan[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) mx[i] = -INFINITY;
+      for (int i = 0; i < VEC; ++i) has_nan[i] = false;
 #pragma unroll 8
-    for (int c = 0; c < nc; ++c) {
-      Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+      for (int c = 0; c < nc; ++c) {
+        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+        const bool ok = class_allowed(f.class_mask, c);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) mx[i] = nanmax(mx[i], DType<DT_IN>::to_f(p.v[i]));
+        for (int i = 0; i < VEC; ++i) {
+          float v = DType<DT_IN>::to_f(p.v[i]);
+          has_nan[i] |= (v != v);
+          rows[i] += (DV::rnd(sigmoid_f(v)) > conf && ok) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (has_nan[i]) rows[i] = 0;  // amax -> NaN -> the anchor is not a candidate (nms.py:76)
+    } else {
+      float m[VEC], m2[VEC];
+      bool has_nan[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { m[i] = -INFINITY; m2[i] = -INFINITY; has_nan[i] = false; }
+#pragma unroll 8
+      for (int c = 0; c < nc; ++c) {
+        Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          float v = DType<DT_IN>::to_f(p.v[i]);
+          has_nan[i] |= (v != v);
+          if (v > m[i]) { m2[i] = m[i]; m[i] = v; cls[i] = c; }
+          else m2[i] = fmaxf(m2[i], v);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float s = DV::rnd(sigmoid_f(m[i]));
+        if (!has_nan[i] && s > conf) {
+          if (DV::rnd(sigmoid_f(m2[i])) == s) {
+            // runner-up rounds to the same score: take the FIRST class that reaches it (nms.py:120)
+            for (int c = 0; c < cls[i]; ++c) {
+              if (DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i]))) == s) { cls[i] = c; break; }
+            }
+          }
+          score[i] = s;
+          rows[i] = class_allowed(f.class_mask, cls[i]) ? 1 : 0;  // nms.py:127-131
+        }
+      }
     }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-      if (DV::rnd(sigmoid_f(mx[i])) > conf) flags |= 1u << i;  // NaN max -> false: the anchor is dropped (amax -> NaN)
   }
 
-  // ---- phase B ---------------------------------------------------------------------------------------------------
-  int total;
-  int off = block_exclusive_scan(__popc(flags), total);
-  if (total == 0) return;  // uniform
-  if (tid == 0) s_ncand = total;
+  int my_rows = 0, my_anchors = 0;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i)
-    if (flags & (1u << i)) s_anchor[off++] = a_glob + i;
+  for (int i = 0; i < VEC; ++i) { my_rows += rows[i]; my_anchors += rows[i] > 0 ? 1 : 0; }
+  int total_rows, total_anchors;
+  int roff = block_exclusive_scan(my_rows, total_rows);
+  if (total_rows == 0) return;  // uniform
+  int aoff = MULTI ? block_exclusive_scan(my_anchors, total_anchors) : roff;
+  if (!MULTI) total_anchors = total_rows;
+  if (tid == 0) {
+    s_base[0] = atomicAdd(&f.row_count[b], total_rows);
+    s_base[1] = atomicAdd(&f.anchor_count[b], total_anchors);
+  }
   __syncthreads();
-  const int ncand = total;
-
-  // ---- phase C ---------------------------------------------------------------------------------------------------
-  for (int ci = warp; ci < ncand; ci += DEC_THREADS / 32) {
-    const int a = s_anchor[ci];
-    int l = 0;
+  if (my_rows == 0) return;
+  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+  int* alist = f.anchor_list + static_cast<long long>(b) * g.anchors;
+  int rpos = s_base[0] + roff, apos = s_base[1] + aoff;
 #pragma unroll
-    for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-      if (i < g.num_levels && a >= g.anchor_start[i]) l = i;
-    const int a_local = a - g.anchor_start[l];
-    const long long cs = g.cstride[l];
-    const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
-    const TI* csrc = src + 64 * cs;
-    int rows;
+  for (int i = 0; i < VEC; ++i) {
+    if (rows[i] == 0) continue;
+    alist[apos++] = a_glob + i;
+    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) * static_cast<uint32_t>(nc);
     if constexpr (MULTI) {
-      int cnt = 0;
-      for (int c = lane; c < nc; c += 32) {
-        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
-        cnt += (s > conf && class_allowed(f.class_mask, c)) ? 1 : 0;
+      for (int c = 0; c < nc; ++c) {
+        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
+        if (s > conf && class_allowed(f.class_mask, c)) {
+          if (rpos < f.rows_cap) keys[rpos] = make_key(s, row0 + c);
+          ++rpos;
+        }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      rows = cnt;
     } else {
-      // first index of the maximal rounded score (nms.py:120), then the re-filter (:121) and class filter (:127-131)
-      float bs = -1.f;
-      int bc = 0x7fffffff;
-      for (int c = lane; c < nc; c += 32) {
-        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
-        if (s > bs) { bs = s; bc = c; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float os = __shfl_xor_sync(0xffffffffu, bs, o);
-        int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-        if (os > bs || (os == bs && oc < bc)) { bs = os; bc = oc; }
-      }
-      rows = (bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;
-      if (lane == 0) { s_score[ci] = bs; s_cls[ci] = bc; }
+      if (rpos < f.rows_cap) keys[rpos] = make_key(score[i], row0 + cls[i]);
+      ++rpos;
     }
-    if (lane == 0) s_rows[ci] = rows;
-    if (rows > 0) {  // warp-uniform
-      // lanes 0-15: side l (ch 0-15) and side r (ch 32-47); lanes 16-31: side t (ch 16-31) and side b (ch 48-63)
-      const float v0 = DType<DT_IN>::to_f(src[static_cast<long long>(lane) * cs]);
-      const float v1 = DType<DT_IN>::to_f(src[static_cast<long long>(lane + 32) * cs]);
-      const float e0 = dfl_expect_lanes16(v0, lane & 15);
-      const float e1 = dfl_expect_lanes16(v1, lane & 15);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused path, kernel 2: box decode of the surviving anchors only (head.py:167-168 restricted to candidates)
+//
+//   warp = one candidate anchor; lane = (side pair, bin): lanes 0-15 hold sides l and r, lanes 16-31 sides t and b.
+//   The 16-bin DFL softmax expectation is a 16-lane shuffle butterfly (block.py:250-253); lane 0 finishes
+//   dist2bbox / dist2rbox, x stride, rounds through the value dtype and converts to corners (nms.py:86).
+//   Warps are spread over the whole GPU, so images with many candidates do not serialise on one CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT_IN, int DT_VAL, bool ROT, int UNROLL>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_candidates_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                         const __grid_constant__ FilterArgs f) {
+  using TI = typename DType<DT_IN>::type;
+  using DV = DType<DT_VAL>;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int warps_per_image = gridDim.x * (DEC_THREADS / 32);
+  const int wid = blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5);
+  const int n = min(f.anchor_count[b], g.anchors);
+  const int* alist = f.anchor_list + static_cast<long long>(b) * g.anchors;
+
+  for (int c0 = wid * UNROLL; c0 < n; c0 += warps_per_image * UNROLL) {
+    int a[UNROLL], l[UNROLL], a_local[UNROLL];
+    float v0[UNROLL], v1[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {  // issue every load of the batch before the first use
+      const int ci = min(c0 + u, n - 1);
+      a[u] = alist[ci];
+      int lv = 0;
+#pragma unroll
+      for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+        if (i < g.num_levels && a[u] >= g.anchor_start[i]) lv = i;
+      l[u] = lv;
+      a_local[u] = a[u] - g.anchor_start[lv];
+      const long long cs = g.cstride[lv];
+      const TI* src = static_cast<const TI*>(g.ptr[lv]) + static_cast<long long>(b) * g.bstride[lv] + a_local[u];
+      v0[u] = DType<DT_IN>::to_f(src[static_cast<long long>(lane) * cs]);
+      v1[u] = DType<DT_IN>::to_f(src[static_cast<long long>(lane + 32) * cs]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float e0 = dfl_expect_lanes16(v0[u], lane & 15);
+      const float e1 = dfl_expect_lanes16(v1[u], lane & 15);
       const float dl = __shfl_sync(0xffffffffu, e0, 0), dt = __shfl_sync(0xffffffffu, e0, 16);
       const float dr = __shfl_sync(0xffffffffu, e1, 0), db = __shfl_sync(0xffffffffu, e1, 16);
-      if (lane == 0) {
-        const int W = g.w[l];
-        const int gy = a_local / W, gx = a_local - gy * W;
+      if (lane == 0 && c0 + u < n) {
+        const int W = g.w[l[u]];
+        const int gy = a_local[u] / W, gx = a_local[u] - gy * W;
         const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-        const float stride = g.stride[l];
-        const long long slot = static_cast<long long>(b) * g.anchors + a;
+        const float stride = g.stride[l[u]];
+        const long long slot = static_cast<long long>(b) * g.anchors + a[u];
         if constexpr (ROT) {
           float t = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
           float theta = angle_is_logit ? DV::rnd(activate_angle(t)) : t;
@@ -294,68 +358,6 @@ filter_from_head_kernel(const __grid_constant__ HeadGeom g, const void* __restri
           BoxXYWH bx = decode_axis_aligned(dl, dt, dr, db, ax, ay, stride, false);
           f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
         }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase D ---------------------------------------------------------------------------------------------------
-  int mine[VEC], my_rows = 0;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int ci = tid * VEC + i;
-    mine[i] = ci < ncand ? s_rows[ci] : 0;
-    my_rows += mine[i];
-  }
-  int roff = block_exclusive_scan(my_rows, total);
-  if (total == 0) return;  // uniform
-  const int base = reserve_rows(f.row_count, b, total);
-  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
-  if constexpr (!MULTI) {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int ci = tid * VEC + i;
-      if (mine[i]) {
-        const int pos = base + roff;
-        if (pos < f.rows_cap)
-          keys[pos] = make_key(s_score[ci], static_cast<uint32_t>(s_anchor[ci]) * static_cast<uint32_t>(nc) + static_cast<uint32_t>(s_cls[ci]));
-        ++roff;
-      }
-    }
-  } else {
-    __syncthreads();  // everyone has read s_rows
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int ci = tid * VEC + i;
-      if (ci < ncand) s_rows[ci] = base + roff;
-      roff += mine[i];
-    }
-    __syncthreads();
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int ci = warp; ci < ncand; ci += DEC_THREADS / 32) {
-      const int a = s_anchor[ci];
-      int l = 0;
-#pragma unroll
-      for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-        if (i < g.num_levels && a >= g.anchor_start[i]) l = i;
-      const long long cs = g.cstride[l];
-      const TI* csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + (a - g.anchor_start[l]) + 64 * cs;
-      int pos = s_rows[ci];
-      const uint32_t row0 = static_cast<uint32_t>(a) * static_cast<uint32_t>(nc);
-      for (int c0 = 0; c0 < nc; c0 += 32) {  // class-minor order inside the anchor
-        const int c = c0 + lane;
-        float s = 0.f;
-        bool pass = false;
-        if (c < nc) {
-          s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs])));
-          pass = s > conf && class_allowed(f.class_mask, c);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-          const int p = pos + __popc(bal & lt_mask);
-          if (p < f.rows_cap) keys[p] = make_key(s, row0 + c);
-        }
-        pos += __popc(bal);
       }
     }
   }
@@ -494,20 +496,28 @@ cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* ang
 
 template <int DT_IN, int DT_VAL, int VEC>
 static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, int angle_is_logit, const FilterArgs& f,
-                                        cudaStream_t st) {
-  const int groups = g.group_start[g.num_levels];
-  dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
-#define YPB_FH(R, M) filter_from_head_kernel<DT_IN, DT_VAL, VEC, R, M><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
-  if (f.rotated) { if (f.multi_label) YPB_FH(true, true); else YPB_FH(true, false); }
-  else           { if (f.multi_label) YPB_FH(false, true); else YPB_FH(false, false); }
-#undef YPB_FH
+                                        int which, cudaStream_t st) {
+  if (which == 1) {
+    const int groups = g.group_start[g.num_levels];
+    dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
+    if (f.multi_label) scan_classes_kernel<DT_IN, DT_VAL, VEC, true><<<grid, DEC_THREADS, 0, st>>>(g, f);
+    else               scan_classes_kernel<DT_IN, DT_VAL, VEC, false><<<grid, DEC_THREADS, 0, st>>>(g, f);
+    return cudaGetLastError();
+  }
+  // kernel 2: enough warps per image to cover the GPU (148 SMs x 16 warps) whatever the batch size
+  int blocks_per_image = (148 * 4 + g.batch - 1) / g.batch;
+  if (blocks_per_image > 64) blocks_per_image = 64;
+  if (blocks_per_image < 1) blocks_per_image = 1;
+  dim3 grid2(blocks_per_image, g.batch);
+  if (f.rotated) decode_candidates_kernel<DT_IN, DT_VAL, true, 2><<<grid2, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f);
+  else           decode_candidates_kernel<DT_IN, DT_VAL, false, 2><<<grid2, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f);
   return cudaGetLastError();
 }
 
 cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_dtype, const void* angle,
-                                    int angle_is_logit, const FilterArgs& f, int vec, cudaStream_t st) {
+                                    int angle_is_logit, const FilterArgs& f, int vec, int which, cudaStream_t st) {
   if (in_dtype != value_dtype) return cudaErrorInvalidValue;
-#define YPB_FD(DT, V) return filter_head_dispatch<DT, DT, V>(g, angle, angle_is_logit, f, st)
+#define YPB_FD(DT, V) return filter_head_dispatch<DT, DT, V>(g, angle, angle_is_logit, f, which, st)
   if (in_dtype == YPB_F32) {
     if (vec == 4) YPB_FD(YPB_F32, 4);
     if (vec == 1) YPB_FD(YPB_F32, 1);
