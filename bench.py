@@ -305,7 +305,7 @@ def run_ours(args):
         e[i][3].record()
     torch.cuda.synchronize(dev)
     t_scan = sum(ev[0].elapsed_time(ev[1]) for ev in e) / KI    # ms: counter memset + class-scan/filter kernel
-    t_decode = sum(ev[1].elapsed_time(ev[2]) for ev in e) / KI  # ms: survivor box-decode kernel
+    t_decode = sum(ev[1].elapsed_time(ev[2]) for ev in e) / KI  # ms: survivor tile box-decode kernel
     t_suppr = sum(ev[2].elapsed_time(ev[3]) for ev in e) / KI   # ms: sort + suppress + gather kernel
     peak, peak_src = _peaks()
     scan_bytes = B * cfg.nc * cfg.anchors * esize  # the class rows: what this kernel must read
@@ -315,7 +315,7 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
                 "algorithmic_bytes_full_head": B * in_bytes_img,
                 "launch_ms": t_scan,
-                "other_kernels_ms": {"decode_candidates_kernel": t_decode, "sort_suppress_kernel": t_suppr}}
+                "other_kernels_ms": {"decode_tiles_kernel": t_decode, "sort_suppress_kernel": t_suppr}}
 
     # ---- dense decode kernel alone (the Detect._inference drop-in), same inputs --------------------------------------
     from ultralytics_pro_b200.head import decode_head

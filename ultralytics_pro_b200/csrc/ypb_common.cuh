@@ -189,8 +189,9 @@ constexpr uint64_t KEY_SENTINEL = ~0ull;
 // workspace carve-up (all offsets 256-byte aligned)
 // ---------------------------------------------------------------------------------------------------------------
 struct Workspace {
-  int32_t* row_count;  // [2B]           [0,B): rows emitted by the filter (atomic); [B,2B): candidate anchors
-  int32_t* anchor_list;  // [B][A]       anchors whose box the fused path must decode
+  int32_t* row_count;  // [B+1]          [0,B): rows emitted by the filter (atomic); [B]: number of tiles to decode
+  int32_t* tile_list;  // [B*tiles]      128-anchor tiles (one warp's span) holding a survivor
+  uint8_t* tile_flags; // [B*tiles*32]   per lane: which of its VEC anchors survived
   uint64_t* keys_a;    // [B][rows_cap]
   uint64_t* keys_b;    // [B][rows_cap]  radix ping-pong
   float4* cand_box;    // [B][A]         box of each candidate anchor (xyxy, or xywh when rotated), un-offset
@@ -214,8 +215,11 @@ __host__ inline Workspace carve_workspace(void* base, int batch, int anchors, in
     return p;
   };
   size_t B = static_cast<size_t>(batch);
-  w.row_count = reinterpret_cast<int32_t*>(take(2 * B * sizeof(int32_t)));
-  w.anchor_list = reinterpret_cast<int32_t*>(take(B * anchors * sizeof(int32_t)));
+  w.row_count = reinterpret_cast<int32_t*>(take((B + 1) * sizeof(int32_t)));
+  // a tile spans >= 32 anchors (VEC >= 1) and every image adds at most 4 partial tiles per CTA row: A/32 + 8 bounds it
+  const size_t tiles = B * (static_cast<size_t>(anchors) / 32 + 8);
+  w.tile_list = reinterpret_cast<int32_t*>(take(tiles * sizeof(int32_t)));
+  w.tile_flags = reinterpret_cast<uint8_t*>(take(tiles * 32));
   w.keys_a = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
   w.keys_b = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
   w.cand_box = reinterpret_cast<float4*>(take(B * anchors * sizeof(float4)));
@@ -248,8 +252,9 @@ struct FilterArgs {
   int nc, multi_label, rotated, rows_cap;
   const uint32_t* class_mask;
   int32_t* row_count;
-  int32_t* anchor_count;
-  int32_t* anchor_list;
+  int32_t* tile_count;
+  int32_t* tile_list;
+  uint8_t* tile_flags;
   uint64_t* keys;
   float4* cand_box;
   float* cand_ang;

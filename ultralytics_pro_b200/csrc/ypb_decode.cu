@@ -1,14 +1,13 @@
 // Decode-side kernels of libyolopost_b200 (sm_100a):
 //   decode_dense_kernel       Detect._inference drop-in (head.py:151-169, OBB head.py:1026-1042)
-//   scan_classes_kernel       fused path 1/2: streaming class scan + confidence pre-filter + anchor compaction (nms.py:76)
-//   decode_candidates_kernel  fused path 2/2: per-survivor class argmax / rows (nms.py:112-131) and DFL box decode with
-//                             warp-shuffle softmax (head.py:167-168)
+//   scan_classes_kernel       fused path 1/2: streaming class scan + confidence filter + row compaction (nms.py:76-131)
+//   decode_tiles_kernel       fused path 2/2: DFL box decode of the 128-anchor tiles that hold a survivor (head.py:167-168)
 //   filter_from_dense_kernel  confidence filter + compaction of an already decoded tensor (nms.py:76-131)
 //
 // Layout facts the mapping is built on: every head level is (B, 4*reg_max+nc, H, W) with the H*W anchors contiguous,
 // so lanes map to ANCHORS (coalesced, 128-bit per lane) and the 16 DFL bins / nc classes of an anchor are walked by
-// the owning thread down the channel stride when a kernel touches EVERY anchor (dense decode, class scan).  The sparse
-// survivor decode instead puts the 16 DFL bins on 16 lanes and reduces with shuffle butterflies.
+// the owning thread down the channel stride.  (A lane-per-channel mapping for the sparse survivors was measured and
+// rejected: every lane then touches its own 128-byte line and the kernel is bound by L1TEX wavefronts, profiles/.)
 #include "ypb_common.cuh"
 
 namespace ypb {
@@ -188,14 +187,18 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused path, kernel 1: streaming confidence pre-filter (nms.py:76 evaluated on head.py:169's scores without ever
-// materialising them)
+// fused path, kernel 1: class scan + confidence filter + compaction (nms.py:76-131 evaluated on head.py:169's scores
+// without ever materialising them)
 //
-//   thread = VEC consecutive anchors; the nc class rows are streamed once with 128-bit loads, DEPTH loads in flight, one
-//   NaN-propagating max per element.  sigmoid_f is monotone after rounding (ypb_selftest_sigmoid_monotone), so
-//   max_c round_T(sigmoid(l_c)) == round_T(sigmoid(max_c l_c)): ONE sigmoid per anchor decides candidacy, and a NaN
-//   logit makes the anchor a non-candidate exactly as amax(1) > conf does.  Survivors (a few % of the anchors) are
-//   compacted into a per-image anchor list: shuffle scan inside the block, one atomicAdd per block.
+//   thread = VEC consecutive anchors; the nc class rows are streamed once with 128-bit loads, DEPTH loads in flight.
+//   single-label: per anchor the max logit m (NaN-propagating), its first index and the runner-up m2: 5 ALU ops per
+//     element, no transcendental.  sigmoid_f is monotone after rounding (ypb_selftest_sigmoid_monotone), so
+//     max_c score == round_T(sigmoid(m)) - ONE sigmoid per anchor - and unless the runner-up rounds to the same score
+//     the first argmax of the scores (nms.py:120) is the first argmax of the logits; the rare tie re-reads the anchor.
+//   multi-label: every (anchor, class) with score > conf is a row (nms.py:115): counted in the streaming pass, the
+//     survivors' classes are re-read to write the keys.
+//   Output: unique 64-bit sort keys (row order irrelevant: one atomicAdd per block reserves the slots) and the list of
+//   128-anchor tiles (one warp's span) that contain a survivor, with a per-lane flag byte, for kernel 2.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float max_nan(float a, float b) {
   float r;
@@ -203,191 +206,188 @@ __device__ __forceinline__ float max_nan(float a, float b) {
   return r;
 }
 
-template <int DT_IN, int DT_VAL, int VEC>
+template <int DT_IN, int DT_VAL, int VEC, bool MULTI>
 __global__ void __launch_bounds__(DEC_THREADS)
 scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ FilterArgs f) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  __shared__ int s_base;
-  const int tid = threadIdx.x;
+  __shared__ int s_base[2];
+  __shared__ int s_active[DEC_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = blockIdx.x * DEC_THREADS + tid;
   const int b = blockIdx.y;
-  uint32_t flags = 0;
+  const int nc = g.nc;
+  const float conf = f.conf;
+
+  int rows[VEC];
+  float score[VEC];
+  int cls[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { rows[i] = 0; score[i] = 0.f; cls[i] = 0; }
   int a_glob = 0;
+  long long cs = 0;
+  const TI* csrc = nullptr;
+
   if (grp < g.group_start[g.num_levels]) {
     const int l = find_level(g, grp);
     const int a_local = (grp - g.group_start[l]) * VEC;
     a_glob = g.anchor_start[l] + a_local;
-    const long long cs = g.cstride[l];
-    const TI* csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local + 64 * cs;
-    float m[VEC];
+    cs = g.cstride[l];
+    csrc = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local + 64 * cs;
+    if constexpr (MULTI) {
+      float nanacc[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) m[i] = -INFINITY;
-    auto visit = [&](const Pack<TI, VEC>& p, int) {
+      for (int i = 0; i < VEC; ++i) nanacc[i] = -INFINITY;
+      auto visit = [&](const Pack<TI, VEC>& p, int c) {
+        const bool ok = class_allowed(f.class_mask, c);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) m[i] = max_nan(m[i], DType<DT_IN>::to_f(p.v[i]));
-    };
-    stream_rows<TI, VEC>(csrc, cs, g.nc, visit);
+        for (int i = 0; i < VEC; ++i) {
+          float v = DType<DT_IN>::to_f(p.v[i]);
+          nanacc[i] = max_nan(nanacc[i], v);
+          rows[i] += (DV::rnd(sigmoid_f(v)) > conf && ok) ? 1 : 0;
+        }
+      };
+      stream_rows<TI, VEC>(csrc, cs, nc, visit);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i)
-      if (DV::rnd(sigmoid_f(m[i])) > f.conf) flags |= 1u << i;
+      for (int i = 0; i < VEC; ++i)
+        if (nanacc[i] != nanacc[i]) rows[i] = 0;  // amax -> NaN -> the anchor is not a candidate (nms.py:76)
+    } else {
+      float m[VEC], m2[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { m[i] = -INFINITY; m2[i] = -INFINITY; }
+      auto visit = [&](const Pack<TI, VEC>& p, int c) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float v = DType<DT_IN>::to_f(p.v[i]);
+          const bool gt = v > m[i];
+          m2[i] = fmaxf(m2[i], fminf(m[i], v));
+          m[i] = max_nan(m[i], v);
+          cls[i] = gt ? c : cls[i];
+        }
+      };
+      stream_rows<TI, VEC>(csrc, cs, nc, visit);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float s = DV::rnd(sigmoid_f(m[i]));
+        if (s > conf) {  // false for a NaN max
+          if (DV::rnd(sigmoid_f(m2[i])) == s) {
+            // the runner-up rounds to the same score: take the FIRST class that reaches it (nms.py:120)
+            for (int c = 0; c < cls[i]; ++c) {
+              if (DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i]))) == s) { cls[i] = c; break; }
+            }
+          }
+          score[i] = s;
+          rows[i] = class_allowed(f.class_mask, cls[i]) ? 1 : 0;  // nms.py:127-131
+        }
+      }
+    }
   }
-  int total;
-  int off = block_exclusive_scan(__popc(flags), total);
-  if (total == 0) return;  // uniform
-  if (tid == 0) s_base = atomicAdd(&f.anchor_count[b], total);
-  __syncthreads();
-  int* alist = f.anchor_list + static_cast<long long>(b) * g.anchors + s_base + off;
+
+  int my_rows = 0;
+  uint32_t flags = 0;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i)
-    if (flags & (1u << i)) *alist++ = a_glob + i;
+  for (int i = 0; i < VEC; ++i) { my_rows += rows[i]; flags |= rows[i] > 0 ? 1u << i : 0u; }
+  const bool warp_active = __ballot_sync(0xffffffffu, flags != 0) != 0;
+  if (lane == 0) s_active[warp] = warp_active ? 1 : 0;
+  int total_rows;
+  int roff = block_exclusive_scan(my_rows, total_rows);  // contains a __syncthreads
+  if (total_rows == 0) return;  // uniform
+  if (tid == 0) {
+    int act = 0;
+#pragma unroll
+    for (int w = 0; w < DEC_THREADS / 32; ++w) act += s_active[w];
+    s_base[0] = atomicAdd(&f.row_count[b], total_rows);
+    s_base[1] = atomicAdd(f.tile_count, act);
+  }
+  __syncthreads();
+  if (warp_active) {
+    int rank = 0;
+    for (int w = 0; w < warp; ++w) rank += s_active[w];
+    const int tile = b * static_cast<int>(gridDim.x * (DEC_THREADS / 32)) + blockIdx.x * (DEC_THREADS / 32) + warp;
+    if (lane == 0) f.tile_list[s_base[1] + rank] = tile;
+    f.tile_flags[static_cast<long long>(tile) * 32 + lane] = static_cast<uint8_t>(flags);
+  }
+  if (my_rows == 0) return;
+  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+  int rpos = s_base[0] + roff;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (rows[i] == 0) continue;
+    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) * static_cast<uint32_t>(nc);
+    if constexpr (MULTI) {
+      for (int c = 0; c < nc; ++c) {
+        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
+        if (s > conf && class_allowed(f.class_mask, c)) {
+          if (rpos < f.rows_cap) keys[rpos] = make_key(s, row0 + c);
+          ++rpos;
+        }
+      }
+    } else {
+      if (rpos < f.rows_cap) keys[rpos] = make_key(score[i], row0 + cls[i]);
+      ++rpos;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused path, kernel 2: everything that only survivors need (nms.py:112-131 + head.py:167-168 restricted to them)
+// fused path, kernel 2: box decode of the tiles that hold a survivor (head.py:167-168 restricted to them)
 //
-//   warp = one candidate anchor, warps spread over the whole GPU (no per-image serialisation).
-//   lanes = classes: exact first-argmax of the rounded scores (nms.py:120), or the multi-label rows (nms.py:115), the
-//           re-filter (:121) and the class filter (:127-131); rows get their slot with one atomicAdd per anchor.
-//   lanes = (side pair, bin): lanes 0-15 hold sides l and r, lanes 16-31 sides t and b; the 16-bin DFL softmax
-//           expectation is a 16-lane shuffle butterfly (block.py:250-253); lane 0 finishes dist2bbox / dist2rbox,
-//           x stride, rounds through the value dtype and converts to corners (nms.py:86).
-//   UNROLL candidates are in flight per warp: all their loads are issued before the first use.
+//   CTA = one 128-anchor tile per iteration (grid-stride over the tile list kernel 1 built); the tile is read with the
+//   same coalesced mapping as kernel 1 (lane = VEC consecutive anchors).  Warp w owns side w (l, t, r, b): its 16 bin
+//   rows are 16 independent 128-bit loads in flight, the softmax expectation (block.py:250-253) is an in-register
+//   reduction for the flagged anchors only, the four sides meet in shared memory and warp 0 finishes dist2bbox /
+//   dist2rbox, x stride, rounding through the value dtype and the corner conversion (nms.py:86).
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT_IN, int DT_VAL, bool ROT, bool MULTI, int UNROLL>
+template <int DT_IN, int DT_VAL, int VEC, bool ROT>
 __global__ void __launch_bounds__(DEC_THREADS)
-decode_candidates_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
-                         const __grid_constant__ FilterArgs f) {
+decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                    const __grid_constant__ FilterArgs f, int tiles_per_image) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  constexpr int MAXCPL = 4;  // classes per lane kept in registers (nc <= 128); larger nc re-reads in a loop
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const int b = blockIdx.y;
-  const int nc = g.nc;
-  const float conf = f.conf;
-  const int warps_per_image = gridDim.x * (DEC_THREADS / 32);
-  const int wid = blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5);
-  const int n = min(f.anchor_count[b], g.anchors);
-  const int* alist = f.anchor_list + static_cast<long long>(b) * g.anchors;
-  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
-  const bool small_nc = nc <= 32 * MAXCPL;
-
-  for (int c0 = wid * UNROLL; c0 < n; c0 += warps_per_image * UNROLL) {
-    int a[UNROLL], lv[UNROLL], a_local[UNROLL];
-    const TI* src[UNROLL];
-    long long cs[UNROLL];
-    float v0[UNROLL], v1[UNROLL], cl[UNROLL][MAXCPL];
+  __shared__ float s_d[4][32 * VEC];
+  const int lane = threadIdx.x & 31, side = threadIdx.x >> 5;
+  const int ntiles = min(*f.tile_count, tiles_per_image * g.batch);
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tile = f.tile_list[t];
+    const int b = tile / tiles_per_image;
+    const int grp = (tile - b * tiles_per_image) * 32 + lane;
+    const uint32_t flags = f.tile_flags[static_cast<long long>(tile) * 32 + lane];
+    int l = 0, a_local = 0, a_glob = 0;
+    if (flags) {  // flagged lanes are always inside the image
+      l = find_level(g, grp);
+      a_local = (grp - g.group_start[l]) * VEC;
+      a_glob = g.anchor_start[l] + a_local;
+      const long long cs = g.cstride[l];
+      const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local +
+                      static_cast<long long>(side * 16) * cs;
+      Pack<TI, VEC> raw[16];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int ci = min(c0 + u, n - 1);
-      a[u] = alist[ci];
-    }
+      for (int k = 0; k < 16; ++k) raw[k] = load_pack<TI, VEC>(src + static_cast<long long>(k) * cs);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {  // issue every load of the batch before the first use
-      int l = 0;
+      for (int i = 0; i < VEC; ++i) {
+        if (flags & (1u << i)) {
+          float v[16];
 #pragma unroll
-      for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-        if (i < g.num_levels && a[u] >= g.anchor_start[i]) l = i;
-      lv[u] = l;
-      a_local[u] = a[u] - g.anchor_start[l];
-      cs[u] = g.cstride[l];
-      src[u] = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local[u];
-      v0[u] = DType<DT_IN>::to_f(src[u][static_cast<long long>(lane) * cs[u]]);
-      v1[u] = DType<DT_IN>::to_f(src[u][static_cast<long long>(lane + 32) * cs[u]]);
-      if (small_nc) {
-#pragma unroll
-        for (int j = 0; j < MAXCPL; ++j) {
-          const int c = lane + 32 * j;
-          cl[u][j] = c < nc ? DType<DT_IN>::to_f(src[u][static_cast<long long>(64 + c) * cs[u]]) : 0.f;
+          for (int k = 0; k < 16; ++k) v[k] = DType<DT_IN>::to_f(raw[k].v[i]);
+          s_d[side][lane * VEC + i] = dfl_expect<16>(v);
         }
       }
     }
+    __syncthreads();
+    if (side == 0 && flags) {
+      const int W = g.w[l];
+      const float stride = g.stride[l];
+      int gy = a_local / W, gx = a_local - gy * W;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const bool live = c0 + u < n;  // warp-uniform
-      const TI* csrc = src[u] + 64 * cs[u];
-      const uint32_t row0 = static_cast<uint32_t>(a[u]) * static_cast<uint32_t>(nc);
-      int rows = 0;
-      if constexpr (MULTI) {
-        // nms.py:115: rows in class-minor order; slot = base + rank of the class among the passing ones
-        int cnt = 0;
-        for (int cb = 0; cb < nc; cb += 32) {
-          const int c = cb + lane;
-          bool pass = false;
-          if (c < nc) {
-            const float v = small_nc ? cl[u][cb >> 5] : DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs[u]]);
-            pass = DV::rnd(sigmoid_f(v)) > conf && class_allowed(f.class_mask, c);
-          }
-          cnt += __popc(__ballot_sync(0xffffffffu, pass));
-        }
-        rows = live ? cnt : 0;
-        if (rows > 0) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&f.row_count[b], rows);
-          int pos = __shfl_sync(0xffffffffu, base, 0);
-          for (int cb = 0; cb < nc; cb += 32) {
-            const int c = cb + lane;
-            bool pass = false;
-            float s = 0.f;
-            if (c < nc) {
-              const float v = small_nc ? cl[u][cb >> 5] : DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs[u]]);
-              s = DV::rnd(sigmoid_f(v));
-              pass = s > conf && class_allowed(f.class_mask, c);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) {
-              const int p = pos + __popc(bal & lt_mask);
-              if (p < f.rows_cap) keys[p] = make_key(s, row0 + c);
-            }
-            pos += __popc(bal);
-          }
-        }
-      } else {
-        // nms.py:120: first index of the maximal rounded score
-        float bs = -1.f;
-        int bc = 0x7fffffff;
-        if (small_nc) {
-#pragma unroll
-          for (int j = 0; j < MAXCPL; ++j) {
-            const int c = lane + 32 * j;
-            if (c < nc) {
-              const float s = DV::rnd(sigmoid_f(cl[u][j]));
-              if (s > bs) { bs = s; bc = c; }
-            }
-          }
-        } else {
-          for (int c = lane; c < nc; c += 32) {
-            const float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs[u]])));
-            if (s > bs) { bs = s; bc = c; }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-          if (os > bs || (os == bs && oc < bc)) { bs = os; bc = oc; }
-        }
-        rows = (live && bs > conf && class_allowed(f.class_mask, bc)) ? 1 : 0;  // nms.py:121, :127-131
-        if (rows && lane == 0) {
-          const int p = atomicAdd(&f.row_count[b], 1);
-          if (p < f.rows_cap) keys[p] = make_key(bs, row0 + static_cast<uint32_t>(bc));
-        }
-      }
-      if (rows > 0) {  // warp-uniform
-        const float e0 = dfl_expect_lanes16(v0[u], lane & 15);
-        const float e1 = dfl_expect_lanes16(v1[u], lane & 15);
-        const float dl = __shfl_sync(0xffffffffu, e0, 0), dt = __shfl_sync(0xffffffffu, e0, 16);
-        const float dr = __shfl_sync(0xffffffffu, e1, 0), db = __shfl_sync(0xffffffffu, e1, 16);
-        if (lane == 0) {
-          const int W = g.w[lv[u]];
-          const int gy = a_local[u] / W, gx = a_local[u] - gy * W;
+      for (int i = 0; i < VEC; ++i) {
+        if (flags & (1u << i)) {
+          const int e = lane * VEC + i;
+          const float dl = s_d[0][e], dt = s_d[1][e], dr = s_d[2][e], db = s_d[3][e];
           const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-          const float stride = g.stride[lv[u]];
-          const long long slot = static_cast<long long>(b) * g.anchors + a[u];
+          const long long slot = static_cast<long long>(b) * g.anchors + a_glob + i;
           if constexpr (ROT) {
-            float t = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
-            float theta = angle_is_logit ? DV::rnd(activate_angle(t)) : t;
+            float tt = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
+            float theta = angle_is_logit ? DV::rnd(activate_angle(tt)) : tt;
             BoxXYWH bx = decode_rotated(dl, dt, dr, db, theta, ax, ay, stride);
             f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
             f.cand_ang[slot] = theta;
@@ -396,8 +396,10 @@ decode_candidates_kernel(const __grid_constant__ HeadGeom g, const void* __restr
             f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
           }
         }
+        if (++gx == W) { gx = 0; ++gy; }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -535,21 +537,22 @@ cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* ang
 template <int DT_IN, int DT_VAL, int VEC>
 static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, int angle_is_logit, const FilterArgs& f,
                                         int which, cudaStream_t st) {
+  const int groups = g.group_start[g.num_levels];
+  const int blocks_x = (groups + DEC_THREADS - 1) / DEC_THREADS;
   if (which == 1) {
-    const int groups = g.group_start[g.num_levels];
-    dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
-    scan_classes_kernel<DT_IN, DT_VAL, VEC><<<grid, DEC_THREADS, 0, st>>>(g, f);
+    dim3 grid(blocks_x, g.batch);
+    if (f.multi_label) scan_classes_kernel<DT_IN, DT_VAL, VEC, true><<<grid, DEC_THREADS, 0, st>>>(g, f);
+    else               scan_classes_kernel<DT_IN, DT_VAL, VEC, false><<<grid, DEC_THREADS, 0, st>>>(g, f);
     return cudaGetLastError();
   }
-  // kernel 2: enough warps per image to cover the GPU (148 SMs x 16 CTAs of 4 warps) whatever the batch size
-  int blocks_per_image = (148 * 16 + g.batch - 1) / g.batch;
-  if (blocks_per_image > 64) blocks_per_image = 64;
-  if (blocks_per_image < 1) blocks_per_image = 1;
-  dim3 grid2(blocks_per_image, g.batch);
-#define YPB_DC(R, M) decode_candidates_kernel<DT_IN, DT_VAL, R, M, 2><<<grid2, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
-  if (f.rotated) { if (f.multi_label) YPB_DC(true, true); else YPB_DC(true, false); }
-  else           { if (f.multi_label) YPB_DC(false, true); else YPB_DC(false, false); }
-#undef YPB_DC
+  // kernel 2: grid-stride over the tile list; enough CTAs to cover the GPU, never more than there are tiles
+  const int tiles_per_image = blocks_x * (DEC_THREADS / 32);
+  long long max_tiles = static_cast<long long>(tiles_per_image) * g.batch;
+  int blocks = 148 * 8;
+  if (blocks > max_tiles) blocks = static_cast<int>(max_tiles);
+  if (blocks < 1) blocks = 1;
+  if (f.rotated) decode_tiles_kernel<DT_IN, DT_VAL, VEC, true><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);
+  else           decode_tiles_kernel<DT_IN, DT_VAL, VEC, false><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);
   return cudaGetLastError();
 }
 
