@@ -1,7 +1,7 @@
 // Decode-side kernels of libyolopost_b200 (sm_100a):
 //   decode_dense_kernel       Detect._inference drop-in (head.py:151-169, OBB head.py:1026-1042)
 //   scan_classes_kernel       fused path 1/2: streaming class scan + confidence filter + row compaction (nms.py:76-131)
-//   decode_tiles_kernel       fused path 2/2: DFL box decode of the 128-anchor tiles that hold a survivor (head.py:167-168)
+//   decode_tiles_kernel       fused path 2/2: DFL box decode of the 32-anchor sub-tiles that hold a survivor (head.py:167-168)
 //   filter_from_dense_kernel  confidence filter + compaction of an already decoded tensor (nms.py:76-131)
 //
 // Layout facts the mapping is built on: every head level is (B, 4*reg_max+nc, H, W) with the H*W anchors contiguous,
@@ -198,7 +198,7 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 //   multi-label: every (anchor, class) with score > conf is a row (nms.py:115): counted in the streaming pass, the
 //     survivors' classes are re-read to write the keys.
 //   Output: unique 64-bit sort keys (row order irrelevant: one atomicAdd per block reserves the slots) and the list of
-//   128-anchor tiles (one warp's span) that contain a survivor, with a per-lane flag byte, for kernel 2.
+//   32-anchor sub-tiles that contain a survivor, with a per-lane flag byte, for kernel 2.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float max_nan(float a, float b) {
   float r;
@@ -287,8 +287,14 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
   uint32_t flags = 0;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { my_rows += rows[i]; flags |= rows[i] > 0 ? 1u << i : 0u; }
-  const bool warp_active = __ballot_sync(0xffffffffu, flags != 0) != 0;
-  if (lane == 0) s_active[warp] = warp_active ? 1 : 0;
+  // 32-anchor sub-tiles of this warp's span (LPT lanes each) that hold a survivor: kernel 2's work list
+  constexpr int LPT = 32 / VEC;
+  const unsigned bal = __ballot_sync(0xffffffffu, flags != 0);
+  uint32_t sub_mask = 0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    if ((bal >> (j * LPT)) & ((LPT == 32) ? 0xffffffffu : ((1u << LPT) - 1u))) sub_mask |= 1u << j;
+  if (lane == 0) s_active[warp] = __popc(sub_mask);
   int total_rows;
   int roff = block_exclusive_scan(my_rows, total_rows);  // contains a __syncthreads
   if (total_rows == 0) return;  // uniform
@@ -300,11 +306,12 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
     s_base[1] = atomicAdd(f.tile_count, act);
   }
   __syncthreads();
-  if (warp_active) {
+  if (sub_mask) {
     int rank = 0;
     for (int w = 0; w < warp; ++w) rank += s_active[w];
     const int tile = b * static_cast<int>(gridDim.x * (DEC_THREADS / 32)) + blockIdx.x * (DEC_THREADS / 32) + warp;
-    if (lane == 0) f.tile_list[s_base[1] + rank] = tile;
+    if (lane < VEC && ((sub_mask >> lane) & 1u))
+      f.tile_list[s_base[1] + rank + __popc(sub_mask & ((1u << lane) - 1u))] = tile * VEC + lane;
     f.tile_flags[static_cast<long long>(tile) * 32 + lane] = static_cast<uint8_t>(flags);
   }
   if (my_rows == 0) return;
@@ -330,12 +337,11 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused path, kernel 2: box decode of the tiles that hold a survivor (head.py:167-168 restricted to them)
+// fused path, kernel 2: box decode of the 32-anchor sub-tiles that hold a survivor (head.py:167-168 restricted to them)
 //
-//   CTA = one 128-anchor tile per iteration (grid-stride over the tile list kernel 1 built); the tile is read with the
-//   same coalesced mapping as kernel 1 (lane = VEC consecutive anchors).  Warp w owns side w (l, t, r, b): its 16 bin
-//   rows are 16 independent 128-bit loads in flight, the softmax expectation (block.py:250-253) is an in-register
-//   reduction for the flagged anchors only, the four sides meet in shared memory and warp 0 finishes dist2bbox /
+//   warp = one sub-tile per iteration (grid-stride over the list kernel 1 built), lane = one anchor: every bin row is
+//   one coalesced 128-byte line per warp, all 64 rows are independent loads in flight, and the 4 x 16-bin softmax
+//   expectation (block.py:250-253) is an in-register reduction that flagged lanes alone execute.  Then dist2bbox /
 //   dist2rbox, x stride, rounding through the value dtype and the corner conversion (nms.py:86).
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT_IN, int DT_VAL, int VEC, bool ROT>
@@ -344,62 +350,46 @@ decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
                     const __grid_constant__ FilterArgs f, int tiles_per_image) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  __shared__ float s_d[4][32 * VEC];
-  const int lane = threadIdx.x & 31, side = threadIdx.x >> 5;
-  const int ntiles = min(*f.tile_count, tiles_per_image * g.batch);
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int tile = f.tile_list[t];
+  constexpr int LPT = 32 / VEC;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (DEC_THREADS / 32);
+  const int ntiles = min(*f.tile_count, tiles_per_image * g.batch * VEC);
+  for (int t = blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5); t < ntiles; t += nwarps) {
+    const int st = f.tile_list[t];
+    const int tile = st / VEC, j = st - tile * VEC;
     const int b = tile / tiles_per_image;
-    const int grp = (tile - b * tiles_per_image) * 32 + lane;
-    const uint32_t flags = f.tile_flags[static_cast<long long>(tile) * 32 + lane];
-    int l = 0, a_local = 0, a_glob = 0;
-    if (flags) {  // flagged lanes are always inside the image
-      l = find_level(g, grp);
-      a_local = (grp - g.group_start[l]) * VEC;
-      a_glob = g.anchor_start[l] + a_local;
-      const long long cs = g.cstride[l];
-      const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local +
-                      static_cast<long long>(side * 16) * cs;
-      Pack<TI, VEC> raw[16];
+    const int sub = j * LPT + lane / VEC;  // K1 lane (= anchor group) this anchor belongs to
+    const int i = lane % VEC;              // anchor inside the group
+    const uint32_t flags = f.tile_flags[static_cast<long long>(tile) * 32 + sub];
+    if (!((flags >> i) & 1u)) continue;    // flagged anchors are always inside the image
+    const int grp = (tile - b * tiles_per_image) * 32 + sub;
+    const int l = find_level(g, grp);
+    const int a_local = (grp - g.group_start[l]) * VEC + i;
+    const long long cs = g.cstride[l];
+    const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+    float d[4];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) raw[k] = load_pack<TI, VEC>(src + static_cast<long long>(k) * cs);
+    for (int side = 0; side < 4; ++side) {
+      float v[16];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        if (flags & (1u << i)) {
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = DType<DT_IN>::to_f(raw[k].v[i]);
-          s_d[side][lane * VEC + i] = dfl_expect<16>(v);
-        }
-      }
+      for (int k = 0; k < 16; ++k) v[k] = DType<DT_IN>::to_f(src[static_cast<long long>(side * 16 + k) * cs]);
+      d[side] = dfl_expect<16>(v);
     }
-    __syncthreads();
-    if (side == 0 && flags) {
-      const int W = g.w[l];
-      const float stride = g.stride[l];
-      int gy = a_local / W, gx = a_local - gy * W;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        if (flags & (1u << i)) {
-          const int e = lane * VEC + i;
-          const float dl = s_d[0][e], dt = s_d[1][e], dr = s_d[2][e], db = s_d[3][e];
-          const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-          const long long slot = static_cast<long long>(b) * g.anchors + a_glob + i;
-          if constexpr (ROT) {
-            float tt = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
-            float theta = angle_is_logit ? DV::rnd(activate_angle(tt)) : tt;
-            BoxXYWH bx = decode_rotated(dl, dt, dr, db, theta, ax, ay, stride);
-            f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
-            f.cand_ang[slot] = theta;
-          } else {
-            BoxXYWH bx = decode_axis_aligned(dl, dt, dr, db, ax, ay, stride, false);
-            f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
-          }
-        }
-        if (++gx == W) { gx = 0; ++gy; }
-      }
+    const int W = g.w[l];
+    const int gy = a_local / W, gx = a_local - gy * W;
+    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+    const float stride = g.stride[l];
+    const long long slot = static_cast<long long>(b) * g.anchors + g.anchor_start[l] + a_local;
+    if constexpr (ROT) {
+      float tt = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
+      float theta = angle_is_logit ? DV::rnd(activate_angle(tt)) : tt;
+      BoxXYWH bx = decode_rotated(d[0], d[1], d[2], d[3], theta, ax, ay, stride);
+      f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
+      f.cand_ang[slot] = theta;
+    } else {
+      BoxXYWH bx = decode_axis_aligned(d[0], d[1], d[2], d[3], ax, ay, stride, false);
+      f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
     }
-    __syncthreads();
   }
 }
 
@@ -547,9 +537,9 @@ static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, in
   }
   // kernel 2: grid-stride over the tile list; enough CTAs to cover the GPU, never more than there are tiles
   const int tiles_per_image = blocks_x * (DEC_THREADS / 32);
-  long long max_tiles = static_cast<long long>(tiles_per_image) * g.batch;
+  long long max_tiles = static_cast<long long>(tiles_per_image) * g.batch * VEC;
   int blocks = 148 * 8;
-  if (blocks > max_tiles) blocks = static_cast<int>(max_tiles);
+  if (blocks > (max_tiles + 3) / 4) blocks = static_cast<int>((max_tiles + 3) / 4);
   if (blocks < 1) blocks = 1;
   if (f.rotated) decode_tiles_kernel<DT_IN, DT_VAL, VEC, true><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);
   else           decode_tiles_kernel<DT_IN, DT_VAL, VEC, false><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);

@@ -21,6 +21,7 @@ constexpr int CH = 128;              // ranks per chunk
 constexpr int CW = CH / 32;          // mask words per rank of a chunk
 constexpr int PARTS = NT / CH;       // threads cooperating on one rank (== CW: part q owns mask word q)
 constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
+constexpr int KEPT_SMEM = 1024;      // kept rows held in shared memory (larger max_det spills the list to the workspace)
 static_assert(PARTS == CW, "one thread per (rank, mask word)");
 
 struct __align__(16) Smem {
@@ -40,6 +41,8 @@ struct __align__(16) Smem {
     float rec[CH * 8];
   } c;
   int dead[CH];  // rank already suppressed by a row outside the chunk
+  float4 kbox[KEPT_SMEM];  // class-offset boxes of the rows kept so far (greedy rule, max_det <= KEPT_SMEM)
+  float karea[KEPT_SMEM];
   uint32_t alive_bits[CW];
   uint32_t kept_bits[CW];
   uint32_t undec_bits[CW];
@@ -51,14 +54,28 @@ struct __align__(16) Smem {
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
 
-// torchvision nms_kernel_impl / nms.py:276-294: inter / (area_i + area_j - inter) > thr, no eps.
-__device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
-  float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-  float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-  float inter = __fmul_rn(w, h);
-  if (inter == 0.f) return false;  // quotient is +-0 or NaN: never > thr (thr >= 0)
-  float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
-  return iou > thr;
+// torchvision nms_kernel_impl / nms.py:276-294: suppress iff fl(inter / (area_i + area_j - inter)) > thr, no eps.
+// The IEEE quotient is never formed: for inter > 0 and union >= 0, round-to-nearest-even gives
+//   fl(inter/union) > thr  <=>  inter/union > mid  (or == mid when thr's mantissa is odd),  mid = (thr + next(thr)) / 2,
+// and  inter >< mid * union  is decided exactly in fp64 (25-bit x 24-bit product).  Branch-free, so the 32 pair tests of
+// a mask word pipeline.  inter == 0 gives a quotient of +-0 or NaN (never > thr >= 0); a negative union a negative
+// quotient; NaN operands compare false - all "not suppressed", as in the reference.
+struct GreedyThr {
+  double mid;
+  bool tie_up;
+};
+__device__ __forceinline__ GreedyThr make_greedy_thr(float thr) {
+  const float nxt = __uint_as_float(__float_as_uint(thr) + 1u);  // thr >= 0
+  return GreedyThr{(static_cast<double>(thr) + static_cast<double>(nxt)) * 0.5, (__float_as_uint(thr) & 1u) != 0u};
+}
+__device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, const GreedyThr& t) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+  const double di = static_cast<double>(inter), lim = t.mid * static_cast<double>(uni);
+  const bool over = t.tie_up ? di >= lim : di > lim;
+  return inter > 0.f && uni >= 0.f && over;
 }
 
 // metrics.py:54-75 with eps in the denominator, rule ">= thr" (nms.py:223).
@@ -265,25 +282,43 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   const uint32_t nc = static_cast<uint32_t>(a.nc);
 
   // thread (t, q): rank t of the chunk, part q.  A warp holds 32 consecutive ranks of ONE part, so the row it tests
-  // against (kept row k, or chunk rank i) is the same for all lanes: shared/L1 broadcast loads, no divergence.
+  // against (kept row k, or chunk rank i) is the same for all lanes: shared-memory broadcast loads, no divergence.
   const int t = tid & (CH - 1);
   const int q = tid / CH;
+  const GreedyThr gthr = make_greedy_thr(thr);
+  float4* kbox = a.max_det <= KEPT_SMEM ? sm.kbox : kept_box;
+  float* karea = a.max_det <= KEPT_SMEM ? sm.karea : kept_area;
+
+  // rank r -> (key, un-offset box); fetched one chunk ahead so the dependent global loads overlap the current chunk
+  auto fetch = [&](int r, uint64_t& key, float4& bx, float& ang) {
+    key = 0; bx = make_float4(0.f, 0.f, 0.f, 0.f); ang = 0.f;
+    if (r < m) {
+      key = sorted[r];
+      const uint32_t anchor = key_row(key) / nc;
+      bx = cand_box[anchor];
+      if constexpr (RULE == YPB_NMS_FAST_PROBIOU) ang = cand_ang[anchor];
+    }
+  };
+  uint64_t key_n; float4 bx_n; float ang_n;
+  fetch(t, key_n, bx_n, ang_n);
+
   int kept_n = 0;
   for (int c0 = 0; c0 < m && kept_n < a.max_det; c0 += CH) {
     const int r = c0 + t;
     const bool valid = r < m;
-    uint64_t key = 0;
+    const uint64_t key = key_n;
+    const float4 bx = bx_n;
+    const float ang = ang_n;
+    fetch(r + CH, key_n, bx_n, ang_n);
     float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
     float area = 0.f;
     ObbRec me{};
     if (valid) {
-      key = sorted[r];
       const uint32_t row = key_row(key);
-      const uint32_t anchor = row / nc, cls = row - anchor * nc;
+      const uint32_t cls = row - (row / nc) * nc;
       const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
-      const float4 bx = cand_box[anchor];
       if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
-        if (q == 0) me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, cand_ang[anchor]);  // nms.py:146
+        if (q == 0) me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, ang);  // nms.py:146
       } else {
         ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // nms.py:149
         area = box_area(ob);
@@ -299,7 +334,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       bool hit = false;
       if (valid) {
 #pragma unroll 4
-        for (int k = q; k < kept_n; k += PARTS) hit |= greedy_suppresses(kept_box[k], kept_area[k], ob, area, thr);
+        for (int k = q; k < kept_n; k += PARTS) hit |= greedy_suppresses(kbox[k], karea[k], ob, area, gthr);
       }
       if (hit) sm.dead[t] = 1;
       __syncthreads();
@@ -308,44 +343,55 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
         const unsigned ab = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) sm.alive_bits[warp] = ab;
       }
-      __syncthreads();
-      // (b) mask word q of rank t: which alive ranks 32q..32q+31 of this chunk (ranked above t) would suppress t
+      // (b) mask word q of rank t: which ranks 32q..32q+31 of this chunk (ranked above t) would suppress t
       const int tw = t >> 5;
       if (alive && q <= tw) {
         uint32_t word = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int idx = q * 32 + i;
-          if (greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, thr)) word |= 1u << i;
+          word |= greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, gthr) ? 1u << i : 0u;
         }
-        word &= sm.alive_bits[q];
         if (q == tw) word &= lt_mask;
         sm.mask[q * CH + t] = word;
       }
       __syncthreads();
-      // (c) fix-point over the chunk (ranks owned by part 0): kept iff no kept suppressor; dead iff some kept suppressor;
-      //     wait while a possible suppressor is still undecided.  The lowest undecided rank always decides.
-      int status = (q == 0 && alive) ? 0 : 2;  // 0 undecided, 1 kept, 2 dead
-      while (true) {
-        if (q == 0) {
-          const unsigned ub = __ballot_sync(0xffffffffu, status == 0);
-          const unsigned kbits = __ballot_sync(0xffffffffu, status == 1);
-          if (lane == 0) { sm.undec_bits[warp] = ub; sm.kept_bits[warp] = kbits; }
-        }
-        if (!__syncthreads_or(status == 0)) break;
-        if (status == 0) {
-          bool hit_kept = false, hit_undec = false;
-          for (int w = 0; w <= tw; ++w) {
-            const uint32_t mw = sm.mask[w * CH + t];
-            hit_kept |= (mw & sm.kept_bits[w]) != 0;
-            hit_undec |= (mw & sm.undec_bits[w]) != 0;
+      // (c) fix-point over the chunk inside ONE warp (no block barriers): lane owns ranks lane + 32 j.  A rank is kept
+      //     iff no kept suppressor, dead iff some kept suppressor, and waits while a possible suppressor is undecided;
+      //     the lowest undecided rank always decides, and words are settled in rank order (Gauss-Seidel).
+      if (warp == 0) {
+        uint32_t undec[CW], kept[CW], mk[CW][CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) { undec[j] = sm.alive_bits[j]; kept[j] = 0; }
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+#pragma unroll
+          for (int w = 0; w <= j; ++w) mk[j][w] = ((undec[j] >> lane) & 1u) ? (sm.mask[w * CH + lane + 32 * j] & undec[w]) : 0u;
+        bool any = true;
+        while (any) {
+          any = false;
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const bool mine = (undec[j] >> lane) & 1u;
+            uint32_t hk = 0, hu = 0;
+#pragma unroll
+            for (int w = 0; w <= j; ++w) { hk |= mk[j][w] & kept[w]; hu |= mk[j][w] & undec[w]; }
+            const unsigned kb = __ballot_sync(0xffffffffu, mine && hk == 0 && hu == 0);
+            const unsigned db = __ballot_sync(0xffffffffu, mine && hk != 0);
+            kept[j] |= kb;
+            undec[j] &= ~(kb | db);
+            any |= undec[j] != 0;
           }
-          if (hit_kept) status = 2;
-          else if (!hit_undec) status = 1;
         }
-        __syncthreads();
+        if (lane < CW) {
+          uint32_t kw = kept[0];
+#pragma unroll
+          for (int j = 1; j < CW; ++j) kw = lane == j ? kept[j] : kw;
+          sm.kept_bits[lane] = kw;
+        }
       }
-      alive = status == 1;
+      __syncthreads();
+      alive = q == 0 && ((sm.kept_bits[t >> 5] >> lane) & 1u);
     } else {
       // Fast-NMS: a rank is dropped iff ANY higher rank (kept or not) overlaps it >= thr, nms.py:221-223.
       float* my = sm.c.rec + t * 8;
@@ -397,7 +443,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       const int pos = kept_n + before + __popc(sm.kept_bits[t >> 5] & lt_mask);
       if (pos < a.max_det) {
         kept_key[pos] = key;
-        if constexpr (RULE == YPB_NMS_GREEDY) { kept_box[pos] = ob; kept_area[pos] = area; }
+        if constexpr (RULE == YPB_NMS_GREEDY) { kbox[pos] = ob; karea[pos] = area; }
       }
     }
     kept_n = min(a.max_det, kept_n + total);
