@@ -173,7 +173,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * (head->batch + 1), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
     ypb::FilterArgs f{};
-    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags;
+    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
@@ -183,7 +183,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     ypb::FilterArgs f{};
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags;
+    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }

@@ -190,8 +190,9 @@ constexpr uint64_t KEY_SENTINEL = ~0ull;
 // ---------------------------------------------------------------------------------------------------------------
 struct Workspace {
   int32_t* row_count;  // [B+1]          [0,B): rows emitted by the filter (atomic); [B]: number of tiles to decode
-  int32_t* tile_list;  // [B*(A/32+32)]  32-anchor sub-tiles holding a survivor
+  int32_t* tile_list;  // [tile_cap]     octets (8 consecutive anchors) holding a survivor
   uint8_t* tile_flags; // [B*(A+128)]    per kernel-1 lane (anchor group): which of its VEC anchors survived
+  int tile_cap;
   uint64_t* keys_a;    // [B][rows_cap]
   uint64_t* keys_b;    // [B][rows_cap]  radix ping-pong
   float4* cand_box;    // [B][A]         box of each candidate anchor (xyxy, or xywh when rotated), un-offset
@@ -216,10 +217,10 @@ __host__ inline Workspace carve_workspace(void* base, int batch, int anchors, in
   };
   size_t B = static_cast<size_t>(batch);
   w.row_count = reinterpret_cast<int32_t*>(take((B + 1) * sizeof(int32_t)));
-  // kernel 1 runs ceil(A/(128 VEC)) CTAs of 4 warps per image; each warp owns VEC sub-tiles of 32 anchors and 32 flag bytes
-  const size_t sub_tiles = B * (static_cast<size_t>(anchors) / 32 + 32);
+  // kernel 1 runs G <= A/VEC + 127 lanes per image, one flag byte each; an octet is 8 anchors: <= A/8 + 128 per image
+  w.tile_cap = static_cast<int>(B * (static_cast<size_t>(anchors) / 8 + 128));
   const size_t flag_bytes = B * (static_cast<size_t>(anchors) + 128);
-  w.tile_list = reinterpret_cast<int32_t*>(take(sub_tiles * sizeof(int32_t)));
+  w.tile_list = reinterpret_cast<int32_t*>(take(static_cast<size_t>(w.tile_cap) * sizeof(int32_t)));
   w.tile_flags = reinterpret_cast<uint8_t*>(take(flag_bytes));
   w.keys_a = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
   w.keys_b = reinterpret_cast<uint64_t*>(take(B * rows_cap * sizeof(uint64_t)));
@@ -256,6 +257,7 @@ struct FilterArgs {
   int32_t* tile_count;
   int32_t* tile_list;
   uint8_t* tile_flags;
+  int tile_cap;
   uint64_t* keys;
   float4* cand_box;
   float* cand_ang;

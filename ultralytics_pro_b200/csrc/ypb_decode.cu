@@ -1,7 +1,7 @@
 // Decode-side kernels of libyolopost_b200 (sm_100a):
 //   decode_dense_kernel       Detect._inference drop-in (head.py:151-169, OBB head.py:1026-1042)
 //   scan_classes_kernel       fused path 1/2: streaming class scan + confidence filter + row compaction (nms.py:76-131)
-//   decode_tiles_kernel       fused path 2/2: DFL box decode of the 32-anchor sub-tiles that hold a survivor (head.py:167-168)
+//   decode_tiles_kernel       fused path 2/2: DFL box decode of the octets (8 anchors) that hold a survivor (head.py:167-168)
 //   filter_from_dense_kernel  confidence filter + compaction of an already decoded tensor (nms.py:76-131)
 //
 // Layout facts the mapping is built on: every head level is (B, 4*reg_max+nc, H, W) with the H*W anchors contiguous,
@@ -198,7 +198,7 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 //   multi-label: every (anchor, class) with score > conf is a row (nms.py:115): counted in the streaming pass, the
 //     survivors' classes are re-read to write the keys.
 //   Output: unique 64-bit sort keys (row order irrelevant: one atomicAdd per block reserves the slots) and the list of
-//   32-anchor sub-tiles that contain a survivor, with a per-lane flag byte, for kernel 2.
+//   octets (8 anchors) that contain a survivor, with a per-lane flag byte, for kernel 2.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float max_nan(float a, float b) {
   float r;
@@ -287,14 +287,16 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
   uint32_t flags = 0;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { my_rows += rows[i]; flags |= rows[i] > 0 ? 1u << i : 0u; }
-  // 32-anchor sub-tiles of this warp's span (LPT lanes each) that hold a survivor: kernel 2's work list
-  constexpr int LPT = 32 / VEC;
+  // octets (8 consecutive anchors = one 32-byte fp32 sector per row) of this warp's span that hold a survivor:
+  // kernel 2's work list.  LPO lanes of this kernel cover one octet.
+  constexpr int LPO = VEC >= 8 ? 1 : 8 / VEC;
+  constexpr int NOCT = 32 / LPO;
   const unsigned bal = __ballot_sync(0xffffffffu, flags != 0);
-  uint32_t sub_mask = 0;
+  uint32_t oct_mask = 0;
 #pragma unroll
-  for (int j = 0; j < VEC; ++j)
-    if ((bal >> (j * LPT)) & ((LPT == 32) ? 0xffffffffu : ((1u << LPT) - 1u))) sub_mask |= 1u << j;
-  if (lane == 0) s_active[warp] = __popc(sub_mask);
+  for (int o = 0; o < NOCT; ++o)
+    if ((bal >> (o * LPO)) & ((1u << LPO) - 1u)) oct_mask |= 1u << o;
+  if (lane == 0) s_active[warp] = __popc(oct_mask);
   int total_rows;
   int roff = block_exclusive_scan(my_rows, total_rows);  // contains a __syncthreads
   if (total_rows == 0) return;  // uniform
@@ -306,13 +308,15 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
     s_base[1] = atomicAdd(f.tile_count, act);
   }
   __syncthreads();
-  if (sub_mask) {
+  if (oct_mask) {
     int rank = 0;
     for (int w = 0; w < warp; ++w) rank += s_active[w];
-    const int tile = b * static_cast<int>(gridDim.x * (DEC_THREADS / 32)) + blockIdx.x * (DEC_THREADS / 32) + warp;
-    if (lane < VEC && ((sub_mask >> lane) & 1u))
-      f.tile_list[s_base[1] + rank + __popc(sub_mask & ((1u << lane) - 1u))] = tile * VEC + lane;
-    f.tile_flags[static_cast<long long>(tile) * 32 + lane] = static_cast<uint8_t>(flags);
+    // flag bytes live in a dense per-lane array: index = b * G + lane-in-image, G = lanes kernel 1 runs per image
+    const int G = static_cast<int>(gridDim.x) * DEC_THREADS;
+    const int lane_idx = b * G + blockIdx.x * DEC_THREADS + tid;
+    if (lane < NOCT && ((oct_mask >> lane) & 1u))
+      f.tile_list[s_base[1] + rank + __popc(oct_mask & ((1u << lane) - 1u))] = (lane_idx - lane) / LPO + lane;
+    f.tile_flags[lane_idx] = static_cast<uint8_t>(flags);
   }
   if (my_rows == 0) return;
   uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
@@ -337,32 +341,33 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused path, kernel 2: box decode of the 32-anchor sub-tiles that hold a survivor (head.py:167-168 restricted to them)
+// fused path, kernel 2: box decode of the octets that hold a survivor (head.py:167-168 restricted to them)
 //
-//   warp = one sub-tile per iteration (grid-stride over the list kernel 1 built), lane = one anchor: every bin row is
-//   one coalesced 128-byte line per warp, all 64 rows are independent loads in flight, and the 4 x 16-bin softmax
-//   expectation (block.py:250-253) is an in-register reduction that flagged lanes alone execute.  Then dist2bbox /
-//   dist2rbox, x stride, rounding through the value dtype and the corner conversion (nms.py:86).
+//   quarter-warp = one octet (8 consecutive anchors) per iteration, lane = one anchor: every bin row costs the warp four
+//   32-byte sectors, the 64 rows are independent loads, and the 4 x 16-bin softmax expectation (block.py:250-253) is an
+//   in-register reduction that flagged lanes alone execute.  Then dist2bbox / dist2rbox, x stride, rounding through
+//   the value dtype and the corner conversion (nms.py:86).  Grid-stride over the octet list kernel 1 built, so the
+//   work is spread over the whole GPU whatever the per-image candidate counts are.
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT_IN, int DT_VAL, int VEC, bool ROT>
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
-                    const __grid_constant__ FilterArgs f, int tiles_per_image) {
+                    const __grid_constant__ FilterArgs f, int G) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
-  constexpr int LPT = 32 / VEC;
+  constexpr int LPO = VEC >= 8 ? 1 : 8 / VEC;  // kernel-1 lanes per octet
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (DEC_THREADS / 32);
-  const int ntiles = min(*f.tile_count, tiles_per_image * g.batch * VEC);
-  for (int t = blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5); t < ntiles; t += nwarps) {
-    const int st = f.tile_list[t];
-    const int tile = st / VEC, j = st - tile * VEC;
-    const int b = tile / tiles_per_image;
-    const int sub = j * LPT + lane / VEC;  // K1 lane (= anchor group) this anchor belongs to
-    const int i = lane % VEC;              // anchor inside the group
-    const uint32_t flags = f.tile_flags[static_cast<long long>(tile) * 32 + sub];
-    if (!((flags >> i) & 1u)) continue;    // flagged anchors are always inside the image
-    const int grp = (tile - b * tiles_per_image) * 32 + sub;
+  const int noct = min(*f.tile_count, f.tile_cap);
+  for (int t = (blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5)) * 4 + (lane >> 3); t < noct; t += nwarps * 4) {
+    const int oct = f.tile_list[t];
+    const int k = lane & 7;                      // anchor inside the octet
+    const int lane_idx = oct * LPO + (VEC >= 8 ? 0 : k / VEC);  // kernel-1 lane (anchor group) holding this anchor
+    const int i = VEC >= 8 ? k : k % VEC;        // anchor inside the group
+    const uint32_t flags = f.tile_flags[lane_idx];
+    if (!((flags >> i) & 1u)) continue;          // flagged anchors are always inside the image
+    const int b = lane_idx / G;
+    const int grp = lane_idx - b * G;
     const int l = find_level(g, grp);
     const int a_local = (grp - g.group_start[l]) * VEC + i;
     const long long cs = g.cstride[l];
@@ -372,7 +377,7 @@ decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
     for (int side = 0; side < 4; ++side) {
       float v[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = DType<DT_IN>::to_f(src[static_cast<long long>(side * 16 + k) * cs]);
+      for (int kk = 0; kk < 16; ++kk) v[kk] = DType<DT_IN>::to_f(src[static_cast<long long>(side * 16 + kk) * cs]);
       d[side] = dfl_expect<16>(v);
     }
     const int W = g.w[l];
@@ -535,14 +540,14 @@ static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, in
     else               scan_classes_kernel<DT_IN, DT_VAL, VEC, false><<<grid, DEC_THREADS, 0, st>>>(g, f);
     return cudaGetLastError();
   }
-  // kernel 2: grid-stride over the tile list; enough CTAs to cover the GPU, never more than there are tiles
-  const int tiles_per_image = blocks_x * (DEC_THREADS / 32);
-  long long max_tiles = static_cast<long long>(tiles_per_image) * g.batch * VEC;
+  // kernel 2: grid-stride over the octet list; enough CTAs to cover the GPU, never more than there can be octets
+  const int G = blocks_x * DEC_THREADS;
   int blocks = 148 * 8;
-  if (blocks > (max_tiles + 3) / 4) blocks = static_cast<int>((max_tiles + 3) / 4);
+  const int max_blocks = (f.tile_cap + 15) / 16;
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  if (f.rotated) decode_tiles_kernel<DT_IN, DT_VAL, VEC, true><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);
-  else           decode_tiles_kernel<DT_IN, DT_VAL, VEC, false><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, tiles_per_image);
+  if (f.rotated) decode_tiles_kernel<DT_IN, DT_VAL, VEC, true><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, G);
+  else           decode_tiles_kernel<DT_IN, DT_VAL, VEC, false><<<blocks, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f, G);
   return cudaGetLastError();
 }
 

@@ -123,19 +123,87 @@ __device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1: ranking
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void bitonic_sort_smem(uint64_t* s, int P) {
+// Bitonic sort of P = 32..4096 keys (power of two) by NT threads, ascending.  Thread tid holds the K = max(1, P/NT)
+// keys at positions s*NT + tid in registers, so a compare-exchange at distance j is
+//   j <  32      : a lane exchange (shuffle), no barrier, no shared memory   (40 of the 55 stages at P = 1024)
+//   32 <= j < NT : a round trip through shared memory (2 barriers)
+//   j >= NT      : between two registers of the same thread.
+// The sorted keys end up in s[0..P).
+__device__ __forceinline__ uint64_t cmpx(uint64_t mine, uint64_t other, bool want_min) {
+  const bool take_other = want_min ? other < mine : other > mine;
+  return take_other ? other : mine;
+}
+
+template <int K>
+__device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* __restrict__ src, int n, int P) {
+  const int tid = threadIdx.x;
+  uint64_t key[K];
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    const int p = u * NT + tid;
+    key[u] = p < n ? src[p] : KEY_SENTINEL;
+  }
+  const bool active = tid < P;  // P < NT: whole warps beyond P idle (P is a multiple of 32)
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += NT) {
-        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int l = i | j;
-        bool up = (i & k) == 0;
-        uint64_t a = s[i], c = s[l];
-        if ((a > c) == up) { s[i] = c; s[l] = a; }
+      if (j >= NT) {
+        if constexpr (K > 1) {
+          const int ju = j / NT;
+#pragma unroll
+          for (int jb = K / 2; jb >= 1; jb >>= 1) {  // compile-time partner distance: registers stay registers
+            if (ju == jb) {
+#pragma unroll
+              for (int u = 0; u < K; ++u) {
+                if ((u & jb) == 0) {
+                  const int p = u * NT + tid;
+                  const bool up = (p & k) == 0;
+                  const uint64_t a = key[u], c = key[u | jb];
+                  const bool swap = (a > c) == up;
+                  key[u] = swap ? c : a;
+                  key[u | jb] = swap ? a : c;
+                }
+              }
+            }
+          }
+        }
+      } else if (j >= 32) {
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < K; ++u) s[u * NT + tid] = key[u];
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < K; ++u) {
+            const int p = u * NT + tid;
+            const bool up = (p & k) == 0, lower = (p & j) == 0;
+            key[u] = cmpx(key[u], s[p ^ j], lower == up);
+          }
+        }
+        __syncthreads();
+      } else if (active) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const int p = u * NT + tid;
+          const bool up = (p & k) == 0, lower = (p & j) == 0;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[u], j);
+          key[u] = cmpx(key[u], other, lower == up);
+        }
       }
-      __syncthreads();
     }
   }
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) s[u * NT + tid] = key[u];
+  }
+  __syncthreads();
+}
+
+__device__ void bitonic_sort(uint64_t* s, const uint64_t* __restrict__ src, int n, int P) {
+  if (P <= NT) bitonic_sort_regs<1>(s, src, n, P);
+  else if (P == 2 * NT) bitonic_sort_regs<2>(s, src, n, P);
+  else if (P == 4 * NT) bitonic_sort_regs<4>(s, src, n, P);
+  else bitonic_sort_regs<8>(s, src, n, P);
 }
 
 // One stable 8-bit LSD pass src -> dst over n keys.
@@ -262,9 +330,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   if (n <= SORT_SMEM_MAX) {
     int P = 32;
     while (P < n) P <<= 1;
-    for (int i = tid; i < P; i += NT) sm.u.keys[i] = i < n ? ka[i] : KEY_SENTINEL;
-    __syncthreads();
-    bitonic_sort_smem(sm.u.keys, P);
+    bitonic_sort(sm.u.keys, ka, n, P);
     sorted = sm.u.keys;
   } else {
     sorted = radix_sort_global(ka, kb, n, sm);
@@ -356,31 +422,25 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
         sm.mask[q * CH + t] = word;
       }
       __syncthreads();
-      // (c) fix-point over the chunk inside ONE warp (no block barriers): lane owns ranks lane + 32 j.  A rank is kept
-      //     iff no kept suppressor, dead iff some kept suppressor, and waits while a possible suppressor is undecided;
-      //     the lowest undecided rank always decides, and words are settled in rank order (Gauss-Seidel).
+      // (c) resolve the chunk inside ONE warp (no block barriers): lane owns ranks lane + 32 j.  The lowest rank still
+      //     standing has every higher-ranked row decided, so it is kept; one ballot per mask word strikes the ranks it
+      //     suppresses.  One step per KEPT rank of the chunk.
       if (warp == 0) {
-        uint32_t undec[CW], kept[CW], mk[CW][CW];
+        uint32_t rem[CW], kept[CW], mk[CW][CW];
 #pragma unroll
-        for (int j = 0; j < CW; ++j) { undec[j] = sm.alive_bits[j]; kept[j] = 0; }
+        for (int j = 0; j < CW; ++j) { rem[j] = sm.alive_bits[j]; kept[j] = 0; }
 #pragma unroll
         for (int j = 0; j < CW; ++j)
 #pragma unroll
-          for (int w = 0; w <= j; ++w) mk[j][w] = ((undec[j] >> lane) & 1u) ? (sm.mask[w * CH + lane + 32 * j] & undec[w]) : 0u;
-        bool any = true;
-        while (any) {
-          any = false;
+          for (int w = 0; w <= j; ++w) mk[j][w] = ((rem[j] >> lane) & 1u) ? sm.mask[w * CH + lane + 32 * j] : 0u;
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const bool mine = (undec[j] >> lane) & 1u;
-            uint32_t hk = 0, hu = 0;
+        for (int w = 0; w < CW; ++w) {
+          while (rem[w]) {
+            const int i = __ffs(rem[w]) - 1;
+            kept[w] |= 1u << i;
+            rem[w] &= ~(1u << i);
 #pragma unroll
-            for (int w = 0; w <= j; ++w) { hk |= mk[j][w] & kept[w]; hu |= mk[j][w] & undec[w]; }
-            const unsigned kb = __ballot_sync(0xffffffffu, mine && hk == 0 && hu == 0);
-            const unsigned db = __ballot_sync(0xffffffffu, mine && hk != 0);
-            kept[j] |= kb;
-            undec[j] &= ~(kb | db);
-            any |= undec[j] != 0;
+            for (int j = w; j < CW; ++j) rem[j] &= ~__ballot_sync(0xffffffffu, (mk[j][w] >> i) & 1u);
           }
         }
         if (lane < CW) {
