@@ -150,6 +150,10 @@ YPB_API int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, in
                   float iou_thres_eff, int64_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* Diagnostic: when set to a device buffer of batch*32 int64, the sort+suppress kernel stores clock64() marks per CTA
+ * (0 start, 1 ranked, 2+i after chunk i, 30 before gather, 31 end); NULL disables (default). */
+YPB_API void ypb_debug_set_phase_buffer(void* device_buffer);
+
 /* Diagnostic: exhaustively checks that the device sigmoid used by the decode kernels is monotone non-decreasing
  * over all finite fp32 inputs after rounding to `dtype`; writes the number of violations to *violations (device). */
 YPB_API int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream);

@@ -31,6 +31,7 @@ EXPORTS = (
     "ypb_nms_boxes_workspace_bytes",
     "ypb_nms_boxes",
     "ypb_selftest_sigmoid_monotone",
+    "ypb_debug_set_phase_buffer",
 )
 
 
@@ -128,6 +129,8 @@ def load():
     lib.ypb_nms_boxes.restype = C.c_int
     lib.ypb_nms_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ypb_debug_set_phase_buffer.restype = None
+    lib.ypb_debug_set_phase_buffer.argtypes = [C.c_void_p]
     lib.ypb_selftest_sigmoid_monotone.restype = C.c_int
     lib.ypb_selftest_sigmoid_monotone.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:

@@ -262,6 +262,8 @@ int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t bo
   return YPB_OK;
 }
 
+void ypb_debug_set_phase_buffer(void* device_buffer) { ypb::set_phase_buffer(static_cast<long long*>(device_buffer)); }
+
 int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream) {
   if (!violations || !dtype_ok(dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "bad arguments");
   cudaError_t e = ypb::launch_sigmoid_selftest(dtype, violations, static_cast<cudaStream_t>(stream));

@@ -285,7 +285,9 @@ struct SuppressArgs {
   int32_t* out_count;
   int32_t* out_cand;
   int idx_as_row;  // ypb_nms_boxes: write the row id itself
+  long long* dbg;  // diagnostic phase timestamps or null
 };
+void set_phase_buffer(long long* p);
 
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,

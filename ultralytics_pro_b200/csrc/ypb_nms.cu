@@ -310,6 +310,14 @@ __device__ __forceinline__ float load_pred(const void* p, int dt, long long off)
   return load_as_float<YPB_BF16>(p, off);
 }
 
+// Optional phase timestamps (diagnostic, ypb_debug_set_phase_buffer): per CTA 32 clock64 marks.
+static long long* g_phase_buf = nullptr;
+void set_phase_buffer(long long* p) { g_phase_buf = p; }
+#define YPB_MARK(slot)                                                                   \
+  do {                                                                                   \
+    if (a.dbg && threadIdx.x == 0 && (slot) < 32) a.dbg[blockIdx.x * 32 + (slot)] = clock64(); \
+  } while (0)
+
 template <int RULE>
 __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant__ SuppressArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
+  YPB_MARK(0);
   const int emitted = a.row_count[b];
   const int n = min(emitted, a.rows_cap);
   if (tid == 0 && a.out_cand) a.out_cand[b] = emitted;
@@ -336,6 +345,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     sorted = radix_sort_global(ka, kb, n, sm);
   }
   const int m = min(n, a.max_nms);
+  YPB_MARK(1);
 
   // ---- stage 2 ---------------------------------------------------------------------------------------------------
   const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
@@ -508,9 +518,11 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     }
     kept_n = min(a.max_det, kept_n + total);
     __syncthreads();  // kept_* visible to the block, smem reusable
+    YPB_MARK(2 + c0 / CH);
   }
 
   // ---- stage 3 ---------------------------------------------------------------------------------------------------
+  YPB_MARK(30);
   if (tid == 0) a.out_count[b] = kept_n;
   const int cols = 6 + a.extra;
   for (int k = tid; k < kept_n; k += NT) {
@@ -533,6 +545,8 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       }
     }
   }
+  __syncthreads();
+  YPB_MARK(31);
 }
 
 __global__ void boxes_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, int box_dim,
@@ -555,13 +569,15 @@ cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   if (a.rule < 0 || a.rule > 2) return cudaErrorInvalidValue;
   const bool need_cfg = dev < 0 || dev >= 64 || !configured[dev][a.rule];
+  SuppressArgs aa = a;
+  aa.dbg = g_phase_buf;
 #define YPB_SS(R)                                                                                                \
   do {                                                                                                           \
     if (need_cfg) {                                                                                              \
       e = cudaFuncSetAttribute(sort_suppress_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return e;                                                                            \
     }                                                                                                            \
-    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(a);                                                       \
+    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(aa);                                                      \
   } while (0)
   switch (a.rule) {
     case YPB_NMS_GREEDY: YPB_SS(YPB_NMS_GREEDY); break;
