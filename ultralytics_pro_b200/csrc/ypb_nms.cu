@@ -22,7 +22,7 @@ constexpr int CW = CH / 32;          // mask words per rank of a chunk
 constexpr int PARTS = NT / CH;       // threads cooperating on one rank (== CW: part q owns mask word q)
 constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
 constexpr int KEPT_SMEM = 1024;      // kept rows held in shared memory (larger max_det spills the list to the workspace)
-static_assert(PARTS == CW, "one thread per (rank, mask word)");
+static_assert(PARTS == CW && CW == 4, "one thread per (rank, mask word); rows are read as one uint4");
 
 struct __align__(16) Smem {
   union {
@@ -32,7 +32,7 @@ struct __align__(16) Smem {
       uint32_t wc[NW * 256];
     } rx;
   } u;
-  uint32_t mask[CW * CH];  // mask[w * CH + t]: bit i set iff rank (w*32+i) of the chunk suppresses rank t
+  alignas(16) uint32_t mask[CW * CH];  // mask[t * CW + w]: bit i set iff rank t of the chunk suppresses rank w*32+i (> t)
   union {
     struct {
       float4 box[CH];
@@ -63,19 +63,46 @@ __device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__
 struct GreedyThr {
   double mid;
   bool tie_up;
+  float lo, hi;  // thr * (1 -+ 2^-20): an fp32 product against these brackets decides all but borderline pairs
 };
 __device__ __forceinline__ GreedyThr make_greedy_thr(float thr) {
   const float nxt = __uint_as_float(__float_as_uint(thr) + 1u);  // thr >= 0
-  return GreedyThr{(static_cast<double>(thr) + static_cast<double>(nxt)) * 0.5, (__float_as_uint(thr) & 1u) != 0u};
+  GreedyThr g;
+  g.mid = (static_cast<double>(thr) + static_cast<double>(nxt)) * 0.5;
+  g.tie_up = (__float_as_uint(thr) & 1u) != 0u;
+  // tiny thresholds: no bracket (every overlapping pair takes the exact test)
+  g.lo = thr > 1e-6f ? thr * (1.0f - 9.5367431640625e-7f) : 0.f;
+  g.hi = thr > 1e-6f ? thr * (1.0f + 9.5367431640625e-7f) : INFINITY;
+  return g;
 }
-__device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, const GreedyThr& t) {
+// exact decision (see above); only reached by borderline pairs
+__device__ __noinline__ bool greedy_exact(float inter, float uni, double mid, bool tie_up) {
+  const double di = static_cast<double>(inter), lim = mid * static_cast<double>(uni);
+  const bool over = tie_up ? di >= lim : di > lim;
+  return inter > 0.f && uni >= 0.f && over;
+}
+struct PairGeom { float inter, uni; };
+__device__ __forceinline__ PairGeom pair_geom(const float4& a, float aa, const float4& b, float ab) {
   const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
   const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-  const float inter = __fmul_rn(w, h);
-  const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
-  const double di = static_cast<double>(inter), lim = t.mid * static_cast<double>(uni);
-  const bool over = t.tie_up ? di >= lim : di > lim;
-  return inter > 0.f && uni >= 0.f && over;
+  PairGeom g;
+  g.inter = __fmul_rn(w, h);
+  g.uni = __fsub_rn(__fadd_rn(aa, ab), g.inter);
+  return g;
+}
+// 1 = suppresses for sure, 0 = surely not, 2 = borderline (needs greedy_exact).  With uni > 1e-30 the fp32 products
+// thr*(1+-2^-20)*uni carry a relative error <= 2^-23, far inside the 2^-20 bracket around mid = thr*(1 + ~2^-24).
+__device__ __forceinline__ int greedy_class(const PairGeom& g, const GreedyThr& t) {
+  const bool normal = g.uni > 1e-30f;
+  const bool sure = normal && g.inter > __fmul_rn(t.hi, g.uni);
+  const bool never = !(g.inter > 0.f) || (normal && g.inter < __fmul_rn(t.lo, g.uni)) || g.uni < 0.f;
+  return sure ? 1 : (never ? 0 : 2);
+}
+__device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, const GreedyThr& t) {
+  const PairGeom g = pair_geom(a, aa, b, ab);
+  const int c = greedy_class(g, t);
+  if (c == 2) return greedy_exact(g.inter, g.uni, t.mid, t.tie_up);
+  return c == 1;
 }
 
 // metrics.py:54-75 with eps in the denominator, rule ">= thr" (nms.py:223).
@@ -404,64 +431,81 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     bool alive;
 
     if constexpr (RULE == YPB_NMS_GREEDY) {
+      if (c0 == CH) YPB_MARK(8);
       if (q == 0) { sm.c.g.box[t] = ob; sm.c.g.area[t] = area; }
       __syncthreads();
+      if (c0 == CH) YPB_MARK(9);
       // (a) against the rows kept in earlier chunks: part q takes every PARTS-th kept row (no early exit: ILP)
       bool hit = false;
       if (valid) {
 #pragma unroll 4
         for (int k = q; k < kept_n; k += PARTS) hit |= greedy_suppresses(kbox[k], karea[k], ob, area, gthr);
       }
+      if (c0 == CH) YPB_MARK(10);
       if (hit) sm.dead[t] = 1;
       __syncthreads();
+      if (c0 == CH) YPB_MARK(11);
       alive = sm.dead[t] == 0;
       if (q == 0) {
         const unsigned ab = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) sm.alive_bits[warp] = ab;
       }
-      // (b) mask word q of rank t: which ranks 32q..32q+31 of this chunk (ranked above t) would suppress t
+      // (b) word q of the suppression row of rank t: which LOWER ranks 32q..32q+31 of this chunk t would suppress if it
+      //     is kept (IoU is symmetric, so this is the transpose of "who suppresses t").  32 branch-free fp32 tests; the
+      //     rare borderline pairs are settled exactly afterwards.
       const int tw = t >> 5;
-      if (alive && q <= tw) {
-        uint32_t word = 0;
+      if (alive && q >= tw) {
+        uint32_t word = 0, maybe = 0;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int idx = q * 32 + i;
-          word |= greedy_suppresses(sm.c.g.box[idx], sm.c.g.area[idx], ob, area, gthr) ? 1u << i : 0u;
+          const int c = greedy_class(pair_geom(ob, area, sm.c.g.box[idx], sm.c.g.area[idx]), gthr);
+          word |= c == 1 ? 1u << i : 0u;
+          maybe |= c == 2 ? 1u << i : 0u;
         }
-        if (q == tw) word &= lt_mask;
-        sm.mask[q * CH + t] = word;
+        while (maybe) {
+          const int i = __ffs(maybe) - 1;
+          maybe &= maybe - 1;
+          const int idx = q * 32 + i;
+          const PairGeom g = pair_geom(ob, area, sm.c.g.box[idx], sm.c.g.area[idx]);
+          if (greedy_exact(g.inter, g.uni, gthr.mid, gthr.tie_up)) word |= 1u << i;
+        }
+        if (q == tw) word &= ~(lt_mask | (1u << lane));  // only ranks below t
+        sm.mask[t * CW + q] = word;
+      }
+      if (c0 == CH) YPB_MARK(12);
+      __syncthreads();
+      if (c0 == CH) YPB_MARK(13);
+      // (c) resolve the chunk: the lowest rank still standing has every higher-ranked row decided, so it is kept and
+      //     its row strikes the ranks it suppresses - one step per KEPT rank.  Every warp runs the same scalar loop on
+      //     broadcast shared-memory reads, so nobody waits for the answer (no barrier, no warp collective).
+      uint32_t rem[CW], kept[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) { rem[j] = sm.alive_bits[j]; kept[j] = 0; }
+#pragma unroll
+      for (int w = 0; w < CW; ++w) {
+        while (rem[w]) {
+          const int i = __ffs(rem[w]) - 1;
+          kept[w] |= 1u << i;
+          rem[w] &= ~(1u << i);
+          const uint4 row = *reinterpret_cast<const uint4*>(&sm.mask[(w * 32 + i) * CW]);
+          const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll
+          for (int j = w; j < CW; ++j) rem[j] &= ~rw[j];
+        }
+      }
+      if (c0 == CH) YPB_MARK(14);
+      alive = q == 0 && ((kept[0] >> lane) & 1u) != 0;
+#pragma unroll
+      for (int j = 1; j < CW; ++j) alive = (q == 0 && tw == j) ? ((kept[j] >> lane) & 1u) != 0 : alive;
+      if (tid < CW) {
+        uint32_t kw = kept[0];
+#pragma unroll
+        for (int j = 1; j < CW; ++j) kw = tid == j ? kept[j] : kw;
+        sm.kept_bits[tid] = kw;
       }
       __syncthreads();
-      // (c) resolve the chunk inside ONE warp (no block barriers): lane owns ranks lane + 32 j.  The lowest rank still
-      //     standing has every higher-ranked row decided, so it is kept; one ballot per mask word strikes the ranks it
-      //     suppresses.  One step per KEPT rank of the chunk.
-      if (warp == 0) {
-        uint32_t rem[CW], kept[CW], mk[CW][CW];
-#pragma unroll
-        for (int j = 0; j < CW; ++j) { rem[j] = sm.alive_bits[j]; kept[j] = 0; }
-#pragma unroll
-        for (int j = 0; j < CW; ++j)
-#pragma unroll
-          for (int w = 0; w <= j; ++w) mk[j][w] = ((rem[j] >> lane) & 1u) ? sm.mask[w * CH + lane + 32 * j] : 0u;
-#pragma unroll
-        for (int w = 0; w < CW; ++w) {
-          while (rem[w]) {
-            const int i = __ffs(rem[w]) - 1;
-            kept[w] |= 1u << i;
-            rem[w] &= ~(1u << i);
-#pragma unroll
-            for (int j = w; j < CW; ++j) rem[j] &= ~__ballot_sync(0xffffffffu, (mk[j][w] >> i) & 1u);
-          }
-        }
-        if (lane < CW) {
-          uint32_t kw = kept[0];
-#pragma unroll
-          for (int j = 1; j < CW; ++j) kw = lane == j ? kept[j] : kw;
-          sm.kept_bits[lane] = kw;
-        }
-      }
-      __syncthreads();
-      alive = q == 0 && ((sm.kept_bits[t >> 5] >> lane) & 1u);
+      if (c0 == CH) YPB_MARK(15);
     } else {
       // Fast-NMS: a rank is dropped iff ANY higher rank (kept or not) overlaps it >= thr, nms.py:221-223.
       float* my = sm.c.rec + t * 8;
