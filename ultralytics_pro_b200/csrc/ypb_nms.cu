@@ -90,19 +90,24 @@ __device__ __forceinline__ PairGeom pair_geom(const float4& a, float aa, const f
   g.uni = __fsub_rn(__fadd_rn(aa, ab), g.inter);
   return g;
 }
-// 1 = suppresses for sure, 0 = surely not, 2 = borderline (needs greedy_exact).  With uni > 1e-30 the fp32 products
-// thr*(1+-2^-20)*uni carry a relative error <= 2^-23, far inside the 2^-20 bracket around mid = thr*(1 + ~2^-24).
-__device__ __forceinline__ int greedy_class(const PairGeom& g, const GreedyThr& t) {
-  const bool normal = g.uni > 1e-30f;
-  const bool sure = normal && g.inter > __fmul_rn(t.hi, g.uni);
-  const bool never = !(g.inter > 0.f) || (normal && g.inter < __fmul_rn(t.lo, g.uni)) || g.uni < 0.f;
-  return sure ? 1 : (never ? 0 : 2);
+// Classifies a pair with fp32 products only: `sure` = suppresses, `maybe` = borderline (needs greedy_exact), neither =
+// surely not.  With uni > 1e-30 the products thr*(1+-2^-20)*uni carry a relative error <= 2^-23, far inside the 2^-20
+// bracket around mid = thr*(1 + ~2^-24).  Written with non-short-circuit logic so it compiles to predicates, not branches.
+__device__ __forceinline__ void greedy_flags(const PairGeom& g, const GreedyThr& t, unsigned& sure, unsigned& maybe) {
+  const unsigned normal = g.uni > 1e-30f;
+  const unsigned above = g.inter > __fmul_rn(t.hi, g.uni);
+  const unsigned below = g.inter < __fmul_rn(t.lo, g.uni);
+  const unsigned pos = g.inter > 0.f;
+  sure = normal & above;
+  const unsigned never = (pos ^ 1u) | (normal & below);
+  maybe = (sure | never) ^ 1u;
 }
 __device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, const float4& b, float ab, const GreedyThr& t) {
   const PairGeom g = pair_geom(a, aa, b, ab);
-  const int c = greedy_class(g, t);
-  if (c == 2) return greedy_exact(g.inter, g.uni, t.mid, t.tie_up);
-  return c == 1;
+  unsigned sure, maybe;
+  greedy_flags(g, t, sure, maybe);
+  if (maybe) return greedy_exact(g.inter, g.uni, t.mid, t.tie_up);
+  return sure != 0u;
 }
 
 // metrics.py:54-75 with eps in the denominator, rule ">= thr" (nms.py:223).
@@ -438,8 +443,18 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       // (a) against the rows kept in earlier chunks: part q takes every PARTS-th kept row (no early exit: ILP)
       bool hit = false;
       if (valid) {
+        unsigned hs = 0, hm = 0;
 #pragma unroll 4
-        for (int k = q; k < kept_n; k += PARTS) hit |= greedy_suppresses(kbox[k], karea[k], ob, area, gthr);
+        for (int k = q; k < kept_n; k += PARTS) {
+          unsigned su, mb;
+          greedy_flags(pair_geom(kbox[k], karea[k], ob, area), gthr, su, mb);
+          hs |= su;
+          hm |= mb;
+        }
+        hit = hs != 0u;
+        if (!hit && hm) {  // some borderline pair and no sure hit: settle exactly (rare)
+          for (int k = q; k < kept_n && !hit; k += PARTS) hit = greedy_suppresses(kbox[k], karea[k], ob, area, gthr);
+        }
       }
       if (c0 == CH) YPB_MARK(10);
       if (hit) sm.dead[t] = 1;
@@ -459,9 +474,10 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int idx = q * 32 + i;
-          const int c = greedy_class(pair_geom(ob, area, sm.c.g.box[idx], sm.c.g.area[idx]), gthr);
-          word |= c == 1 ? 1u << i : 0u;
-          maybe |= c == 2 ? 1u << i : 0u;
+          unsigned su, mb;
+          greedy_flags(pair_geom(ob, area, sm.c.g.box[idx], sm.c.g.area[idx]), gthr, su, mb);
+          word |= su << i;
+          maybe |= mb << i;
         }
         while (maybe) {
           const int i = __ffs(maybe) - 1;
