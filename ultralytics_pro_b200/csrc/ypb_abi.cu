@@ -50,8 +50,8 @@ int build_geom(const ypb_head_desc* h, ypb::HeadGeom* g, int* vec_out, const voi
     if (hw % wide || h->level_channel_stride[l] % wide || h->level_batch_stride[l] % wide || !aligned(h->level_ptr[l], 16))
       vec = 1;
   }
-  if (anchors > 0x7fffffffLL / (h->nc > 1 ? h->nc : 1))
-    return fail(YPB_ERR_UNSUPPORTED, "anchors*nc does not fit the 31-bit row id");
+  if (ypb::bits_for(anchors) + ypb::bits_for(h->nc) > 31)
+    return fail(YPB_ERR_UNSUPPORTED, "anchor and class index do not fit the 31-bit row id");
   if (extra_ptr_a && !aligned(extra_ptr_a, 16)) vec = 1;
   if (extra_ptr_b && !aligned(extra_ptr_b, 16)) vec = 1;
   if (extra_stride_a % wide || extra_stride_b % wide) vec = 1;
@@ -99,6 +99,7 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   ypb::SuppressArgs s{};
   s.batch = batch; s.anchors = anchors; s.nc = p->nc; s.extra = p->extra; s.max_det = p->max_det; s.max_nms = p->max_nms;
   s.rule = p->rule; s.rows_cap = p->rows_cap; s.multi_label = p->multi_label;
+  s.cls_bits = ypb::bits_for(p->nc); s.anchor_bits = ypb::bits_for(anchors);
   s.iou_thr = p->iou_thres_eff; s.max_wh = p->max_wh;
   s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
   s.cand_ang = p->rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
@@ -175,14 +176,14 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     ypb::FilterArgs f{};
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-    f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
     if (e != cudaSuccess) return cuda_fail(e, "scan_classes");
   }
   if (stage & 2) {
     ypb::FilterArgs f{};
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-    f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
@@ -207,8 +208,8 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
   const bool rotated = p->rule == YPB_NMS_FAST_PROBIOU;
   if (rotated && p->extra < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "rotated rule needs the angle as last channel (nms.py:146)");
-  if (static_cast<long long>(pred->anchors) > 0x7fffffffLL / p->nc)
-    return fail(YPB_ERR_UNSUPPORTED, "anchors*nc does not fit the 31-bit row id");
+  if (ypb::bits_for(pred->anchors) + ypb::bits_for(p->nc) > 31)
+    return fail(YPB_ERR_UNSUPPORTED, "anchor and class index do not fit the 31-bit row id");
   if (!pred->ptr && pred->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "prediction pointer is NULL");
   ypb::Workspace w = ypb::carve_workspace(workspace, pred->batch, pred->anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
   if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
@@ -219,7 +220,7 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
   ypb::FilterArgs f{};
   f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-  f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+  f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
   e = ypb::launch_filter_from_dense(*pred, f, st);
   if (e != cudaSuccess) return cuda_fail(e, "filter_from_dense");
   ypb::SuppressArgs s = suppress_args(p, out, w, pred->batch, pred->anchors);
@@ -252,7 +253,7 @@ int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t bo
   if (e != cudaSuccess) return cuda_fail(e, "boxes_prep");
   ypb::SuppressArgs s{};
   s.batch = 1; s.anchors = m; s.nc = 1; s.extra = 0; s.max_det = m; s.max_nms = m; s.rule = rule; s.rows_cap = m;
-  s.iou_thr = iou_thres_eff; s.max_wh = 0.f;
+  s.iou_thr = iou_thres_eff; s.max_wh = 0.f; s.cls_bits = 0; s.anchor_bits = ypb::bits_for(m);
   s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
   s.cand_ang = rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
   s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;

@@ -166,7 +166,7 @@ __device__ __forceinline__ BoxXYWH decode_rotated(float dl, float dt, float dr, 
 __device__ __forceinline__ float activate_angle(float t) { return (sigmoid_f(t) - 0.25f) * 3.14159265358979323846f; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// sort keys: 64-bit, unique per image.  hi = ~orderable(score), lo = row id (anchor * nc + cls), so an ascending
+// sort keys: 64-bit, unique per image.  hi = ~orderable(score), lo = row id ((anchor << cls_bits) | cls), so an ascending
 // sort is "score descending, then lower row first" == torchvision's stable descending sort (Ties).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t orderable_bits(float f) {
@@ -203,6 +203,12 @@ struct Workspace {
   float* rec;          // [B][min(rows_cap,max_nms)][8]  per-rank records (fast rules only)
   size_t bytes;
 };
+
+__host__ inline int bits_for(long long n) {  // smallest b with n <= 2^b
+  int b = 0;
+  while ((1LL << b) < n) ++b;
+  return b;
+}
 
 __host__ inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -252,6 +258,7 @@ struct HeadGeom {  // device-side view of ypb_head_desc, passed by value
 struct FilterArgs {
   float conf;
   int nc, multi_label, rotated, rows_cap;
+  int cls_bits;  // row id = (anchor << cls_bits) | cls
   const uint32_t* class_mask;
   int32_t* row_count;
   int32_t* tile_count;
@@ -265,6 +272,7 @@ struct FilterArgs {
 
 struct SuppressArgs {
   int batch, anchors, nc, extra, max_det, max_nms, rule, rows_cap, multi_label;
+  int cls_bits, anchor_bits;  // row id = (anchor << cls_bits) | cls; anchors < 2^anchor_bits
   float iou_thr, max_wh;
   int32_t* row_count;
   uint64_t* keys_a;

@@ -324,7 +324,7 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     if (rows[i] == 0) continue;
-    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) * static_cast<uint32_t>(nc);
+    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) << f.cls_bits;
     if constexpr (MULTI) {
       for (int c = 0; c < nc; ++c) {
         float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
@@ -461,7 +461,7 @@ filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_
   if (my_rows == 0) return;
   uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
   int pos = base + off;
-  const uint32_t row0 = static_cast<uint32_t>(a) * static_cast<uint32_t>(nc);
+  const uint32_t row0 = static_cast<uint32_t>(a) << f.cls_bits;
   if constexpr (MULTI) {
     for (int c = 0; c < nc; ++c) {
       float s = D::to_f(pc[c * sc]);

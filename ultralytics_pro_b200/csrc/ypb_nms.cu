@@ -43,6 +43,15 @@ struct __align__(16) Smem {
   int dead[CH];  // rank already suppressed by a row outside the chunk
   float4 kbox[KEPT_SMEM];  // class-offset boxes of the rows kept so far (greedy rule, max_det <= KEPT_SMEM)
   float karea[KEPT_SMEM];
+  // class-wise path: every candidate of the image, in (class, score desc) order
+  float4 cbox[SORT_SMEM_MAX];
+  float carea[SORT_SMEM_MAX];
+  uint32_t kbits[SORT_SMEM_MAX / 32];    // kept flags by sorted position
+  uint32_t headw[SORT_SMEM_MAX / 32];    // segment-head flags by sorted position
+  uint32_t headpre[SORT_SMEM_MAX / 32];  // heads before each word
+  uint16_t seg_start[SORT_SMEM_MAX + 2];
+  float red_min[NW], red_max[NW];
+  int nseg, kcount;
   uint32_t alive_bits[CW];
   uint32_t kept_bits[CW];
   uint32_t undec_bits[CW];
@@ -166,15 +175,34 @@ __device__ __forceinline__ uint64_t cmpx(uint64_t mine, uint64_t other, bool wan
   return take_other ? other : mine;
 }
 
-template <int K>
-__device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* __restrict__ src, int n, int P) {
+struct KeyIdentity {
+  __device__ __forceinline__ uint64_t operator()(uint64_t k) const { return k; }
+};
+// (score desc, row asc) key -> (class asc, score desc, anchor asc): same order inside a class, classes contiguous.
+struct KeyClassMajor {
+  int cbits, abits;
+  __device__ __forceinline__ uint64_t operator()(uint64_t k) const {
+    const uint32_t row = static_cast<uint32_t>(k);
+    const uint64_t cls = row & ((1u << cbits) - 1u), anchor = row >> cbits;
+    return (cls << (32 + abits)) | ((k >> 32) << abits) | anchor;
+  }
+  __device__ __forceinline__ uint64_t inverse(uint64_t c) const {
+    const uint64_t anchor = c & ((1ull << abits) - 1ull), cls = c >> (32 + abits);
+    const uint64_t hi = (c >> abits) & 0xffffffffull;
+    return (hi << 32) | (anchor << cbits) | cls;
+  }
+};
+
+template <int K, typename XF>
+__device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* src, int n, int P, XF xf) {
   const int tid = threadIdx.x;
   uint64_t key[K];
 #pragma unroll
   for (int u = 0; u < K; ++u) {
     const int p = u * NT + tid;
-    key[u] = p < n ? src[p] : KEY_SENTINEL;
+    key[u] = p < n ? xf(src[p]) : KEY_SENTINEL;
   }
+  __syncthreads();  // src may alias other shared memory that the exchange stages are about to overwrite
   const bool active = tid < P;  // P < NT: whole warps beyond P idle (P is a multiple of 32)
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -231,11 +259,14 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* _
   __syncthreads();
 }
 
-__device__ void bitonic_sort(uint64_t* s, const uint64_t* __restrict__ src, int n, int P) {
-  if (P <= NT) bitonic_sort_regs<1>(s, src, n, P);
-  else if (P == 2 * NT) bitonic_sort_regs<2>(s, src, n, P);
-  else if (P == 4 * NT) bitonic_sort_regs<4>(s, src, n, P);
-  else bitonic_sort_regs<8>(s, src, n, P);
+template <typename XF>
+__device__ __noinline__ void bitonic_sort(uint64_t* s, const uint64_t* src, int n, XF xf) {
+  int P = 32;
+  while (P < n) P <<= 1;
+  if (P <= NT) bitonic_sort_regs<1>(s, src, n, P, xf);
+  else if (P == 2 * NT) bitonic_sort_regs<2>(s, src, n, P, xf);
+  else if (P == 4 * NT) bitonic_sort_regs<4>(s, src, n, P, xf);
+  else bitonic_sort_regs<8>(s, src, n, P, xf);
 }
 
 // One stable 8-bit LSD pass src -> dst over n keys.
@@ -330,6 +361,141 @@ __device__ const uint64_t* radix_sort_global(uint64_t* a, uint64_t* b, int n, Sm
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// class-wise greedy NMS (fast path of the class-aware rule)
+//
+// nms.py:143-149 makes NMS class-aware by adding cls * max_wh to every coordinate.  When all un-offset coordinates of
+// the image span no more than max_wh, boxes of different classes cannot intersect after the offset (the offsets differ
+// by >= max_wh and fp32 rounding is monotone), so their IoU is exactly 0 and the greedy walk decomposes EXACTLY into
+// independent walks per class.  The candidates are sorted by (class, score desc, anchor asc); every class segment is
+// resolved by one warp with lane = candidate: the lowest surviving lane is kept, one ballot strikes what it
+// suppresses - one step per KEPT box instead of one IoU per pair of candidates.  The kept rows are then re-sorted by
+// the original (score desc, row asc) key and cut at max_det (nms.py:157).  Same fp32 arithmetic on the same offset
+// boxes as the dense path, so results are bit-identical.  Returns the number of kept rows (their keys in sm.u.keys),
+// or -1 if the span condition fails (caller falls back to the dense walk).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t* ka, int n, const float4* cand_box,
+                                const GreedyThr& gthr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const KeyClassMajor xf{a.cls_bits, a.anchor_bits};
+  bitonic_sort(sm.u.keys, ka, n, xf);
+  const int nwords = (n + 31) >> 5;
+
+  // offset boxes by sorted position, coordinate span, segment heads
+  float lo = INFINITY, hi = -INFINITY;
+  bool finite = true;
+  for (int w = warp; w < nwords; w += NW) {
+    const int p = 32 * w + lane;
+    bool head = false;
+    if (p < n) {
+      const uint64_t k = sm.u.keys[p];
+      const uint32_t anchor = static_cast<uint32_t>(k & ((1ull << a.anchor_bits) - 1ull));
+      const uint32_t cls = static_cast<uint32_t>(k >> (32 + a.anchor_bits));
+      const float4 bx = cand_box[anchor];
+      lo = fminf(lo, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
+      hi = fmaxf(hi, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+      finite &= isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w);
+      const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
+      const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+      sm.cbox[p] = ob;
+      sm.carea[p] = box_area(ob);
+      head = p == 0 || static_cast<uint32_t>(sm.u.keys[p - 1] >> (32 + a.anchor_bits)) != cls;
+    }
+    const unsigned hb = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) { sm.headw[w] = hb; sm.kbits[w] = 0; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { sm.red_min[warp] = lo; sm.red_max[warp] = hi; }
+  if (tid == 0) sm.kcount = 0;
+  const int bad = __syncthreads_or(!finite);
+  float glo = sm.red_min[0], ghi = sm.red_max[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) { glo = fminf(glo, sm.red_min[w]); ghi = fmaxf(ghi, sm.red_max[w]); }
+  if (bad || !(ghi - glo <= 0.999f * a.max_wh)) return -1;  // uniform
+
+  // segment table: prefix of the head flags
+  if (warp == 0) {
+    int run = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+      const int w = w0 + lane;
+      const int c = w < nwords ? __popc(sm.headw[w]) : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (w < nwords) sm.headpre[w] = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) { sm.nseg = run; sm.seg_start[run] = static_cast<uint16_t>(n); }
+  }
+  __syncthreads();
+  for (int w = warp; w < nwords; w += NW) {
+    const uint32_t hb = sm.headw[w];
+    if ((hb >> lane) & 1u) sm.seg_start[sm.headpre[w] + __popc(hb & lt_mask)] = static_cast<uint16_t>(32 * w + lane);
+  }
+  __syncthreads();
+
+  // one warp per class segment
+  const int nseg = sm.nseg;
+  for (int sid = warp; sid < nseg; sid += NW) {
+    const int s = sm.seg_start[sid], e = sm.seg_start[sid + 1];
+    const int w_first = s >> 5, w_last = (e - 1) >> 5;
+    for (int w = w_first; w <= w_last; ++w) {
+      const int p = 32 * w + lane;
+      const bool in = p >= s && p < e;
+      float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+      float marea = 0.f;
+      if (in) { mine = sm.cbox[p]; marea = sm.carea[p]; }
+      bool alive = in;
+      // rows of this class kept in earlier words
+      for (int w2 = w_first; w2 < w; ++w2) {
+        uint32_t kb = sm.kbits[w2];
+        if (w2 == w_first) kb &= ~((1u << (s & 31)) - 1u);
+        while (kb) {
+          const int i = __ffs(kb) - 1;
+          kb &= kb - 1;
+          const int pi = 32 * w2 + i;
+          if (alive && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr)) alive = false;
+        }
+      }
+      // inside the word: the lowest surviving lane is kept and strikes the lanes it suppresses
+      uint32_t m = __ballot_sync(0xffffffffu, alive), keptw = 0;
+      while (m) {
+        const int i = __ffs(m) - 1;
+        keptw |= 1u << i;
+        const int pi = 32 * w + i;
+        const bool hit = alive && lane > i && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr);
+        const uint32_t kill = __ballot_sync(0xffffffffu, hit);
+        m &= ~((1u << i) | kill);
+      }
+      if (lane == 0 && keptw) atomicOr(&sm.kbits[w], keptw);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // kept rows -> original keys (cbox is free now), then rank them by (score desc, row asc)
+  uint64_t* kkeys = reinterpret_cast<uint64_t*>(sm.cbox);
+  for (int w = warp; w < nwords; w += NW) {
+    const uint32_t kb = sm.kbits[w];
+    int base = 0;
+    if (lane == 0 && kb) base = atomicAdd(&sm.kcount, __popc(kb));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((kb >> lane) & 1u) kkeys[base + __popc(kb & lt_mask)] = xf.inverse(sm.u.keys[32 * w + lane]);
+  }
+  __syncthreads();
+  const int kc = sm.kcount;
+  bitonic_sort(sm.u.keys, kkeys, kc, KeyIdentity{});
+  return min(kc, a.max_det);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT>
@@ -366,34 +532,46 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   uint64_t* ka = a.keys_a + static_cast<long long>(b) * a.rows_cap;
   uint64_t* kb = a.keys_b + static_cast<long long>(b) * a.rows_cap;
 
+  const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
+  const float thr = a.iou_thr;
+  const GreedyThr gthr = make_greedy_thr(thr);
+  const int cbits = a.cls_bits;
+  const uint32_t cmask = (1u << cbits) - 1u;
+  int kept_n = 0;
+  const uint64_t* kk = nullptr;  // kept keys in rank order (stage 3 input)
+
+  // ---- fast path: class-wise walk (class-aware greedy rule, everything fits shared memory) ----------------------------
+  bool done = false;
+  if constexpr (RULE == YPB_NMS_GREEDY) {
+    if (a.max_wh > 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && a.cls_bits + a.anchor_bits + 32 <= 64 && n > 0) {
+      const int r = classwise_greedy(sm, a, ka, n, cand_box, gthr);
+      if (r >= 0) { kept_n = r; kk = sm.u.keys; done = true; }
+    }
+  }
+  YPB_MARK(1);
+
+  if (!done) {
   // ---- stage 1 ---------------------------------------------------------------------------------------------------
   const uint64_t* sorted;
   if (n <= SORT_SMEM_MAX) {
-    int P = 32;
-    while (P < n) P <<= 1;
-    bitonic_sort(sm.u.keys, ka, n, P);
+    bitonic_sort(sm.u.keys, ka, n, KeyIdentity{});
     sorted = sm.u.keys;
   } else {
     sorted = radix_sort_global(ka, kb, n, sm);
   }
   const int m = min(n, a.max_nms);
-  YPB_MARK(1);
 
   // ---- stage 2 ---------------------------------------------------------------------------------------------------
-  const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
   const float* cand_ang = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
   float4* kept_box = a.kept_box + static_cast<long long>(b) * a.max_det;
   float* kept_area = a.kept_area + static_cast<long long>(b) * a.max_det;
   uint64_t* kept_key = a.kept_key + static_cast<long long>(b) * a.max_det;
   float* rec_g = RULE == YPB_NMS_GREEDY ? nullptr : a.rec + static_cast<long long>(b) * min(a.rows_cap, a.max_nms) * 8;
-  const float thr = a.iou_thr;
-  const uint32_t nc = static_cast<uint32_t>(a.nc);
 
   // thread (t, q): rank t of the chunk, part q.  A warp holds 32 consecutive ranks of ONE part, so the row it tests
   // against (kept row k, or chunk rank i) is the same for all lanes: shared-memory broadcast loads, no divergence.
   const int t = tid & (CH - 1);
   const int q = tid / CH;
-  const GreedyThr gthr = make_greedy_thr(thr);
   float4* kbox = a.max_det <= KEPT_SMEM ? sm.kbox : kept_box;
   float* karea = a.max_det <= KEPT_SMEM ? sm.karea : kept_area;
 
@@ -402,7 +580,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     key = 0; bx = make_float4(0.f, 0.f, 0.f, 0.f); ang = 0.f;
     if (r < m) {
       key = sorted[r];
-      const uint32_t anchor = key_row(key) / nc;
+      const uint32_t anchor = key_row(key) >> cbits;
       bx = cand_box[anchor];
       if constexpr (RULE == YPB_NMS_FAST_PROBIOU) ang = cand_ang[anchor];
     }
@@ -410,7 +588,6 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   uint64_t key_n; float4 bx_n; float ang_n;
   fetch(t, key_n, bx_n, ang_n);
 
-  int kept_n = 0;
   for (int c0 = 0; c0 < m && kept_n < a.max_det; c0 += CH) {
     const int r = c0 + t;
     const bool valid = r < m;
@@ -423,7 +600,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     ObbRec me{};
     if (valid) {
       const uint32_t row = key_row(key);
-      const uint32_t cls = row - (row / nc) * nc;
+      const uint32_t cls = row & cmask;
       const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
       if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
         if (q == 0) me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, ang);  // nms.py:146
@@ -581,14 +758,19 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     YPB_MARK(2 + c0 / CH);
   }
 
+    __syncthreads();
+    kk = kept_key;
+  }  // !done
+
   // ---- stage 3 ---------------------------------------------------------------------------------------------------
   YPB_MARK(30);
   if (tid == 0) a.out_count[b] = kept_n;
   const int cols = 6 + a.extra;
+  const float* cand_ang3 = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
   for (int k = tid; k < kept_n; k += NT) {
-    const uint64_t key = kept_key[k];
+    const uint64_t key = kk[k];
     const uint32_t row = key_row(key);
-    const uint32_t anchor = row / nc, cls = row - anchor * nc;
+    const uint32_t anchor = row >> cbits, cls = row & cmask;
     if (a.out_idx) a.out_idx[static_cast<long long>(b) * a.max_det + k] = a.idx_as_row ? row : anchor;
     if (a.out_rows) {
       float* o = a.out_rows + (static_cast<long long>(b) * a.max_det + k) * cols;
@@ -600,8 +782,8 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
         const long long base = static_cast<long long>(b) * a.pred_sb + static_cast<long long>(anchor) * a.pred_sa;
         for (int e = 0; e < a.extra; ++e)
           o[6 + e] = load_pred(a.pred, a.pred_dtype, base + static_cast<long long>(4 + a.nc + e) * a.pred_sc);
-      } else if (a.extra == 1 && cand_ang) {
-        o[6] = cand_ang[anchor];
+      } else if (a.extra == 1 && cand_ang3) {
+        o[6] = cand_ang3[anchor];
       }
     }
   }
