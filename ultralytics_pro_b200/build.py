@@ -56,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("YPB_EXTRA_NVCC", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -21,6 +21,7 @@ constexpr int CH = 128;              // ranks per chunk
 constexpr int CW = CH / 32;          // mask words per rank of a chunk
 constexpr int PARTS = NT / CH;       // threads cooperating on one rank (== CW: part q owns mask word q)
 constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
+constexpr int RANK_COUNT_MAX = 1024;  // kept rows ranked by counting; beyond that they are sorted
 constexpr int KEPT_SMEM = 1024;      // kept rows held in shared memory (larger max_det spills the list to the workspace)
 static_assert(PARTS == CW && CW == 4, "one thread per (rank, mask word); rows are read as one uint4");
 
@@ -51,7 +52,7 @@ struct __align__(16) Smem {
   uint32_t headpre[SORT_SMEM_MAX / 32];  // heads before each word
   uint16_t seg_start[SORT_SMEM_MAX + 2];
   float red_min[NW], red_max[NW];
-  int nseg, kcount;
+  int nseg, kcount, next_seg;
   uint32_t alive_bits[CW];
   uint32_t kept_bits[CW];
   uint32_t undec_bits[CW];
@@ -164,12 +165,15 @@ __device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1: ranking
 // ---------------------------------------------------------------------------------------------------------------
-// Bitonic sort of P = 32..4096 keys (power of two) by NT threads, ascending.  Thread tid holds the K = max(1, P/NT)
-// keys at positions s*NT + tid in registers, so a compare-exchange at distance j is
-//   j <  32      : a lane exchange (shuffle), no barrier, no shared memory   (40 of the 55 stages at P = 1024)
-//   32 <= j < NT : a round trip through shared memory (2 barriers)
-//   j >= NT      : between two registers of the same thread.
-// The sorted keys end up in s[0..P).
+// Bitonic sort of n <= SORT_SMEM_MAX keys, ascending, result in s[0..P), P = max(256, next power of two).
+// Blocked layout: thread tid holds the KPT = 8 consecutive keys at positions tid*8 .. tid*8+7 in registers, so a
+// compare-exchange at distance j is
+//   j < 8          : between two registers of the same thread (27 of the 55 stages at P = 1024; full ILP)
+//   8 <= j < 256   : a lane exchange (shuffle) between threads of one warp, 8 independent exchanges in flight
+//   j >= 256       : a round trip through shared memory (2 barriers) - 3 stages at P = 1024, none at P = 256.
+// Only P/8 threads take part (one warp up to 256 keys); the others just meet the barriers.
+constexpr int KPT = 8;
+
 __device__ __forceinline__ uint64_t cmpx(uint64_t mine, uint64_t other, bool want_min) {
   const bool take_other = want_min ? other < mine : other > mine;
   return take_other ? other : mine;
@@ -193,30 +197,31 @@ struct KeyClassMajor {
   }
 };
 
-template <int K, typename XF>
-__device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* src, int n, int P, XF xf) {
+template <typename XF>
+__device__ __noinline__ void bitonic_sort(uint64_t* s, const uint64_t* src, int n, XF xf) {
+  int P = 32 * KPT;
+  while (P < n) P <<= 1;
   const int tid = threadIdx.x;
-  uint64_t key[K];
+  const int T = P / KPT;  // participating threads (a multiple of 32)
+  const bool active = tid < T;
+  uint64_t key[KPT];
 #pragma unroll
-  for (int u = 0; u < K; ++u) {
-    const int p = u * NT + tid;
-    key[u] = p < n ? xf(src[p]) : KEY_SENTINEL;
+  for (int u = 0; u < KPT; ++u) {
+    const int p = tid * KPT + u;
+    key[u] = (active && p < n) ? xf(src[p]) : KEY_SENTINEL;
   }
-  __syncthreads();  // src may alias other shared memory that the exchange stages are about to overwrite
-  const bool active = tid < P;  // P < NT: whole warps beyond P idle (P is a multiple of 32)
+  __syncthreads();  // src may alias shared memory that the exchange stages are about to overwrite
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NT) {
-        if constexpr (K > 1) {
-          const int ju = j / NT;
+      if (j < KPT) {
+        if (active) {
 #pragma unroll
-          for (int jb = K / 2; jb >= 1; jb >>= 1) {  // compile-time partner distance: registers stay registers
-            if (ju == jb) {
+          for (int jb = KPT / 2; jb >= 1; jb >>= 1) {  // compile-time distance: registers stay registers
+            if (j == jb) {
 #pragma unroll
-              for (int u = 0; u < K; ++u) {
+              for (int u = 0; u < KPT; ++u) {
                 if ((u & jb) == 0) {
-                  const int p = u * NT + tid;
-                  const bool up = (p & k) == 0;
+                  const bool up = ((tid * KPT + u) & k) == 0;
                   const uint64_t a = key[u], c = key[u | jb];
                   const bool swap = (a > c) == up;
                   key[u] = swap ? c : a;
@@ -226,47 +231,40 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* s
             }
           }
         }
-      } else if (j >= 32) {
+      } else if (j < 32 * KPT) {
+        if (active) {
+          const int lane_xor = j / KPT;
+          const bool lower = (tid & lane_xor) == 0;
+#pragma unroll
+          for (int u = 0; u < KPT; ++u) {
+            const bool up = ((tid * KPT + u) & k) == 0;
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, key[u], lane_xor);
+            key[u] = cmpx(key[u], other, lower == up);
+          }
+        }
+      } else {
         if (active) {
 #pragma unroll
-          for (int u = 0; u < K; ++u) s[u * NT + tid] = key[u];
+          for (int u = 0; u < KPT; ++u) s[tid * KPT + u] = key[u];
         }
         __syncthreads();
         if (active) {
 #pragma unroll
-          for (int u = 0; u < K; ++u) {
-            const int p = u * NT + tid;
+          for (int u = 0; u < KPT; ++u) {
+            const int p = tid * KPT + u;
             const bool up = (p & k) == 0, lower = (p & j) == 0;
             key[u] = cmpx(key[u], s[p ^ j], lower == up);
           }
         }
         __syncthreads();
-      } else if (active) {
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-          const int p = u * NT + tid;
-          const bool up = (p & k) == 0, lower = (p & j) == 0;
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[u], j);
-          key[u] = cmpx(key[u], other, lower == up);
-        }
       }
     }
   }
   if (active) {
 #pragma unroll
-    for (int u = 0; u < K; ++u) s[u * NT + tid] = key[u];
+    for (int u = 0; u < KPT; ++u) s[tid * KPT + u] = key[u];
   }
   __syncthreads();
-}
-
-template <typename XF>
-__device__ __noinline__ void bitonic_sort(uint64_t* s, const uint64_t* src, int n, XF xf) {
-  int P = 32;
-  while (P < n) P <<= 1;
-  if (P <= NT) bitonic_sort_regs<1>(s, src, n, P, xf);
-  else if (P == 2 * NT) bitonic_sort_regs<2>(s, src, n, P, xf);
-  else if (P == 4 * NT) bitonic_sort_regs<4>(s, src, n, P, xf);
-  else bitonic_sort_regs<8>(s, src, n, P, xf);
 }
 
 // One stable 8-bit LSD pass src -> dst over n keys.
@@ -360,6 +358,14 @@ __device__ const uint64_t* radix_sort_global(uint64_t* a, uint64_t* b, int n, Sm
   return src;
 }
 
+// Optional phase timestamps (diagnostic, ypb_debug_set_phase_buffer): per CTA 32 clock64 marks.
+static long long* g_phase_buf = nullptr;
+void set_phase_buffer(long long* p) { g_phase_buf = p; }
+#define YPB_MARK(slot)                                                                   \
+  do {                                                                                   \
+    if (a.dbg && threadIdx.x == 0 && (slot) < 32) a.dbg[blockIdx.x * 32 + (slot)] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // class-wise greedy NMS (fast path of the class-aware rule)
 //
@@ -378,7 +384,10 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const KeyClassMajor xf{a.cls_bits, a.anchor_bits};
+  YPB_MARK(16);
   bitonic_sort(sm.u.keys, ka, n, xf);
+  YPB_MARK(17);
+
   const int nwords = (n + 31) >> 5;
 
   // offset boxes by sorted position, coordinate span, segment heads
@@ -410,13 +419,14 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   if (lane == 0) { sm.red_min[warp] = lo; sm.red_max[warp] = hi; }
-  if (tid == 0) sm.kcount = 0;
+  if (tid == 0) { sm.kcount = 0; sm.next_seg = 0; }
   const int bad = __syncthreads_or(!finite);
   float glo = sm.red_min[0], ghi = sm.red_max[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) { glo = fminf(glo, sm.red_min[w]); ghi = fmaxf(ghi, sm.red_max[w]); }
   if (bad || !(ghi - glo <= 0.999f * a.max_wh)) return -1;  // uniform
 
+  YPB_MARK(18);
   // segment table: prefix of the head flags
   if (warp == 0) {
     int run = 0;
@@ -441,9 +451,14 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   }
   __syncthreads();
 
-  // one warp per class segment
+  YPB_MARK(19);
+  // one warp per class segment, handed out dynamically (segment lengths vary a lot)
   const int nseg = sm.nseg;
-  for (int sid = warp; sid < nseg; sid += NW) {
+  while (true) {
+    int sid = 0;
+    if (lane == 0) sid = atomicAdd(&sm.next_seg, 1);
+    sid = __shfl_sync(0xffffffffu, sid, 0);
+    if (sid >= nseg) break;
     const int s = sm.seg_start[sid], e = sm.seg_start[sid + 1];
     const int w_first = s >> 5, w_last = (e - 1) >> 5;
     for (int w = w_first; w <= w_last; ++w) {
@@ -480,6 +495,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   }
   __syncthreads();
 
+  YPB_MARK(20);
   // kept rows -> original keys (cbox is free now), then rank them by (score desc, row asc)
   uint64_t* kkeys = reinterpret_cast<uint64_t*>(sm.cbox);
   for (int w = warp; w < nwords; w += NW) {
@@ -491,7 +507,21 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   }
   __syncthreads();
   const int kc = sm.kcount;
-  bitonic_sort(sm.u.keys, kkeys, kc, KeyIdentity{});
+  YPB_MARK(21);
+  if (kc <= RANK_COUNT_MAX) {
+    // rank of a kept row = number of kept rows with a smaller key; rows ranked < max_det land in order in sm.u.keys
+    for (int i = tid; i < kc; i += NT) {
+      const uint64_t mine = kkeys[i];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < kc; ++j) rank += kkeys[j] < mine ? 1 : 0;
+      if (rank < a.max_det) sm.u.keys[rank] = mine;
+    }
+    __syncthreads();
+  } else {
+    bitonic_sort(sm.u.keys, kkeys, kc, KeyIdentity{});
+  }
+  YPB_MARK(22);
   return min(kc, a.max_det);
 }
 
@@ -507,14 +537,6 @@ __device__ __forceinline__ float load_pred(const void* p, int dt, long long off)
   if (dt == YPB_F16) return load_as_float<YPB_F16>(p, off);
   return load_as_float<YPB_BF16>(p, off);
 }
-
-// Optional phase timestamps (diagnostic, ypb_debug_set_phase_buffer): per CTA 32 clock64 marks.
-static long long* g_phase_buf = nullptr;
-void set_phase_buffer(long long* p) { g_phase_buf = p; }
-#define YPB_MARK(slot)                                                                   \
-  do {                                                                                   \
-    if (a.dbg && threadIdx.x == 0 && (slot) < 32) a.dbg[blockIdx.x * 32 + (slot)] = clock64(); \
-  } while (0)
 
 template <int RULE>
 __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant__ SuppressArgs a) {
