@@ -198,12 +198,12 @@ struct KeyClassMajor {
 };
 
 template <typename XF>
-__device__ __noinline__ void bitonic_sort(uint64_t* s, const uint64_t* src, int n, XF xf) {
+__device__ __forceinline__ void bitonic_sort(uint64_t* s, const uint64_t* src, int n, XF xf) {
   int P = 32 * KPT;
   while (P < n) P <<= 1;
   const int tid = threadIdx.x;
-  const int T = P / KPT;  // participating threads (a multiple of 32)
-  const bool active = tid < T;
+  const int T = P / KPT;  // participating threads (a multiple of 32: whole warps take part or idle)
+  const bool active = __all_sync(0xffffffffu, tid < T) != 0;  // vote result: warp-uniform for the compiler too
   uint64_t key[KPT];
 #pragma unroll
   for (int u = 0; u < KPT; ++u) {
