@@ -22,7 +22,9 @@ constexpr int CW = CH / 32;          // mask words per rank of a chunk
 constexpr int PARTS = NT / CH;       // threads cooperating on one rank (== CW: part q owns mask word q)
 constexpr int SORT_SMEM_MAX = 4096;  // rows sorted in shared memory
 constexpr int RANK_COUNT_MAX = 1024;  // kept rows ranked by counting; beyond that they are sorted
+constexpr int CW_CLASS_MAX = 1024;    // class histogram bins of the class-wise path
 constexpr int KEPT_SMEM = 1024;      // kept rows held in shared memory (larger max_det spills the list to the workspace)
+static_assert(KEPT_SMEM * 16 >= 2 * RANK_COUNT_MAX * 8, "kept-key scratch");
 static_assert(PARTS == CW && CW == 4, "one thread per (rank, mask word); rows are read as one uint4");
 
 struct __align__(16) Smem {
@@ -47,10 +49,10 @@ struct __align__(16) Smem {
   // class-wise path: every candidate of the image, in (class, score desc) order
   float4 cbox[SORT_SMEM_MAX];
   float carea[SORT_SMEM_MAX];
-  uint32_t kbits[SORT_SMEM_MAX / 32];    // kept flags by sorted position
-  uint32_t headw[SORT_SMEM_MAX / 32];    // segment-head flags by sorted position
-  uint32_t headpre[SORT_SMEM_MAX / 32];  // heads before each word
-  uint16_t seg_start[SORT_SMEM_MAX + 2];
+  uint32_t kbits[SORT_SMEM_MAX / 32];  // kept flags by slot in (class, rank) order
+  uint16_t order[SORT_SMEM_MAX];       // slot in (class, rank) order -> scattered position
+  int ccount[CW_CLASS_MAX];            // rows per class
+  int cstart[CW_CLASS_MAX + 1];        // first slot of each class
   float red_min[NW], red_max[NW];
   int nseg, kcount, next_seg;
   uint32_t alive_bits[CW];
@@ -372,46 +374,139 @@ void set_phase_buffer(long long* p) { g_phase_buf = p; }
 // nms.py:143-149 makes NMS class-aware by adding cls * max_wh to every coordinate.  When all un-offset coordinates of
 // the image span no more than max_wh, boxes of different classes cannot intersect after the offset (the offsets differ
 // by >= max_wh and fp32 rounding is monotone), so their IoU is exactly 0 and the greedy walk decomposes EXACTLY into
-// independent walks per class.  The candidates are sorted by (class, score desc, anchor asc); every class segment is
-// resolved by one warp with lane = candidate: the lowest surviving lane is kept, one ballot strikes what it
-// suppresses - one step per KEPT box instead of one IoU per pair of candidates.  The kept rows are then re-sorted by
-// the original (score desc, row asc) key and cut at max_det (nms.py:157).  Same fp32 arithmetic on the same offset
-// boxes as the dense path, so results are bit-identical.  Returns the number of kept rows (their keys in sm.u.keys),
-// or -1 if the span condition fails (caller falls back to the dense walk).
+// independent walks per class:
+//   1. counting sort of the candidates by class (shared-memory histogram + scatter), boxes gathered on the way;
+//   2. one warp per class (handed out dynamically): the class's rows are ranked (score desc, anchor asc) with a
+//      register/shuffle bitonic network, then walked with lane = row: the lowest surviving lane is kept and one ballot
+//      strikes what it suppresses - one step per KEPT box instead of one IoU per pair of candidates;
+//   3. the kept rows of all classes are ranked by the original (score desc, row asc) key by counting and cut at
+//      max_det (nms.py:157).
+// Same fp32 arithmetic on the same offset boxes as the dense path, so results are bit-identical.  Returns the number
+// of kept rows (their keys, in order, in sm.u.keys) or -1 when a precondition fails (span, a class with more than
+// CW_SEG_MAX rows, non-finite boxes): the caller then takes the dense walk.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int CW_SEG_MAX = 256;     // rows of one class a single warp ranks in registers (8 per lane)
+
+// ascending bitonic sort of 32*KP keys held KP per lane (blocked: lane holds ranks lane*KP .. lane*KP+KP-1)
+template <int KP>
+__device__ __forceinline__ void warp_bitonic(uint64_t (&key)[KP], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * KP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < KP) {
+#pragma unroll
+        for (int u = 0; u < KP; ++u) {
+          if ((u & j) == 0) {
+            const bool up = ((lane * KP + u) & k) == 0;
+            const uint64_t a = key[u], c = key[u | j];
+            const bool swap = (a > c) == up;
+            key[u] = swap ? c : a;
+            key[u | j] = swap ? a : c;
+          }
+        }
+      } else {
+        const int lx = j / KP;
+        const bool lower = (lane & lx) == 0;
+#pragma unroll
+        for (int u = 0; u < KP; ++u) {
+          const bool up = ((lane * KP + u) & k) == 0;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[u], lx);
+          key[u] = cmpx(key[u], other, lower == up);
+        }
+      }
+    }
+  }
+}
+
+// Ranks the L <= 32*KP rows of one class: order[s + r] = scattered position of the row of rank r.
+template <int KP>
+__device__ __forceinline__ void rank_segment(Smem& sm, int s, int L, int abits, int cbits, int lane) {
+  uint64_t key[KP];
+#pragma unroll
+  for (int u = 0; u < KP; ++u) {
+    const int e = lane * KP + u;
+    key[u] = KEY_SENTINEL;
+    if (e < L) {
+      const uint64_t k = sm.u.keys[s + e];
+      const uint64_t anchor = static_cast<uint32_t>(k) >> cbits;
+      key[u] = ((k >> 32) << (abits + 12)) | (anchor << 12) | static_cast<uint64_t>(s + e);
+    }
+  }
+  warp_bitonic<KP>(key, lane);
+#pragma unroll
+  for (int u = 0; u < KP; ++u) {
+    const int r = lane * KP + u;
+    if (r < L) sm.order[s + r] = static_cast<uint16_t>(key[u] & 0xfffull);
+  }
+}
+
 __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t* ka, int n, const float4* cand_box,
                                 const GreedyThr& gthr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const KeyClassMajor xf{a.cls_bits, a.anchor_bits};
+  const int cbits = a.cls_bits;
+  const uint32_t cmask = (1u << cbits) - 1u;
+  const int nbins = 1 << cbits;
   YPB_MARK(16);
-  bitonic_sort(sm.u.keys, ka, n, xf);
-  YPB_MARK(17);
 
-  const int nwords = (n + 31) >> 5;
-
-  // offset boxes by sorted position, coordinate span, segment heads
+  // ---- 1. counting sort by class ----------------------------------------------------------------------------------
+  for (int c = tid; c < nbins; c += NT) sm.ccount[c] = 0;
+  if (tid == 0) { sm.kcount = 0; sm.next_seg = 0; }
+  for (int w = tid; w < (n + 31) / 32; w += NT) sm.kbits[w] = 0;
+  __syncthreads();
+  constexpr int PER = SORT_SMEM_MAX / NT;  // rows per thread
+  uint64_t mykey[PER];
+  int myslot[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = u * NT + tid;
+    if (i < n) {
+      mykey[u] = ka[i];
+      myslot[u] = atomicAdd(&sm.ccount[static_cast<uint32_t>(mykey[u]) & cmask], 1);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive prefix over the class bins (32 per step); also the longest class
+    int run = 0, longest = 0;
+    for (int c0 = 0; c0 < nbins; c0 += 32) {
+      const int c = c0 + lane;
+      const int v = c < nbins ? sm.ccount[c] : 0;
+      longest = max(longest, v);
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (c < nbins) sm.cstart[c] = run + inc - v;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
+    if (lane == 0) { sm.cstart[nbins] = run; sm.nseg = longest; }
+  }
+  __syncthreads();
+  if (sm.nseg > CW_SEG_MAX) return -1;  // uniform: a class too long for one warp - dense walk
   float lo = INFINITY, hi = -INFINITY;
   bool finite = true;
-  for (int w = warp; w < nwords; w += NW) {
-    const int p = 32 * w + lane;
-    bool head = false;
-    if (p < n) {
-      const uint64_t k = sm.u.keys[p];
-      const uint32_t anchor = static_cast<uint32_t>(k & ((1ull << a.anchor_bits) - 1ull));
-      const uint32_t cls = static_cast<uint32_t>(k >> (32 + a.anchor_bits));
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = u * NT + tid;
+    if (i < n) {
+      const uint32_t row = static_cast<uint32_t>(mykey[u]);
+      const uint32_t cls = row & cmask, anchor = row >> cbits;
+      const int pos = sm.cstart[cls] + myslot[u];
       const float4 bx = cand_box[anchor];
       lo = fminf(lo, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
       hi = fmaxf(hi, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
       finite &= isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w);
       const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
       const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
-      sm.cbox[p] = ob;
-      sm.carea[p] = box_area(ob);
-      head = p == 0 || static_cast<uint32_t>(sm.u.keys[p - 1] >> (32 + a.anchor_bits)) != cls;
+      sm.u.keys[pos] = mykey[u];
+      sm.cbox[pos] = ob;
+      sm.carea[pos] = box_area(ob);
     }
-    const unsigned hb = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) { sm.headw[w] = hb; sm.kbits[w] = 0; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -419,54 +514,34 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   if (lane == 0) { sm.red_min[warp] = lo; sm.red_max[warp] = hi; }
-  if (tid == 0) { sm.kcount = 0; sm.next_seg = 0; }
   const int bad = __syncthreads_or(!finite);
   float glo = sm.red_min[0], ghi = sm.red_max[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) { glo = fminf(glo, sm.red_min[w]); ghi = fmaxf(ghi, sm.red_max[w]); }
   if (bad || !(ghi - glo <= 0.999f * a.max_wh)) return -1;  // uniform
-
-  YPB_MARK(18);
-  // segment table: prefix of the head flags
-  if (warp == 0) {
-    int run = 0;
-    for (int w0 = 0; w0 < nwords; w0 += 32) {
-      const int w = w0 + lane;
-      const int c = w < nwords ? __popc(sm.headw[w]) : 0;
-      int inc = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (w < nwords) sm.headpre[w] = run + inc - c;
-      run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) { sm.nseg = run; sm.seg_start[run] = static_cast<uint16_t>(n); }
-  }
-  __syncthreads();
-  for (int w = warp; w < nwords; w += NW) {
-    const uint32_t hb = sm.headw[w];
-    if ((hb >> lane) & 1u) sm.seg_start[sm.headpre[w] + __popc(hb & lt_mask)] = static_cast<uint16_t>(32 * w + lane);
-  }
-  __syncthreads();
-
   YPB_MARK(19);
-  // one warp per class segment, handed out dynamically (segment lengths vary a lot)
-  const int nseg = sm.nseg;
+
+  // ---- 2. one warp per class, handed out dynamically ------------------------------------------------------------------
   while (true) {
-    int sid = 0;
-    if (lane == 0) sid = atomicAdd(&sm.next_seg, 1);
-    sid = __shfl_sync(0xffffffffu, sid, 0);
-    if (sid >= nseg) break;
-    const int s = sm.seg_start[sid], e = sm.seg_start[sid + 1];
+    int cid = 0;
+    if (lane == 0) cid = atomicAdd(&sm.next_seg, 1);
+    cid = __shfl_sync(0xffffffffu, cid, 0);
+    if (cid >= nbins) break;
+    const int s = sm.cstart[cid], e = sm.cstart[cid + 1];
+    const int L = e - s;
+    if (L == 0) continue;
+    if (L <= 32) rank_segment<1>(sm, s, L, a.anchor_bits, cbits, lane);
+    else if (L <= 64) rank_segment<2>(sm, s, L, a.anchor_bits, cbits, lane);
+    else if (L <= 128) rank_segment<4>(sm, s, L, a.anchor_bits, cbits, lane);
+    else rank_segment<8>(sm, s, L, a.anchor_bits, cbits, lane);
+    __syncwarp();
     const int w_first = s >> 5, w_last = (e - 1) >> 5;
     for (int w = w_first; w <= w_last; ++w) {
-      const int p = 32 * w + lane;
-      const bool in = p >= s && p < e;
+      const int q = 32 * w + lane;  // slot in rank order (slots s..e-1 belong to this class)
+      const bool in = q >= s && q < e;
       float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
       float marea = 0.f;
-      if (in) { mine = sm.cbox[p]; marea = sm.carea[p]; }
+      if (in) { const int p = sm.order[q]; mine = sm.cbox[p]; marea = sm.carea[p]; }
       bool alive = in;
       // rows of this class kept in earlier words
       for (int w2 = w_first; w2 < w; ++w2) {
@@ -475,7 +550,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
         while (kb) {
           const int i = __ffs(kb) - 1;
           kb &= kb - 1;
-          const int pi = 32 * w2 + i;
+          const int pi = sm.order[32 * w2 + i];
           if (alive && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr)) alive = false;
         }
       }
@@ -484,7 +559,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
       while (m) {
         const int i = __ffs(m) - 1;
         keptw |= 1u << i;
-        const int pi = 32 * w + i;
+        const int pi = sm.order[32 * w + i];
         const bool hit = alive && lane > i && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr);
         const uint32_t kill = __ballot_sync(0xffffffffu, hit);
         m &= ~((1u << i) | kill);
@@ -494,33 +569,34 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     }
   }
   __syncthreads();
-
   YPB_MARK(20);
-  // kept rows -> original keys (cbox is free now), then rank them by (score desc, row asc)
-  uint64_t* kkeys = reinterpret_cast<uint64_t*>(sm.cbox);
+
+  // ---- 3. kept rows, ranked by (score desc, row asc) -------------------------------------------------------------------
+  uint64_t* kkeys = reinterpret_cast<uint64_t*>(sm.kbox);  // KEPT_SMEM float4 = 2 * RANK_COUNT_MAX keys
+  const int nwords = (n + 31) >> 5;
   for (int w = warp; w < nwords; w += NW) {
     const uint32_t kb = sm.kbits[w];
     int base = 0;
     if (lane == 0 && kb) base = atomicAdd(&sm.kcount, __popc(kb));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if ((kb >> lane) & 1u) kkeys[base + __popc(kb & lt_mask)] = xf.inverse(sm.u.keys[32 * w + lane]);
+    if (((kb >> lane) & 1u) && base + __popc(kb & lt_mask) < RANK_COUNT_MAX * 2)
+      kkeys[base + __popc(kb & lt_mask)] = sm.u.keys[sm.order[32 * w + lane]];
   }
   __syncthreads();
   const int kc = sm.kcount;
   YPB_MARK(21);
-  if (kc <= RANK_COUNT_MAX) {
-    // rank of a kept row = number of kept rows with a smaller key; rows ranked < max_det land in order in sm.u.keys
-    for (int i = tid; i < kc; i += NT) {
-      const uint64_t mine = kkeys[i];
-      int rank = 0;
+  if (kc > RANK_COUNT_MAX * 2) return -1;  // uniform; more kept rows than the ranking scratch holds - dense walk
+  // rank of a kept row = number of kept rows with a smaller key; the first max_det land in order in out_keys
+  uint64_t* out_keys = reinterpret_cast<uint64_t*>(sm.cbox);  // boxes are no longer needed
+  __syncthreads();
+  for (int i = tid; i < kc; i += NT) {
+    const uint64_t mine = kkeys[i];
+    int rank = 0;
 #pragma unroll 4
-      for (int j = 0; j < kc; ++j) rank += kkeys[j] < mine ? 1 : 0;
-      if (rank < a.max_det) sm.u.keys[rank] = mine;
-    }
-    __syncthreads();
-  } else {
-    bitonic_sort(sm.u.keys, kkeys, kc, KeyIdentity{});
+    for (int j = 0; j < kc; ++j) rank += kkeys[j] < mine ? 1 : 0;
+    if (rank < a.max_det) out_keys[rank] = mine;
   }
+  __syncthreads();
   YPB_MARK(22);
   return min(kc, a.max_det);
 }
@@ -565,9 +641,10 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   // ---- fast path: class-wise walk (class-aware greedy rule, everything fits shared memory) ----------------------------
   bool done = false;
   if constexpr (RULE == YPB_NMS_GREEDY) {
-    if (a.max_wh > 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && a.cls_bits + a.anchor_bits + 32 <= 64 && n > 0) {
+    if (a.max_wh > 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && (1 << a.cls_bits) <= CW_CLASS_MAX &&
+        a.anchor_bits <= 20 && n > 0) {
       const int r = classwise_greedy(sm, a, ka, n, cand_box, gthr);
-      if (r >= 0) { kept_n = r; kk = sm.u.keys; done = true; }
+      if (r >= 0) { kept_n = r; kk = reinterpret_cast<const uint64_t*>(sm.cbox); done = true; }
     }
   }
   YPB_MARK(1);
