@@ -24,7 +24,7 @@ m = buf.view(B, 32).cpu()
 cand = plan.cand.cpu(); cnt = plan.count.cpu()
 for b in list(range(min(B, 6))):
     r = m[b]
-    marks = [(i, int(r[i] - r[0])) for i in range(32) if r[i] != 0]
+    marks = [(i, int(r[i] - r[0]) if i not in (23,24,25,26) else int(r[i])) for i in range(32) if r[i] != 0]
     print(f"img {b}: cand {int(cand[b])} kept {int(cnt[b])} cycles:", marks)
 tot = (m[:, 31] - m[:, 0]).float()
 print("total cycles per CTA: mean %.0f max %.0f min %.0f" % (tot.mean(), tot.max(), tot.min()))

@@ -52,9 +52,12 @@ struct __align__(16) Smem {
   uint32_t kbits[SORT_SMEM_MAX / 32];  // kept flags by slot in (class, rank) order
   uint16_t order[SORT_SMEM_MAX];       // slot in (class, rank) order -> scattered position
   int ccount[CW_CLASS_MAX];            // rows per class
+  int ckept[CW_CLASS_MAX];             // kept rows per class so far
+  uint16_t krank[SORT_SMEM_MAX];       // per class (at its slot range): ranks of the kept rows, in order
   int cstart[CW_CLASS_MAX + 1];        // first slot of each class
   float red_min[NW], red_max[NW];
-  int nseg, kcount, next_seg;
+  uint16_t clist[CW_CLASS_MAX];        // non-empty classes
+  int nseg, kcount, next_seg, longest;
   uint32_t alive_bits[CW];
   uint32_t kept_bits[CW];
   uint32_t undec_bits[CW];
@@ -387,58 +390,50 @@ void set_phase_buffer(long long* p) { g_phase_buf = p; }
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int CW_SEG_MAX = 256;     // rows of one class a single warp ranks in registers (8 per lane)
 
-// ascending bitonic sort of 32*KP keys held KP per lane (blocked: lane holds ranks lane*KP .. lane*KP+KP-1)
+// Ranks the L <= 32*KP rows of one class by counting: rank = number of rows of the class with a smaller
+// (score desc, anchor asc) key.  Every row's key is read by all lanes as one shared-memory broadcast; the L x KP
+// comparisons are independent (no exchange network, no dependent chain).  order[s + rank] = scattered position.
 template <int KP>
-__device__ __forceinline__ void warp_bitonic(uint64_t (&key)[KP], int lane) {
+__device__ __forceinline__ void rank_segment(Smem& sm, int s, int L, int cbits, int lane) {
+  uint64_t mine[KP];
+  int rank[KP];
 #pragma unroll
-  for (int k = 2; k <= 32 * KP; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j < KP) {
-#pragma unroll
-        for (int u = 0; u < KP; ++u) {
-          if ((u & j) == 0) {
-            const bool up = ((lane * KP + u) & k) == 0;
-            const uint64_t a = key[u], c = key[u | j];
-            const bool swap = (a > c) == up;
-            key[u] = swap ? c : a;
-            key[u | j] = swap ? a : c;
-          }
-        }
-      } else {
-        const int lx = j / KP;
-        const bool lower = (lane & lx) == 0;
-#pragma unroll
-        for (int u = 0; u < KP; ++u) {
-          const bool up = ((lane * KP + u) & k) == 0;
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[u], lx);
-          key[u] = cmpx(key[u], other, lower == up);
-        }
-      }
+  for (int u = 0; u < KP; ++u) {
+    const int e = lane + 32 * u;
+    rank[u] = 0;
+    mine[u] = KEY_SENTINEL;
+    if (e < L) {
+      const uint64_t k = sm.u.keys[s + e];
+      mine[u] = (k & 0xffffffff00000000ull) | (static_cast<uint32_t>(k) >> cbits);  // (score desc, anchor asc)
     }
+  }
+#pragma unroll 4
+  for (int e = 0; e < L; ++e) {
+    const uint64_t k = sm.u.keys[s + e];
+    const uint64_t o = (k & 0xffffffff00000000ull) | (static_cast<uint32_t>(k) >> cbits);
+#pragma unroll
+    for (int u = 0; u < KP; ++u) rank[u] += o < mine[u] ? 1 : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < KP; ++u) {
+    const int e = lane + 32 * u;
+    if (e < L) sm.order[s + rank[u]] = static_cast<uint16_t>(s + e);
   }
 }
 
-// Ranks the L <= 32*KP rows of one class: order[s + r] = scattered position of the row of rank r.
-template <int KP>
-__device__ __forceinline__ void rank_segment(Smem& sm, int s, int L, int abits, int cbits, int lane) {
-  uint64_t key[KP];
-#pragma unroll
-  for (int u = 0; u < KP; ++u) {
-    const int e = lane * KP + u;
-    key[u] = KEY_SENTINEL;
-    if (e < L) {
-      const uint64_t k = sm.u.keys[s + e];
-      const uint64_t anchor = static_cast<uint32_t>(k) >> cbits;
-      key[u] = ((k >> 32) << (abits + 12)) | (anchor << 12) | static_cast<uint64_t>(s + e);
-    }
+// One greedy test of every lane's row against the same higher-ranked row (kb, ka) of its class.  Branch-free for the
+// whole warp; only a borderline pair (|IoU - thr| within 2^-20 relative) takes the exact fp64 decision.
+__device__ __forceinline__ bool lanes_suppressed_by(const float4& kb, float ka, const float4& mine, float marea,
+                                                    const GreedyThr& t, bool consider) {
+  const PairGeom g = pair_geom(kb, ka, mine, marea);
+  unsigned su, mb;
+  greedy_flags(g, t, su, mb);
+  bool hit = consider && su != 0u;
+  const bool border = consider && mb != 0u;
+  if (__any_sync(0xffffffffu, border)) {
+    if (border) hit = greedy_exact(g.inter, g.uni, t.mid, t.tie_up);
   }
-  warp_bitonic<KP>(key, lane);
-#pragma unroll
-  for (int u = 0; u < KP; ++u) {
-    const int r = lane * KP + u;
-    if (r < L) sm.order[s + r] = static_cast<uint16_t>(key[u] & 0xfffull);
-  }
+  return hit;
 }
 
 __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t* ka, int n, const float4* cand_box,
@@ -451,7 +446,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   YPB_MARK(16);
 
   // ---- 1. counting sort by class ----------------------------------------------------------------------------------
-  for (int c = tid; c < nbins; c += NT) sm.ccount[c] = 0;
+  for (int c = tid; c < nbins; c += NT) { sm.ccount[c] = 0; sm.ckept[c] = 0; }
   if (tid == 0) { sm.kcount = 0; sm.next_seg = 0; }
   for (int w = tid; w < (n + 31) / 32; w += NT) sm.kbits[w] = 0;
   __syncthreads();
@@ -468,7 +463,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   }
   __syncthreads();
   if (warp == 0) {  // exclusive prefix over the class bins (32 per step); also the longest class
-    int run = 0, longest = 0;
+    int run = 0, longest = 0, nlist = 0;
     for (int c0 = 0; c0 < nbins; c0 += 32) {
       const int c = c0 + lane;
       const int v = c < nbins ? sm.ccount[c] : 0;
@@ -481,13 +476,16 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
       }
       if (c < nbins) sm.cstart[c] = run + inc - v;
       run += __shfl_sync(0xffffffffu, inc, 31);
+      const unsigned ne = __ballot_sync(0xffffffffu, v > 0);
+      if (v > 0) sm.clist[nlist + __popc(ne & lt_mask)] = static_cast<uint16_t>(c);
+      nlist += __popc(ne);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
-    if (lane == 0) { sm.cstart[nbins] = run; sm.nseg = longest; }
+    if (lane == 0) { sm.cstart[nbins] = run; sm.longest = longest; sm.nseg = nlist; }
   }
   __syncthreads();
-  if (sm.nseg > CW_SEG_MAX) return -1;  // uniform: a class too long for one warp - dense walk
+  if (sm.longest > CW_SEG_MAX) return -1;  // uniform: a class too long for one warp - dense walk
   float lo = INFINITY, hi = -INFINITY;
   bool finite = true;
 #pragma unroll
@@ -522,49 +520,59 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   YPB_MARK(19);
 
   // ---- 2. one warp per class, handed out dynamically ------------------------------------------------------------------
+  const int nseg = sm.nseg;
   while (true) {
-    int cid = 0;
-    if (lane == 0) cid = atomicAdd(&sm.next_seg, 1);
-    cid = __shfl_sync(0xffffffffu, cid, 0);
-    if (cid >= nbins) break;
+    int sid = 0;
+    if (lane == 0) sid = atomicAdd(&sm.next_seg, 1);
+    sid = __shfl_sync(0xffffffffu, sid, 0);
+    if (sid >= nseg) break;
+    const int cid = sm.clist[sid];
     const int s = sm.cstart[cid], e = sm.cstart[cid + 1];
     const int L = e - s;
-    if (L == 0) continue;
-    if (L <= 32) rank_segment<1>(sm, s, L, a.anchor_bits, cbits, lane);
-    else if (L <= 64) rank_segment<2>(sm, s, L, a.anchor_bits, cbits, lane);
-    else if (L <= 128) rank_segment<4>(sm, s, L, a.anchor_bits, cbits, lane);
-    else rank_segment<8>(sm, s, L, a.anchor_bits, cbits, lane);
+    if (L <= 32) rank_segment<1>(sm, s, L, cbits, lane);
+    else if (L <= 64) rank_segment<2>(sm, s, L, cbits, lane);
+    else if (L <= 128) rank_segment<4>(sm, s, L, cbits, lane);
+    else rank_segment<8>(sm, s, L, cbits, lane);
     __syncwarp();
-    const int w_first = s >> 5, w_last = (e - 1) >> 5;
-    for (int w = w_first; w <= w_last; ++w) {
-      const int q = 32 * w + lane;  // slot in rank order (slots s..e-1 belong to this class)
-      const bool in = q >= s && q < e;
+    // walk the class in rank order, 32 ranks (one per lane) at a time
+    for (int r0 = 0; r0 < L; r0 += 32) {
+      const bool in = r0 + lane < L;
       float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
       float marea = 0.f;
-      if (in) { const int p = sm.order[q]; mine = sm.cbox[p]; marea = sm.carea[p]; }
+      if (in) { const int p = sm.order[s + r0 + lane]; mine = sm.cbox[p]; marea = sm.carea[p]; }
       bool alive = in;
-      // rows of this class kept in earlier words
-      for (int w2 = w_first; w2 < w; ++w2) {
-        uint32_t kb = sm.kbits[w2];
-        if (w2 == w_first) kb &= ~((1u << (s & 31)) - 1u);
-        while (kb) {
-          const int i = __ffs(kb) - 1;
-          kb &= kb - 1;
-          const int pi = sm.order[32 * w2 + i];
-          if (alive && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr)) alive = false;
-        }
+      // rows of this class kept in earlier groups: their boxes were parked in rank order at the front of the segment
+      const int nk = sm.ckept[cid];
+      for (int k = 0; k < nk; ++k) {
+        const int pk = sm.order[s + sm.krank[s + k]];
+        const bool hit = lanes_suppressed_by(sm.cbox[pk], sm.carea[pk], mine, marea, gthr, alive);  // all lanes call
+        alive = alive && !hit;
       }
-      // inside the word: the lowest surviving lane is kept and strikes the lanes it suppresses
+      // inside the group: the lowest surviving lane is kept; its box reaches the others by shuffle and one ballot
+      // strikes the lanes it suppresses
       uint32_t m = __ballot_sync(0xffffffffu, alive), keptw = 0;
       while (m) {
         const int i = __ffs(m) - 1;
         keptw |= 1u << i;
-        const int pi = sm.order[32 * w + i];
-        const bool hit = alive && lane > i && greedy_suppresses(sm.cbox[pi], sm.carea[pi], mine, marea, gthr);
-        const uint32_t kill = __ballot_sync(0xffffffffu, hit);
-        m &= ~((1u << i) | kill);
+        const float4 kb = make_float4(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i),
+                                      __shfl_sync(0xffffffffu, mine.z, i), __shfl_sync(0xffffffffu, mine.w, i));
+        const float ka = __shfl_sync(0xffffffffu, marea, i);
+        const bool hit = lanes_suppressed_by(kb, ka, mine, marea, gthr, lane > i && ((m >> lane) & 1u) != 0u);
+        m &= ~((1u << i) | __ballot_sync(0xffffffffu, hit));
       }
-      if (lane == 0 && keptw) atomicOr(&sm.kbits[w], keptw);
+      // record the group's kept ranks (kept flag by slot, and the per-class list used by later groups)
+      if ((keptw >> lane) & 1u) {
+        sm.krank[s + nk + __popc(keptw & lt_mask)] = static_cast<uint16_t>(r0 + lane);
+      }
+      if (lane == 0) {
+        sm.ckept[cid] = nk + __popc(keptw);
+        if (keptw) {
+          // slots s+r0 .. s+r0+31 straddle at most two kbits words
+          const int q0 = s + r0;
+          atomicOr(&sm.kbits[q0 >> 5], keptw << (q0 & 31));
+          if ((q0 & 31) && ((q0 >> 5) + 1) < SORT_SMEM_MAX / 32) atomicOr(&sm.kbits[(q0 >> 5) + 1], keptw >> (32 - (q0 & 31)));
+        }
+      }
       __syncwarp();
     }
   }
