@@ -57,6 +57,7 @@ struct __align__(16) Smem {
   int cstart[CW_CLASS_MAX + 1];        // first slot of each class
   float red_min[NW], red_max[NW];
   uint16_t clist[CW_CLASS_MAX];        // non-empty classes
+  uint16_t clist2[CW_CLASS_MAX];       // the same, longest first
   int nseg, kcount, next_seg, longest;
   uint32_t alive_bits[CW];
   uint32_t kept_bits[CW];
@@ -485,6 +486,20 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     if (lane == 0) { sm.cstart[nbins] = run; sm.longest = longest; sm.nseg = nlist; }
   }
   __syncthreads();
+  // longest classes first: they bound the critical path of the dynamic hand-out (rank by counting, ties by class id)
+  {
+    const int nl = sm.nseg;
+    for (int i = tid; i < nl; i += NT) {
+      const int c = sm.clist[i], v = sm.ccount[c];
+      int r = 0;
+      for (int j = 0; j < nl; ++j) {
+        const int cj = sm.clist[j], vj = sm.ccount[cj];
+        r += (vj > v || (vj == v && cj < c)) ? 1 : 0;
+      }
+      sm.clist2[r] = static_cast<uint16_t>(c);
+    }
+  }
+  __syncthreads();
   if (sm.longest > CW_SEG_MAX) return -1;  // uniform: a class too long for one warp - dense walk
   float lo = INFINITY, hi = -INFINITY;
   bool finite = true;
@@ -526,7 +541,7 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     if (lane == 0) sid = atomicAdd(&sm.next_seg, 1);
     sid = __shfl_sync(0xffffffffu, sid, 0);
     if (sid >= nseg) break;
-    const int cid = sm.clist[sid];
+    const int cid = sm.clist2[sid];
     const int s = sm.cstart[cid], e = sm.cstart[cid + 1];
     const int L = e - s;
     if (L <= 32) rank_segment<1>(sm, s, L, cbits, lane);
@@ -543,10 +558,23 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
       bool alive = in;
       // rows of this class kept in earlier groups: their boxes were parked in rank order at the front of the segment
       const int nk = sm.ckept[cid];
-      for (int k = 0; k < nk; ++k) {
-        const int pk = sm.order[s + sm.krank[s + k]];
-        const bool hit = lanes_suppressed_by(sm.cbox[pk], sm.carea[pk], mine, marea, gthr, alive);  // all lanes call
-        alive = alive && !hit;
+      for (int k0 = 0; k0 < nk; k0 += 32) {
+        // lane l fetches kept row k0 + l (independent 3-hop shared-memory chains), then they are broadcast by shuffle
+        float4 kb = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ka = 0.f;
+        if (k0 + lane < nk) {
+          const int pk = sm.order[s + sm.krank[s + k0 + lane]];
+          kb = sm.cbox[pk];
+          ka = sm.carea[pk];
+        }
+        const int cnt = min(32, nk - k0);
+        for (int k = 0; k < cnt; ++k) {
+          const float4 b4 = make_float4(__shfl_sync(0xffffffffu, kb.x, k), __shfl_sync(0xffffffffu, kb.y, k),
+                                        __shfl_sync(0xffffffffu, kb.z, k), __shfl_sync(0xffffffffu, kb.w, k));
+          const float a1 = __shfl_sync(0xffffffffu, ka, k);
+          const bool hit = lanes_suppressed_by(b4, a1, mine, marea, gthr, alive);  // all lanes call
+          alive = alive && !hit;
+        }
       }
       // inside the group: the lowest surviving lane is kept; its box reaches the others by shuffle and one ballot
       // strikes the lanes it suppresses
