@@ -1,0 +1,104 @@
+"""Rebind the reference's own symbols to the B200 implementations.
+
+    import ultralytics_pro_b200.patch as ypb_patch
+    ypb_patch.install()        # after `import ultralytics`
+    ...
+    ypb_patch.uninstall()
+
+What is rebound (reference paths relative to ultralytics/):
+  utils/nms.py:13          non_max_suppression   - on the module object (seen by models/yolo/detect/predict.py:54 and
+                                                   detect/val.py:115, which call `nms.non_max_suppression`) and on
+                                                   nn/autobackend.py:22, which imported the function by name
+  utils/nms.py:169         TorchNMS.nms / fast_nms / batched_nms - patched as static methods ON the class object, because
+                                                   models/yolo/obb/val.py:14 and engine/exporter.py:122 hold the class by name
+  nn/modules/head.py:151   Detect._inference (and the byte-identical copies MAFDetect :340, IDetect :535, DDetect :724);
+                                                   Segment/Pose/OBB/World/YOLOE/v10 inherit it
+CUDA tensors take the kernels; anything else (CPU tensors, training mode, export) is handed to the original, untouched
+reference function - that is the reference running, not a fallback of this library.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+_saved: dict = {}
+
+_HEAD_CLASSES = ("Detect", "MAFDetect", "IDetect", "DDetect")
+
+
+def _wrap_nms(ref_fn, ours):
+    def non_max_suppression(prediction, *args, **kwargs):
+        p = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
+        if getattr(p, "is_cuda", False):
+            return ours(prediction, *args, **kwargs)
+        return ref_fn(prediction, *args, **kwargs)
+
+    non_max_suppression.__wrapped__ = ref_fn
+    non_max_suppression.__doc__ = ref_fn.__doc__
+    return non_max_suppression
+
+
+def _wrap_inference(ref_fn, ours):
+    def _inference(self, x):
+        if x[0].is_cuda and not getattr(self, "export", False):
+            return ours(self, x)
+        return ref_fn(self, x)
+
+    _inference.__wrapped__ = ref_fn
+    return _inference
+
+
+def _wrap_static(ref_fn, ours):
+    def f(boxes, *args, **kwargs):
+        if getattr(boxes, "is_cuda", False):
+            return ours(boxes, *args, **kwargs)
+        return ref_fn(boxes, *args, **kwargs)
+
+    f.__wrapped__ = ref_fn
+    return staticmethod(f)
+
+
+def install() -> list:
+    """Patch the already-importable `ultralytics` package in place; returns the list of rebound symbols."""
+    from . import head as our_head
+    from . import nms as our_nms
+
+    if _saved:
+        return sorted(_saved)
+    done = []
+    ref_nms = importlib.import_module("ultralytics.utils.nms")
+    _saved["ultralytics.utils.nms.non_max_suppression"] = (ref_nms, "non_max_suppression", ref_nms.non_max_suppression)
+    wrapped = _wrap_nms(ref_nms.non_max_suppression, our_nms.non_max_suppression)
+    ref_nms.non_max_suppression = wrapped
+    done.append("ultralytics.utils.nms.non_max_suppression")
+    ab = sys.modules.get("ultralytics.nn.autobackend")
+    if ab is not None and hasattr(ab, "non_max_suppression"):
+        _saved["ultralytics.nn.autobackend.non_max_suppression"] = (ab, "non_max_suppression", ab.non_max_suppression)
+        ab.non_max_suppression = wrapped
+        done.append("ultralytics.nn.autobackend.non_max_suppression")
+    cls = ref_nms.TorchNMS
+    for name in ("nms", "fast_nms", "batched_nms"):
+        orig = cls.__dict__[name]
+        _saved[f"ultralytics.utils.nms.TorchNMS.{name}"] = (cls, name, orig)
+        setattr(cls, name, _wrap_static(getattr(cls, name), getattr(our_nms.TorchNMS, name)))
+        done.append(f"ultralytics.utils.nms.TorchNMS.{name}")
+    # fast_nms resolves iou_func by __name__, so the reference's own box_iou / batch_probiou callables are recognised
+    try:
+        ref_head = importlib.import_module("ultralytics.nn.modules.head")
+    except Exception:  # optional third-party imports of the modules zoo missing: decode stays with the reference
+        ref_head = None
+    if ref_head is not None:
+        for cname in _HEAD_CLASSES:
+            c = getattr(ref_head, cname, None)
+            if c is None or "_inference" not in c.__dict__:
+                continue
+            _saved[f"ultralytics.nn.modules.head.{cname}._inference"] = (c, "_inference", c.__dict__["_inference"])
+            c._inference = _wrap_inference(c.__dict__["_inference"], our_head.detect_inference)
+            done.append(f"ultralytics.nn.modules.head.{cname}._inference")
+    return done
+
+
+def uninstall() -> None:
+    for _, (obj, name, orig) in list(_saved.items()):
+        setattr(obj, name, orig)
+    _saved.clear()
