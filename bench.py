@@ -225,45 +225,55 @@ def run_ours(args):
     in_bytes_img = cfg.no * cfg.anchors * esize  # algorithmic bytes per image of the fused path
 
     # ---- synthetic inputs, resident in HBM before any timing; NSETS x 310 MB > 126 MB L2 ---------------------------
-    NSETS = 3
+    # LANES independent pipelines (own stream, scratch, result buffers, CUDA graphs) take the steps round-robin, so the
+    # HBM-bound class scan of one batch overlaps the latency-bound survivor decode / suppression of the previous one.
+    LANES = max(1, args.lanes)
+    NSETS = 2 * LANES
     sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B)[0]
             for s in range(NSETS)]
-    post = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
     use_graph = not args.no_graph
-    graphs = [post.capture(lv) for lv in sets] if use_graph else None
-    plan = post.enqueue(sets[0])  # builds the plan / result buffers (also when graphs are off)
+    main = torch.cuda.current_stream(dev)
+    lanes = []
+    for ln in range(LANES):
+        st = torch.cuda.Stream(dev)
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
+            my_sets = [sets[ln + LANES * j] for j in range(2)]
+            gr = [pp.capture(lv) for lv in my_sets] if use_graph else None
+            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers (also when graphs are off)
+            gb = None
+            if world > 1:
+                gb = torch.empty((world * B, 1 + pl.rows.shape[1] * pl.rows.shape[2]), dtype=torch.float32, device=dev)
+        st.synchronize()
+        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": gr, "plan": pl, "gather": gb})
+    post, plan = lanes[0]["post"], lanes[0]["plan"]
 
     def step(i):
-        if use_graph:
-            graphs[i % NSETS].replay()
-        else:
-            post.enqueue(sets[i % NSETS])
+        ln = lanes[i % LANES]
+        j = (i // LANES) % 2
+        with torch.cuda.stream(ln["stream"]):
+            if use_graph:
+                ln["graphs"][j].replay()
+            else:
+                ln["post"].enqueue(ln["sets"][j])
+            if world > 1:
+                # the only collective of the path: ONE packed all_gather of counts + rows (the analogue of
+                # gather_object(stats), detect/val.py:226-240); it overlaps the other lane's compute
+                dist.all_gather_into_tensor(ln["gather"], ypb_dist.pack_results(ln["plan"].rows, ln["plan"].count))
 
-    # result gather across ranks (counts + rows, one packed all_gather) on a side stream, overlapped with the next step
-    gather_stream = torch.cuda.Stream(dev) if world > 1 else None
-    gather_buf = None
-    if world > 1:
-        per = B
-        gather_buf = [torch.empty((world * per, 1 + plan.rows.shape[1] * plan.rows.shape[2]), dtype=torch.float32, device=dev)
-                      for _ in range(2)]
+    def fork():
+        for ln in lanes:
+            ln["stream"].wait_stream(main)
 
-    def gather(i):
-        if world == 1:
-            return
-        done = torch.cuda.Event()
-        done.record()
-        with torch.cuda.stream(gather_stream):
-            gather_stream.wait_event(done)
-            packed = ypb_dist.pack_results(plan.rows, plan.count)
-            dist.all_gather_into_tensor(gather_buf[i % 2], packed)
-        # the next step overwrites plan.rows: it must not start before `packed` was built
-        packed_done = torch.cuda.Event()
-        packed_done.record(gather_stream)
-        torch.cuda.current_stream(dev).wait_event(packed_done)
+    def join():
+        for ln in lanes:
+            main.wait_stream(ln["stream"])
 
+    fork()
     for i in range(W):
         step(i)
-        gather(i)
+    join()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -273,11 +283,10 @@ def run_ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    fork()
     for i in range(K):
         step(i)
-        gather(i)
-    if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(gather_stream)
+    join()
     ev1.record()
     torch.cuda.synchronize(dev)
     sampler.stop()
@@ -388,9 +397,9 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC, "batch_per_gpu": B, "global_batch": B * world,
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
-                       "cuda_graph": use_graph,
+                       "cuda_graph": use_graph, "lanes": LANES,
                        "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
-                                      "of counts+rows per step on a side stream" if world > 1 else "single GPU"},
+                                      "of counts+rows per step, overlapped with the other lane" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
             "gpu_launches": 3 * K,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
@@ -419,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

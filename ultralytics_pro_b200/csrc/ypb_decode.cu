@@ -12,7 +12,13 @@
 
 namespace ypb {
 
-constexpr int DEC_THREADS = 128;
+#ifndef YPB_DEC_THREADS
+#define YPB_DEC_THREADS 128
+#endif
+#ifndef YPB_SCAN_DEPTH
+#define YPB_SCAN_DEPTH 8
+#endif
+constexpr int DEC_THREADS = YPB_DEC_THREADS;
 
 // ---------------------------------------------------------------------------------------------------------------
 // helpers
@@ -71,7 +77,7 @@ __device__ __forceinline__ float4 corners_in_dtype(float cx, float cy, float w, 
 
 // Walk `n` channel rows of one anchor group with DEPTH independent 128-bit loads in flight per thread: the loads of a
 // batch are issued back to back before the first value is consumed (Little's law: ~30 warps/SM x 32 lanes x DEPTH x 16 B).
-template <typename TI, int VEC, int DEPTH = 8, typename F>
+template <typename TI, int VEC, int DEPTH = YPB_SCAN_DEPTH, typename F>
 __device__ __forceinline__ void stream_rows(const TI* base, long long cs, int n, F&& visit) {
   int c = 0;
   for (; c + DEPTH <= n; c += DEPTH) {
