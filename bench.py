@@ -240,13 +240,22 @@ def run_ours(args):
         with torch.cuda.stream(st):
             pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
             my_sets = [sets[ln + LANES * j] for j in range(2)]
-            gr = [pp.capture(lv) for lv in my_sets] if use_graph else None
-            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers (also when graphs are off)
-            gb = None
-            if world > 1:
-                gb = torch.empty((world * B, 1 + pl.rows.shape[1] * pl.rows.shape[2]), dtype=torch.float32, device=dev)
+            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers
+            gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev) if world > 1 else None
+            gr, gather_in_graph = None, False
+            if use_graph:
+                if world > 1 and not args.no_graph_gather:
+                    try:  # the collective rides inside the graph: zero host work per step
+                        gr = [pp.capture(lv, after=lambda: ypb_dist.gather_packed(pl.packed, gb)) for lv in my_sets]
+                        gather_in_graph = True
+                    except Exception as exc:  # older NCCL/torch: capture of collectives unsupported
+                        sys.stderr.write(f"[bench] NCCL capture failed ({exc}); gathering eagerly\n")
+                        gr = None
+                if gr is None:
+                    gr = [pp.capture(lv) for lv in my_sets]
         st.synchronize()
-        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": gr, "plan": pl, "gather": gb})
+        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": gr, "plan": pl, "gather": gb,
+                      "gather_in_graph": gather_in_graph})
     post, plan = lanes[0]["post"], lanes[0]["plan"]
 
     def step(i):
@@ -257,10 +266,10 @@ def run_ours(args):
                 ln["graphs"][j].replay()
             else:
                 ln["post"].enqueue(ln["sets"][j])
-            if world > 1:
-                # the only collective of the path: ONE packed all_gather of counts + rows (the analogue of
-                # gather_object(stats), detect/val.py:226-240); it overlaps the other lane's compute
-                dist.all_gather_into_tensor(ln["gather"], ypb_dist.pack_results(ln["plan"].rows, ln["plan"].count))
+            if world > 1 and not ln["gather_in_graph"]:
+                # the only collective of the path: ONE all_gather of the plan's packed rows+counts buffer (the analogue
+                # of gather_object(stats), detect/val.py:226-240); it overlaps the other lanes' compute
+                ypb_dist.gather_packed(ln["plan"].packed, ln["gather"])
 
     def fork():
         for ln in lanes:
@@ -399,7 +408,8 @@ def run_ours(args):
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
                        "cuda_graph": use_graph, "lanes": LANES,
                        "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
-                                      "of counts+rows per step, overlapped with the other lane" if world > 1 else "single GPU"},
+                                      "of counts+rows per step" + (" captured in the CUDA graph" if lanes[0]["gather_in_graph"] else "")
+                                      + ", overlapped with the other lanes" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
             "gpu_launches": 3 * K,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
@@ -428,7 +438,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="independent pipelines (streams) the steps are spread over")
+    ap.add_argument("--no-graph-gather", action="store_true", help="do not capture the NCCL all_gather in the CUDA graph")
+    ap.add_argument("--lanes", type=int, default=3, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

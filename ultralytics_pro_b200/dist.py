@@ -62,3 +62,18 @@ def gather_results(rows: torch.Tensor, count: torch.Tensor, batch: int, group=No
     if async_op:
         return work, finish
     return finish()
+
+
+def gather_packed(packed: torch.Tensor, out: torch.Tensor, group=None, async_op: bool = False):
+    """all_gather of a plan's own result buffer (`NmsPlan.packed`: rows and counts of one rank in ONE allocation), so the
+    gather needs no packing kernels at all.  `out` is (world, packed.numel()); equal shard sizes on every rank."""
+    return dist.all_gather_into_tensor(out, packed, group=group, async_op=async_op)
+
+
+def split_packed(out: torch.Tensor, batch_per_rank: int, max_det: int, cols: int):
+    """(world, n) gathered buffer -> rows (world*B, max_det, cols) view pieces and counts (world*B,) int32."""
+    world = out.shape[0]
+    nrow = batch_per_rank * max_det * cols
+    rows = out[:, :nrow].reshape(world * batch_per_rank, max_det, cols)
+    count = out[:, nrow:].contiguous().view(torch.int32).reshape(world * batch_per_rank)
+    return rows, count

@@ -98,8 +98,9 @@ class NmsPlan:
     idx: torch.Tensor
     count: torch.Tensor
     cand: torch.Tensor
-    scratch: torch.Tensor
-    keep_alive: tuple
+    packed: torch.Tensor  # rows and count are views of this one fp32 buffer: [B*max_det*cols rows | B counts (int32 bits)]
+    scratch: torch.Tensor = None
+    keep_alive: tuple = ()
 
 
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
@@ -112,9 +113,11 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     nbytes = lib.ypb_nms_workspace_bytes(batch, anchors, rows_cap, max_det, max_nms, rule)
     scratch = _scratch(device, nbytes)
     cols = 6 + extra
-    rows = torch.empty((batch, max_det, cols), dtype=torch.float32, device=device)
+    nrow = batch * max_det * cols
+    packed = torch.empty((nrow + batch,), dtype=torch.float32, device=device)
+    rows = packed[:nrow].view(batch, max_det, cols)
+    count = packed[nrow:].view(torch.int32)
     idx = torch.empty((batch, max_det), dtype=torch.int64, device=device)
-    count = torch.empty((batch,), dtype=torch.int32, device=device)
     cand = torch.empty((batch,), dtype=torch.int32, device=device)
     mask = class_mask_tensor(classes, nc, device)
     p = _cabi.NmsParams()
@@ -124,7 +127,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     p.class_mask = mask.data_ptr() if mask is not None else None
     o = _cabi.NmsOut()
     o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
-    return NmsPlan(p, o, rows, idx, count, cand, scratch, (mask,))
+    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,))
 
 
 def fetch_counts(count: torch.Tensor) -> list:

@@ -68,13 +68,18 @@ class HeadPostProcessor:
         self.last = plan
         return plan
 
-    def capture(self, levels, angle_logits=None) -> "torch.cuda.CUDAGraph":
-        """Capture one batch's launches into a CUDA graph bound to these input tensors (static addresses)."""
+    def capture(self, levels, angle_logits=None, after=None) -> "torch.cuda.CUDAGraph":
+        """Capture one batch's launches into a CUDA graph bound to these input tensors (static addresses).
+        `after()` (optional) is captured behind the kernels, e.g. the NCCL gather of the result buffer."""
         self.enqueue(levels, angle_logits)  # warm: attributes set, plan built, scratch allocated
+        if after is not None:
+            after()
         torch.cuda.current_stream(levels[0].device).synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=torch.cuda.current_stream(levels[0].device)):
             self.enqueue(levels, angle_logits)
+            if after is not None:
+                after()
         return graph
 
     def __call__(self, levels, angle_logits=None, return_idxs: bool = False):
