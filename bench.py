@@ -217,7 +217,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     cfg = CONFIGS[WORKLOAD]
     dtype = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
     B, K, W = cfg.batch, args.steps, max(args.warmup, 3)
@@ -244,7 +246,7 @@ def run_ours(args):
             gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev) if world > 1 else None
             gr, gather_in_graph = None, False
             if use_graph:
-                if world > 1 and not args.no_graph_gather:
+                if world > 1 and args.graph_gather:
                     try:  # the collective rides inside the graph: zero host work per step
                         gr = [pp.capture(lv, after=lambda: ypb_dist.gather_packed(pl.packed, gb)) for lv in my_sets]
                         gather_in_graph = True
@@ -438,7 +440,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-graph-gather", action="store_true", help="do not capture the NCCL all_gather in the CUDA graph")
+    ap.add_argument("--graph-gather", action="store_true",
+                    help="EXPERIMENTAL: capture the NCCL all_gather inside each lane's CUDA graph (needs --lanes 1: "
+                         "collectives replayed from several streams have no defined cross-rank order and can deadlock)")
     ap.add_argument("--lanes", type=int, default=3, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
