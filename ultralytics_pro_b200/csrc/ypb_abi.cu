@@ -2,6 +2,7 @@
 // workspace carve-up and kernel sequencing.  Nothing here allocates, frees or synchronises.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ypb_common.cuh"
@@ -20,6 +21,13 @@ int fail(int code, const char* fmt, ...) {
 
 int cuda_fail(cudaError_t e, const char* where) {
   return fail(YPB_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+
+// Diagnostic switch: YPB_SPLIT_DECODE=1 runs the survivor decode as its own GPU-wide kernel (decode_tiles_kernel)
+// instead of inside the class-scan kernel.
+bool split_decode_requested() {
+  static const bool v = [] { const char* e = std::getenv("YPB_SPLIT_DECODE"); return e && e[0] == '1'; }();
+  return v;
 }
 
 size_t dtype_size(int dt) { return dt == YPB_F32 ? 4 : 2; }
@@ -175,6 +183,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
     ypb::FilterArgs f{};
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
+    f.fuse_decode = split_decode_requested() ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
@@ -185,6 +194,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
+    f.fuse_decode = split_decode_requested() ? 0 : 1;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }

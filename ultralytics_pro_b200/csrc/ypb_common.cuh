@@ -286,6 +286,7 @@ struct FilterArgs {
   int32_t* tile_list;
   uint8_t* tile_flags;
   int tile_cap;
+  int fuse_decode;  // 1: the class-scan kernel decodes the boxes of its own survivors; 0: separate decode_tiles kernel
   uint64_t* keys;
   float4* cand_box;
   float* cand_ang;

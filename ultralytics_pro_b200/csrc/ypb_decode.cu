@@ -206,19 +206,26 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 //   Output: unique 64-bit sort keys (row order irrelevant: one atomicAdd per block reserves the slots) and the list of
 //   octets (8 anchors) that contain a survivor, with a per-lane flag byte, for kernel 2.
 // ---------------------------------------------------------------------------------------------------------------
+template <int DT_IN, int DT_VAL, bool ROT>
+__device__ __forceinline__ void decode_survivor(const HeadGeom& g, const FilterArgs& f, const void* angle_v,
+                                                int angle_is_logit, int b, int l, int a_local);
+
 __device__ __forceinline__ float max_nan(float a, float b) {
   float r;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
 
-template <int DT_IN, int DT_VAL, int VEC, bool MULTI>
+template <int DT_IN, int DT_VAL, int VEC, bool MULTI, bool ROT>
 __global__ void __launch_bounds__(DEC_THREADS)
-scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ FilterArgs f) {
+scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                    const __grid_constant__ FilterArgs f) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_VAL>;
   __shared__ int s_base[2];
   __shared__ int s_active[DEC_THREADS / 32];
+  __shared__ uint8_t s_flags[DEC_THREADS];             // fused decode: survivor flags of every lane of the CTA
+  __shared__ uint8_t s_oct[DEC_THREADS * VEC / 8 + 1]; // fused decode: octets of the CTA that hold a survivor
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = blockIdx.x * DEC_THREADS + tid;
   const int b = blockIdx.y;
@@ -311,38 +318,94 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const __grid_constant__ 
 #pragma unroll
     for (int w = 0; w < DEC_THREADS / 32; ++w) act += s_active[w];
     s_base[0] = atomicAdd(&f.row_count[b], total_rows);
-    s_base[1] = atomicAdd(f.tile_count, act);
+    s_base[1] = f.fuse_decode ? 0 : atomicAdd(f.tile_count, act);
   }
   __syncthreads();
-  if (oct_mask) {
-    int rank = 0;
-    for (int w = 0; w < warp; ++w) rank += s_active[w];
+  int oct_rank = 0;
+  for (int w = 0; w < warp; ++w) oct_rank += s_active[w];
+  int oct_total = oct_rank;
+  for (int w = warp; w < DEC_THREADS / 32; ++w) oct_total += s_active[w];
+  if (f.fuse_decode) {
+    s_flags[tid] = static_cast<uint8_t>(flags);
+    if (lane < NOCT && ((oct_mask >> lane) & 1u))
+      s_oct[oct_rank + __popc(oct_mask & ((1u << lane) - 1u))] = static_cast<uint8_t>(warp * NOCT + lane);
+  } else if (oct_mask) {
     // flag bytes live in a dense per-lane array: index = b * G + lane-in-image, G = lanes kernel 1 runs per image
     const int G = static_cast<int>(gridDim.x) * DEC_THREADS;
     const int lane_idx = b * G + blockIdx.x * DEC_THREADS + tid;
     if (lane < NOCT && ((oct_mask >> lane) & 1u))
-      f.tile_list[s_base[1] + rank + __popc(oct_mask & ((1u << lane) - 1u))] = (lane_idx - lane) / LPO + lane;
+      f.tile_list[s_base[1] + oct_rank + __popc(oct_mask & ((1u << lane) - 1u))] = (lane_idx - lane) / LPO + lane;
     f.tile_flags[lane_idx] = static_cast<uint8_t>(flags);
   }
-  if (my_rows == 0) return;
-  uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
-  int rpos = s_base[0] + roff;
+  if (my_rows > 0) {
+    uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
+    int rpos = s_base[0] + roff;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    if (rows[i] == 0) continue;
-    const uint32_t row0 = static_cast<uint32_t>(a_glob + i) << f.cls_bits;
-    if constexpr (MULTI) {
-      for (int c = 0; c < nc; ++c) {
-        float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
-        if (s > conf && class_allowed(f.class_mask, c)) {
-          if (rpos < f.rows_cap) keys[rpos] = make_key(s, row0 + c);
-          ++rpos;
+    for (int i = 0; i < VEC; ++i) {
+      if (rows[i] == 0) continue;
+      const uint32_t row0 = static_cast<uint32_t>(a_glob + i) << f.cls_bits;
+      if constexpr (MULTI) {
+        for (int c = 0; c < nc; ++c) {
+          float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
+          if (s > conf && class_allowed(f.class_mask, c)) {
+            if (rpos < f.rows_cap) keys[rpos] = make_key(s, row0 + c);
+            ++rpos;
+          }
         }
+      } else {
+        if (rpos < f.rows_cap) keys[rpos] = make_key(score[i], row0 + cls[i]);
+        ++rpos;
       }
-    } else {
-      if (rpos < f.rows_cap) keys[rpos] = make_key(score[i], row0 + cls[i]);
-      ++rpos;
     }
+  }
+  if (!f.fuse_decode) return;
+
+  // ---- fused survivor decode (head.py:167-168 restricted to survivors): quarter-warp = one octet, lane = one anchor ----
+  __syncthreads();
+  for (int t = warp * 4 + (lane >> 3); t < oct_total; t += (DEC_THREADS / 32) * 4) {
+    const int oct = s_oct[t];
+    const int k = lane & 7;
+    const int src_lane = oct * LPO + (VEC >= 8 ? 0 : k / VEC);  // lane of this CTA that scanned the anchor
+    const int i = VEC >= 8 ? k : k % VEC;
+    if (!((s_flags[src_lane] >> i) & 1u)) continue;
+    const int grp2 = blockIdx.x * DEC_THREADS + src_lane;
+    const int l2 = find_level(g, grp2);
+    const int a_loc = (grp2 - g.group_start[l2]) * VEC + i;
+    decode_survivor<DT_IN, DT_VAL, ROT>(g, f, angle_v, angle_is_logit, b, l2, a_loc);
+  }
+}
+
+// One survivor anchor: 64 independent bin-row loads, in-register softmax expectation per side (block.py:250-253),
+// dist2bbox / dist2rbox, x stride, rounding through the value dtype, corners (nms.py:86).
+template <int DT_IN, int DT_VAL, bool ROT>
+__device__ __forceinline__ void decode_survivor(const HeadGeom& g, const FilterArgs& f, const void* angle_v,
+                                                int angle_is_logit, int b, int l, int a_local) {
+  using TI = typename DType<DT_IN>::type;
+  using DV = DType<DT_VAL>;
+  const long long cs = g.cstride[l];
+  const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+  float d[4];
+#pragma unroll
+  for (int side = 0; side < 4; ++side) {
+    float v[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) v[kk] = DType<DT_IN>::to_f(src[static_cast<long long>(side * 16 + kk) * cs]);
+    d[side] = dfl_expect<16>(v);
+  }
+  const int W = g.w[l];
+  const int gy = a_local / W, gx = a_local - gy * W;
+  const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+  const float stride = g.stride[l];
+  const long long slot = static_cast<long long>(b) * g.anchors + g.anchor_start[l] + a_local;
+  if constexpr (ROT) {
+    float tt = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
+    float theta = angle_is_logit ? DV::rnd(activate_angle(tt)) : tt;
+    BoxXYWH bx = decode_rotated(d[0], d[1], d[2], d[3], theta, ax, ay, stride);
+    f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
+    f.cand_ang[slot] = theta;
+  } else {
+    BoxXYWH bx = decode_axis_aligned(d[0], d[1], d[2], d[3], ax, ay, stride, false);
+    f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
   }
 }
 
@@ -375,32 +438,7 @@ decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
     const int b = lane_idx / G;
     const int grp = lane_idx - b * G;
     const int l = find_level(g, grp);
-    const int a_local = (grp - g.group_start[l]) * VEC + i;
-    const long long cs = g.cstride[l];
-    const TI* src = static_cast<const TI*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
-    float d[4];
-#pragma unroll
-    for (int side = 0; side < 4; ++side) {
-      float v[16];
-#pragma unroll
-      for (int kk = 0; kk < 16; ++kk) v[kk] = DType<DT_IN>::to_f(src[static_cast<long long>(side * 16 + kk) * cs]);
-      d[side] = dfl_expect<16>(v);
-    }
-    const int W = g.w[l];
-    const int gy = a_local / W, gx = a_local - gy * W;
-    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-    const float stride = g.stride[l];
-    const long long slot = static_cast<long long>(b) * g.anchors + g.anchor_start[l] + a_local;
-    if constexpr (ROT) {
-      float tt = DType<DT_IN>::to_f(static_cast<const TI*>(angle_v)[slot]);
-      float theta = angle_is_logit ? DV::rnd(activate_angle(tt)) : tt;
-      BoxXYWH bx = decode_rotated(d[0], d[1], d[2], d[3], theta, ax, ay, stride);
-      f.cand_box[slot] = make_float4(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
-      f.cand_ang[slot] = theta;
-    } else {
-      BoxXYWH bx = decode_axis_aligned(d[0], d[1], d[2], d[3], ax, ay, stride, false);
-      f.cand_box[slot] = corners_in_dtype<DT_VAL>(DV::rnd(bx.cx), DV::rnd(bx.cy), DV::rnd(bx.w), DV::rnd(bx.h));
-    }
+    decode_survivor<DT_IN, DT_VAL, ROT>(g, f, angle_v, angle_is_logit, b, l, (grp - g.group_start[l]) * VEC + i);
   }
 }
 
@@ -542,10 +580,13 @@ static cudaError_t filter_head_dispatch(const HeadGeom& g, const void* angle, in
   const int blocks_x = (groups + DEC_THREADS - 1) / DEC_THREADS;
   if (which == 1) {
     dim3 grid(blocks_x, g.batch);
-    if (f.multi_label) scan_classes_kernel<DT_IN, DT_VAL, VEC, true><<<grid, DEC_THREADS, 0, st>>>(g, f);
-    else               scan_classes_kernel<DT_IN, DT_VAL, VEC, false><<<grid, DEC_THREADS, 0, st>>>(g, f);
+#define YPB_SC(M, R) scan_classes_kernel<DT_IN, DT_VAL, VEC, M, R><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, f)
+    if (f.multi_label) { if (f.rotated) YPB_SC(true, true); else YPB_SC(true, false); }
+    else               { if (f.rotated) YPB_SC(false, true); else YPB_SC(false, false); }
+#undef YPB_SC
     return cudaGetLastError();
   }
+  if (f.fuse_decode) return cudaSuccess;  // kernel 1 decoded its own survivors
   // kernel 2: grid-stride over the octet list; enough CTAs to cover the GPU, never more than there can be octets
   const int G = blocks_x * DEC_THREADS;
   int blocks = 148 * 8;
