@@ -330,13 +330,12 @@ def run_ours(args):
     peak, peak_src = _peaks()
     scan_bytes = B * cfg.nc * cfg.anchors * esize  # the class rows: what this kernel must read
     achieved = scan_bytes / (t_scan * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_classes_kernel (class scan + sigmoid/confidence filter + compaction + DFL box decode "
-                                          "of the survivors)",
+    roofline = {"bound": "hbm", "kernel": "scan_classes_kernel (class scan + sigmoid/confidence filter + compaction)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(args.dtype),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
                 "algorithmic_bytes_full_head": B * in_bytes_img,
                 "launch_ms": t_scan,
-                "other_kernels_ms": {"decode_tiles_kernel (0: fused into the scan kernel unless YPB_SPLIT_DECODE=1)": t_decode,
+                "other_kernels_ms": {"decode_tiles_kernel": t_decode,
                                      "sort_suppress_kernel": t_suppr}}
 
     # ---- dense decode kernel alone (the Detect._inference drop-in), same inputs --------------------------------------
@@ -415,7 +414,7 @@ def run_ours(args):
                                       "of counts+rows per step" + (" captured in the CUDA graph" if lanes[0]["gather_in_graph"] else "")
                                       + ", overlapped with the other lanes" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
-            "gpu_launches": (3 if os.environ.get("YPB_SPLIT_DECODE") == "1" else 2) * K,
+            "gpu_launches": (2 if os.environ.get("YPB_FUSE_DECODE") == "1" else 3) * K,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
                     "note": "postprocess_from_head on pinned HOST head tensors: H2D + decode+NMS + D2H of rows and counts, "
                             "synchronised every step"},
