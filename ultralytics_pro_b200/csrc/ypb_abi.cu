@@ -184,9 +184,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
     ypb::FilterArgs f{};
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
-    // octet ids of the split decode must fit 24 bits (the entry's top byte carries the survivor flags)
-    const bool ids_fit = static_cast<long long>(head->batch) * (g.anchors + 1024) / 8 < (1LL << 24);
-    f.fuse_decode = (split_decode_requested() && ids_fit) ? 0 : 1;
+    f.fuse_decode = split_decode_requested() ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
@@ -197,9 +195,7 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
-    // octet ids of the split decode must fit 24 bits (the entry's top byte carries the survivor flags)
-    const bool ids_fit = static_cast<long long>(head->batch) * (g.anchors + 1024) / 8 < (1LL << 24);
-    f.fuse_decode = (split_decode_requested() && ids_fit) ? 0 : 1;
+    f.fuse_decode = split_decode_requested() ? 0 : 1;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }

@@ -333,22 +333,9 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
     // octet ids index a dense per-lane space: index = b * G + lane-in-image, G = lanes kernel 1 runs per image
     const int G = static_cast<int>(gridDim.x) * DEC_THREADS;
     const int lane_idx = b * G + blockIdx.x * DEC_THREADS + tid;
-    // list entry = octet id | its 8 survivor flags << 24 (one hop less for kernel 2)
-    uint32_t oflags = 0;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const unsigned bi = __ballot_sync(0xffffffffu, (flags >> i) & 1u);
-      if (lane < NOCT) {
-        if constexpr (VEC >= 8) oflags |= ((bi >> lane) & 1u) << i;
-        else {
-#pragma unroll
-          for (int j = 0; j < LPO; ++j) oflags |= ((bi >> (lane * LPO + j)) & 1u) << (j * VEC + i);
-        }
-      }
-    }
     if (lane < NOCT && ((oct_mask >> lane) & 1u))
-      f.tile_list[s_base[1] + oct_rank + __popc(oct_mask & ((1u << lane) - 1u))] =
-          static_cast<int32_t>(static_cast<uint32_t>((lane_idx - lane) / LPO + lane) | (oflags << 24));
+      f.tile_list[s_base[1] + oct_rank + __popc(oct_mask & ((1u << lane) - 1u))] = (lane_idx - lane) / LPO + lane;
+    f.tile_flags[lane_idx] = static_cast<uint8_t>(flags);
   }
   if (my_rows > 0) {
     uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
@@ -445,12 +432,12 @@ decode_tiles_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
   const int nwarps = gridDim.x * (DEC_THREADS / 32);
   const int noct = min(*f.tile_count, f.tile_cap);
   for (int t = (blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5)) * 4 + (lane >> 3); t < noct; t += nwarps * 4) {
-    const uint32_t entry = static_cast<uint32_t>(f.tile_list[t]);
-    const int oct = static_cast<int>(entry & 0xffffffu);
+    const int oct = f.tile_list[t];
     const int k = lane & 7;                      // anchor inside the octet
-    if (!((entry >> (24 + k)) & 1u)) continue;   // flagged anchors are always inside the image
     const int lane_idx = oct * LPO + (VEC >= 8 ? 0 : k / VEC);  // kernel-1 lane (anchor group) holding this anchor
     const int i = VEC >= 8 ? k : k % VEC;        // anchor inside the group
+    const uint32_t flags = f.tile_flags[lane_idx];
+    if (!((flags >> i) & 1u)) continue;          // flagged anchors are always inside the image
     const int b = lane_idx / G;
     const int grp = lane_idx - b * G;
     const int l = find_level(g, grp);
