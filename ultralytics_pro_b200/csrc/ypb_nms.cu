@@ -380,8 +380,8 @@ void set_phase_buffer(long long* p) { g_phase_buf = p; }
 // by >= max_wh and fp32 rounding is monotone), so their IoU is exactly 0 and the greedy walk decomposes EXACTLY into
 // independent walks per class:
 //   1. counting sort of the candidates by class (shared-memory histogram + scatter), boxes gathered on the way;
-//   2. one warp per class (handed out dynamically): the class's rows are ranked (score desc, anchor asc) with a
-//      register/shuffle bitonic network, then walked with lane = row: the lowest surviving lane is kept and one ballot
+//   2. every row is ranked inside its class by counting (all threads), then one warp per class (handed out
+//      dynamically, longest class first) walks it with lane = row: the lowest surviving lane is kept and one ballot
 //      strikes what it suppresses - one step per KEPT box instead of one IoU per pair of candidates;
 //   3. the kept rows of all classes are ranked by the original (score desc, row asc) key by counting and cut at
 //      max_det (nms.py:157).
@@ -390,37 +390,6 @@ void set_phase_buffer(long long* p) { g_phase_buf = p; }
 // CW_SEG_MAX rows, non-finite boxes): the caller then takes the dense walk.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int CW_SEG_MAX = 256;     // rows of one class a single warp ranks in registers (8 per lane)
-
-// Ranks the L <= 32*KP rows of one class by counting: rank = number of rows of the class with a smaller
-// (score desc, anchor asc) key.  Every row's key is read by all lanes as one shared-memory broadcast; the L x KP
-// comparisons are independent (no exchange network, no dependent chain).  order[s + rank] = scattered position.
-template <int KP>
-__device__ __forceinline__ void rank_segment(Smem& sm, int s, int L, int cbits, int lane) {
-  uint64_t mine[KP];
-  int rank[KP];
-#pragma unroll
-  for (int u = 0; u < KP; ++u) {
-    const int e = lane + 32 * u;
-    rank[u] = 0;
-    mine[u] = KEY_SENTINEL;
-    if (e < L) {
-      const uint64_t k = sm.u.keys[s + e];
-      mine[u] = (k & 0xffffffff00000000ull) | (static_cast<uint32_t>(k) >> cbits);  // (score desc, anchor asc)
-    }
-  }
-#pragma unroll 4
-  for (int e = 0; e < L; ++e) {
-    const uint64_t k = sm.u.keys[s + e];
-    const uint64_t o = (k & 0xffffffff00000000ull) | (static_cast<uint32_t>(k) >> cbits);
-#pragma unroll
-    for (int u = 0; u < KP; ++u) rank[u] += o < mine[u] ? 1 : 0;
-  }
-#pragma unroll
-  for (int u = 0; u < KP; ++u) {
-    const int e = lane + 32 * u;
-    if (e < L) sm.order[s + rank[u]] = static_cast<uint16_t>(s + e);
-  }
-}
 
 // One greedy test of every lane's row against the same higher-ranked row (kb, ka) of its class.  Branch-free for the
 // whole warp; only a borderline pair (|IoU - thr| within 2^-20 relative) takes the exact fp64 decision.
@@ -534,7 +503,26 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   if (bad || !(ghi - glo <= 0.999f * a.max_wh)) return -1;  // uniform
   YPB_MARK(19);
 
-  // ---- 2. one warp per class, handed out dynamically ------------------------------------------------------------------
+  // ---- 2a. rank every row inside its class, all threads in parallel: rank = number of rows of the class with a smaller
+  //          (score desc, anchor asc) key.  Rows are class-contiguous, so the lanes of a warp mostly share a class and
+  //          read the same shared-memory words (broadcast).  order[slot of (class, rank)] = scattered position.
+  for (int p = tid; p < n; p += NT) {
+    const uint64_t k = sm.u.keys[p];
+    const uint32_t cls = static_cast<uint32_t>(k) & cmask;
+    const uint64_t mine = (k & 0xffffffff00000000ull) | (static_cast<uint32_t>(k) >> cbits);
+    const int s = sm.cstart[cls], e = sm.cstart[cls + 1];
+    int rank = 0;
+#pragma unroll 4
+    for (int q = s; q < e; ++q) {
+      const uint64_t o = sm.u.keys[q];
+      rank += ((o & 0xffffffff00000000ull) | (static_cast<uint32_t>(o) >> cbits)) < mine ? 1 : 0;
+    }
+    sm.order[s + rank] = static_cast<uint16_t>(p);
+  }
+  __syncthreads();
+  YPB_MARK(18);
+
+  // ---- 2b. one warp per class, handed out dynamically (longest first) ---------------------------------------------------
   const int nseg = sm.nseg;
   while (true) {
     int sid = 0;
@@ -544,11 +532,6 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
     const int cid = sm.clist2[sid];
     const int s = sm.cstart[cid], e = sm.cstart[cid + 1];
     const int L = e - s;
-    if (L <= 32) rank_segment<1>(sm, s, L, cbits, lane);
-    else if (L <= 64) rank_segment<2>(sm, s, L, cbits, lane);
-    else if (L <= 128) rank_segment<4>(sm, s, L, cbits, lane);
-    else rank_segment<8>(sm, s, L, cbits, lane);
-    __syncwarp();
     // walk the class in rank order, 32 ranks (one per lane) at a time
     for (int r0 = 0; r0 < L; r0 += 32) {
       const bool in = r0 + lane < L;
