@@ -312,3 +312,89 @@ def test_sigmoid_monotone_selftest(cuda_device, dtype):
     v = torch.zeros(1, dtype=torch.int64, device=cuda_device)
     _cabi.check(lib.ypb_selftest_sigmoid_monotone(_cabi.dtype_code(dtype), v.data_ptr(), _cabi.stream_ptr(cuda_device)), "selftest")
     assert int(v.item()) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fallback and corner paths of the suppression kernel
+# ------------------------------------------------------------------------------------------------------------------
+def _random_decoded(n_anchors, nc, batch, seed, span=600.0, extra=0, crowd_cls=None):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.zeros(batch, 4 + nc + extra, n_anchors)
+    cx = torch.rand(batch, n_anchors, generator=g) * span
+    cy = torch.rand(batch, n_anchors, generator=g) * span
+    w = torch.rand(batch, n_anchors, generator=g) * 80 + 4
+    h = torch.rand(batch, n_anchors, generator=g) * 80 + 4
+    y[:, 0], y[:, 1], y[:, 2], y[:, 3] = cx, cy, w, h
+    sc = torch.rand(batch, nc, n_anchors, generator=g) * 0.2
+    hot = torch.randint(0, nc, (batch, n_anchors), generator=g) if crowd_cls is None else torch.full((batch, n_anchors), crowd_cls)
+    sc.scatter_(1, hot.unsqueeze(1), torch.rand(batch, 1, n_anchors, generator=g))
+    y[:, 4:4 + nc] = sc
+    if extra:
+        y[:, 4 + nc:] = torch.randn(batch, extra, n_anchors, generator=g)
+    return y
+
+
+@pytest.mark.parametrize("case", ["single_class", "crowded_class", "wide_span", "big_max_det", "many_classes", "tiny_nc2"])
+def test_suppression_fallback_paths(cuda_device, case):
+    """Every precondition of the class-wise walk, violated in turn, must land on the dense walk with identical results."""
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    kw = dict(conf=0.3, iou=0.5, max_det=300)
+    if case == "single_class":      # nc = 1: one class holds every row (> 256) -> dense walk
+        y = _random_decoded(3000, 1, 2, 1)
+    elif case == "crowded_class":   # 80 classes but one of them holds ~1500 rows
+        y = _random_decoded(3000, 80, 2, 2, crowd_cls=7)
+    elif case == "wide_span":       # coordinates span more than max_wh: classes may interact through the offset
+        y = _random_decoded(1500, 4, 2, 3, span=20000.0)
+        y[:, 2:4] *= 60             # boxes thousands of pixels wide, so cross-class overlaps really occur
+    elif case == "big_max_det":     # kept list larger than the shared-memory list
+        y = _random_decoded(6000, 1, 1, 4, span=4000.0)
+        kw.update(max_det=2500, iou=0.3)
+    elif case == "many_classes":    # more classes than histogram bins -> dense walk
+        y = _random_decoded(1200, 1500, 1, 5)
+    else:
+        y = _random_decoded(900, 2, 3, 6)
+    y = make_scores_unique(y, y.shape[1] - 4, kw["conf"])
+    want, want_idx = nms_oracle(y, kw["conf"], kw["iou"], max_det=kw["max_det"])
+    got, got_idx = non_max_suppression(y.to(cuda_device), kw["conf"], kw["iou"], max_det=kw["max_det"], return_idxs=True)
+    assert sum(w.shape[0] for w in want) > 0
+    assert_rows_equal(got, got_idx, want, want_idx, case)
+
+
+def test_labels_and_end2end_shortcuts(cuda_device):
+    from ultralytics_pro_b200.nms import non_max_suppression
+
+    # a-priori labels (autolabelling, nms.py:100-105): rows appended after the candidates
+    y = _random_decoded(400, 5, 2, 11)
+    labels = [torch.tensor([[2.0, 100.0, 120.0, 30.0, 40.0], [4.0, 300.0, 310.0, 50.0, 20.0]]), torch.zeros((0, 5))]
+    want, _ = nms_oracle(y, 0.3, 0.5, labels=labels)
+    got = non_max_suppression(y.to(cuda_device), 0.3, 0.5, labels=[l.to(cuda_device) for l in labels])
+    assert_rows_equal(got, None, want, None, "labels")
+    # end-to-end layout (B, N, 6): threshold, cap, class filter (nms.py:66-70)
+    e = torch.zeros(2, 50, 6)
+    e[..., 4] = torch.rand(2, 50, generator=torch.Generator().manual_seed(3))
+    e[..., 5] = torch.randint(0, 4, (2, 50), generator=torch.Generator().manual_seed(4)).float()
+    e[..., :4] = torch.rand(2, 50, 4, generator=torch.Generator().manual_seed(5)) * 100
+    for kwargs in (dict(max_det=7), dict(max_det=300, classes=[1, 3])):
+        want, _ = nms_oracle(e, 0.4, 0.5, **kwargs)
+        got = non_max_suppression(e.to(cuda_device), 0.4, 0.5, **kwargs)
+        assert_rows_equal(got, None, want, None, f"end2end {kwargs}")
+
+
+def test_head_post_processor_and_graph(cuda_device):
+    """The cached-plan API and its CUDA-graph replay give the same rows as the functional call."""
+    from ultralytics_pro_b200.head import postprocess_from_head
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+
+    cfg = CONFIGS["c2_v8x_640_b64"]
+    levels, _ = make_head_batch(cfg, batch=3, seed=51)
+    dl = [lv.to(cuda_device) for lv in levels]
+    want, want_idx = postprocess_from_head(dl, cfg.strides, cfg.nc, cfg.conf, cfg.iou, return_idxs=True)
+    post = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou)
+    got, got_idx = post(dl, return_idxs=True)
+    assert_rows_equal(got, got_idx, [w.cpu() for w in want], [w.cpu() for w in want_idx], "post processor")
+    graph = post.capture(dl)
+    post.last.rows.zero_()
+    graph.replay()
+    got, got_idx = post.results(return_idxs=True)
+    assert_rows_equal(got, got_idx, [w.cpu() for w in want], [w.cpu() for w in want_idx], "graph replay")
