@@ -74,9 +74,13 @@ class HeadPostProcessor:
         self.enqueue(levels, angle_logits)  # warm: attributes set, plan built, scratch allocated
         if after is not None:
             after()
-        torch.cuda.current_stream(levels[0].device).synchronize()
+        dev = levels[0].device
+        cur = torch.cuda.current_stream(dev)
+        cur.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=torch.cuda.current_stream(levels[0].device)):
+        # capture needs a non-default stream; keep the caller's stream when it already is one
+        cap = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(dev)
+        with torch.cuda.graph(graph, stream=cap):
             self.enqueue(levels, angle_logits)
             if after is not None:
                 after()
