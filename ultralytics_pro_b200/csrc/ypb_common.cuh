@@ -39,6 +39,22 @@ template <> struct DType<YPB_BF16> {
   static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 };
 
+// packed x2 view of the 16-bit types (class scan of bf16/fp16 heads)
+template <int DT> struct Packed2;
+template <> struct Packed2<YPB_F16> {
+  using type = __half2;
+  static __device__ __forceinline__ __half2 neg_inf() { return __half2half2(__ushort_as_half(0xFC00)); }
+  static __device__ __forceinline__ float lo(__half2 v) { return __low2float(v); }
+  static __device__ __forceinline__ float hi(__half2 v) { return __high2float(v); }
+};
+template <> struct Packed2<YPB_BF16> {
+  using type = __nv_bfloat162;
+  static __device__ __forceinline__ __nv_bfloat162 neg_inf() { return __bfloat162bfloat162(__ushort_as_bfloat16(0xFF80)); }
+  static __device__ __forceinline__ float lo(__nv_bfloat162 v) { return __low2float(v); }
+  static __device__ __forceinline__ float hi(__nv_bfloat162 v) { return __high2float(v); }
+};
+template <> struct Packed2<YPB_F32> { using type = float2; };
+
 // A VEC-wide, naturally aligned group of T moved with one LDG/STG (128-bit for fp32 x4 / 16-bit x8).
 template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 

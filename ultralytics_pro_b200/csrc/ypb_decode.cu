@@ -266,19 +266,48 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
         if (nanacc[i] != nanacc[i]) rows[i] = 0;  // amax -> NaN -> the anchor is not a candidate (nms.py:76)
     } else {
       float m[VEC], m2[VEC];
+      if constexpr (DT_IN != YPB_F32 && VEC == 8) {
+        // 16-bit inputs: the whole scan stays in packed x2 arithmetic (comparisons and max/min of 16-bit floats are
+        // exact): per PAIR of elements one compare-mask, min, max, NaN-propagating max and a bit-select of the packed
+        // 16-bit class indices - 2.5 instructions per element instead of ~7 through fp32.
+        using T2 = typename Packed2<DT_IN>::type;
+        T2 pm[4], pm2[4];
+        uint32_t pidx[4];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { m[i] = -INFINITY; m2[i] = -INFINITY; }
-      auto visit = [&](const Pack<TI, VEC>& p, int c) {
+        for (int j = 0; j < 4; ++j) { pm[j] = Packed2<DT_IN>::neg_inf(); pm2[j] = pm[j]; pidx[j] = 0u; }
+        auto visit = [&](const Pack<TI, VEC>& p, int c) {
+          const T2* v2 = reinterpret_cast<const T2*>(&p);
+          const uint32_t cc = static_cast<uint32_t>(c) * 0x00010001u;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float v = DType<DT_IN>::to_f(p.v[i]);
-          const bool gt = v > m[i];
-          m2[i] = fmaxf(m2[i], fminf(m[i], v));
-          m[i] = max_nan(m[i], v);
-          cls[i] = gt ? c : cls[i];
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t gt = __hgt2_mask(v2[j], pm[j]);
+            pm2[j] = __hmax2(pm2[j], __hmin2(pm[j], v2[j]));
+            pm[j] = __hmax2_nan(pm[j], v2[j]);
+            pidx[j] = (cc & gt) | (pidx[j] & ~gt);
+          }
+        };
+        stream_rows<TI, VEC>(csrc, cs, nc, visit);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m[2 * j] = Packed2<DT_IN>::lo(pm[j]);   m[2 * j + 1] = Packed2<DT_IN>::hi(pm[j]);
+          m2[2 * j] = Packed2<DT_IN>::lo(pm2[j]); m2[2 * j + 1] = Packed2<DT_IN>::hi(pm2[j]);
+          cls[2 * j] = static_cast<int>(pidx[j] & 0xffffu); cls[2 * j + 1] = static_cast<int>(pidx[j] >> 16);
         }
-      };
-      stream_rows<TI, VEC>(csrc, cs, nc, visit);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { m[i] = -INFINITY; m2[i] = -INFINITY; }
+        auto visit = [&](const Pack<TI, VEC>& p, int c) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float v = DType<DT_IN>::to_f(p.v[i]);
+            const bool gt = v > m[i];
+            m2[i] = fmaxf(m2[i], fminf(m[i], v));
+            m[i] = max_nan(m[i], v);
+            cls[i] = gt ? c : cls[i];
+          }
+        };
+        stream_rows<TI, VEC>(csrc, cs, nc, visit);
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float s = DV::rnd(sigmoid_f(m[i]));
