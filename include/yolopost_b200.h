@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 1
+#define YPB_ABI_VERSION 2
 #define YPB_MAX_LEVELS 8
 
 typedef enum { YPB_F32 = 0, YPB_F16 = 1, YPB_BF16 = 2 } ypb_dtype;
@@ -98,14 +98,42 @@ typedef struct {
   const uint32_t* class_mask; /* device bitmask of allowed classes (nms.py:127-131) or NULL */
 } ypb_nms_params;
 
+/* Per-image letterbox transform, values exactly as the reference computes them on the host:
+ *   utils/ops.py:120-127 (scale_boxes): gain = min(h1/h0, w1/w0) or ratio_pad[0][0]; pad_x/pad_y = round((w1-w0*gain)/2-0.1)
+ *                                       or ratio_pad[1]; img_w/img_h = the target image size used by clip_boxes (:163)
+ *   utils/ops.py:580-587 (scale_coords): cpad_x/cpad_y = (w1-w0*gain)/2 un-rounded, or ratio_pad[1]
+ * every member already rounded to fp32 (what torch does to a Python scalar operand of an fp32 tensor op). */
+typedef struct {
+  float gain, pad_x, pad_y, img_w, img_h, cpad_x, cpad_y, reserved;
+} ypb_scale_xform;
+
+typedef enum {
+  YPB_BOXES_NONE = 0,            /* leave columns 0..3 alone */
+  YPB_BOXES_XYXY = 1,            /* ops.py:102-135 scale_boxes(xywh=False): pad all four, / gain, clip_boxes */
+  YPB_BOXES_XYWH = 2,            /* scale_boxes(xywh=True): pad x,y only, / gain, no clip (obb/predict.py:60, obb/val.py:223) */
+  YPB_BOXES_XYWHR = 3,           /* ops.py:621-636 regularize_rboxes on (x,y,w,h,angle@angle_col), then XYWH (obb/predict.py:59-60) */
+  YPB_BOXES_CLIP_ONLY = 4,       /* ops.py:152-177 clip_boxes */
+  YPB_BOXES_REGULARIZE_ONLY = 5  /* ops.py:621-636 regularize_rboxes */
+} ypb_box_mode;
+
+#define YPB_SCALE_PADDING 1          /* ops.py:128 `padding=True` */
+#define YPB_SCALE_NORMALIZE 2        /* ops.py:591-594 `normalize=True` (coords only) */
+#define YPB_SCALE_COORDS_CLIP_ONLY 4 /* ops.py:598-618 clip_coords alone */
+
 /* Result buffers (device).  rows: (B, max_det, 6+extra) fp32 = x1,y1,x2,y2,conf,cls,extra... (xywh + angle when
  * rotated); idx: (B, max_det) int64 anchor index of each kept row (nms.py:161 keepi) or NULL; count: (B) int32;
- * cand_count: (B) int32 rows that passed the confidence filter before any cap (diagnostic) or NULL. */
+ * cand_count: (B) int32 rows that passed the confidence filter before any cap (diagnostic) or NULL.
+ * scale_xforms: NULL, or a device array of B transforms: the kept rows are written already rescaled to the original
+ * image - detect/predict.py:120 scale_boxes (greedy rule) or obb/predict.py:59-60 regularize_rboxes + scale_boxes(xywh=True)
+ * (FAST_PROBIOU rule) fused into the gather; scale_padding = ops.py:128 `padding`. */
 typedef struct {
   float* rows;
   int64_t* idx;
   int32_t* count;
   int32_t* cand_count;
+  const ypb_scale_xform* scale_xforms;
+  int32_t scale_padding;
+  int32_t reserved;
 } ypb_nms_out;
 
 YPB_API int ypb_abi_version(void);
@@ -149,6 +177,19 @@ YPB_API size_t ypb_nms_boxes_workspace_bytes(int32_t n);
 YPB_API int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t box_dim, int32_t rule,
                   float iou_thres_eff, int64_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* ---- result-side steps that follow NMS in the reference's predictors / validators -------- */
+
+/* In-place rescale of result rows from the letterboxed network input to the original image.
+ *   rows            : fp32, row r of image b at rows + b*image_stride + r*row_stride (elements); columns 0..3 = box
+ *   count           : device (B) int32 kept rows per image (ypb_nms_out.count) or NULL = all rows_per_image rows
+ *   xforms / xform  : device array of B transforms, or NULL to use the single host `xform` for every image
+ *   coords,nk,ndim  : optional keypoints riding on each row (pose/predict.py:73-75): nk points of ndim (2|3) floats, the first
+ *                     at coords + b*coord_image_stride + r*coord_row_stride; scaled like ops.py:562-595 scale_coords */
+YPB_API int ypb_scale_rows(float* rows, int64_t image_stride, int64_t row_stride, int32_t batch, int32_t rows_per_image,
+                           const int32_t* count, const ypb_scale_xform* xforms, const ypb_scale_xform* xform,
+                           int32_t box_mode, int32_t flags, int32_t angle_col, float* coords,
+                           int64_t coord_image_stride, int64_t coord_row_stride, int32_t nk, int32_t ndim, void* stream);
 
 /* Diagnostic: when set to a device buffer of batch*32 int64, the sort+suppress kernel stores clock64() marks per CTA
  * (0 start, 1 ranked, 2+i after chunk i, 30 before gather, 31 end); NULL disables (default). */

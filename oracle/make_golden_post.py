@@ -1,0 +1,101 @@
+"""Generate tests/golden/post/result_ops.npz by running the LIVE reference's result-side helpers (utils/ops.py).
+
+TEST INFRASTRUCTURE.  Build container only:   python oracle/make_golden_post.py
+Each case stores the seeded input, the call's arguments (meta JSON) and the reference's output.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "post", "result_ops.npz")
+
+SHAPES = [  # (network input HW, original image HW[C], ratio_pad)
+    ((640, 640), (480, 640, 3), None),
+    ((384, 640), (1080, 1920, 3), None),
+    ((640, 640), (427, 640), None),
+    ((640, 480), (1333, 999, 3), None),
+    ((1024, 1024), (3000, 4000, 3), None),
+    ((640, 640), (720, 1280), ((0.5, 0.5), (0.0, 140.0))),
+    ((640, 640), (500, 375), ((1.28, 1.28), (80.5, 0.25))),
+]
+
+
+def boxes_input(rng, n, h, w):
+    xy = rng.uniform(-40, max(h, w) + 40, size=(n, 2))
+    wh = rng.uniform(1, max(h, w) * 0.6, size=(n, 2))
+    b = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    b[0] = [0, 0, w, h]
+    b[1] = [-0.0, 1e-3, w + 1e-3, h - 1e-3]
+    if n > 4:
+        b[2, 1] = np.nan
+        b[3] = [np.inf, -np.inf, 1e9, -1e9]
+    return b
+
+
+def main():
+    ref = load_reference()
+    ops = ref.ops
+    rng = np.random.default_rng(20261017)
+    blob, meta = {}, []
+
+    def add(kind, args, inp, out):
+        i = len(meta)
+        blob[f"c{i}_in"] = np.asarray(inp, dtype=np.float32)
+        blob[f"c{i}_out"] = np.asarray(out, dtype=np.float32)
+        meta.append({"kind": kind, **args})
+        print(i, kind, args, blob[f"c{i}_in"].shape)
+
+    for s1, s0, rp in SHAPES:
+        for padding in (True, False):
+            for xywh in (False, True):
+                b = boxes_input(rng, 41, *s1)
+                out = ops.scale_boxes(s1, torch.from_numpy(b.copy()), s0, ratio_pad=rp, padding=padding, xywh=xywh)
+                add("scale_boxes", dict(img1=list(s1), img0=list(s0), ratio_pad=rp, padding=padding, xywh=xywh), b, out.numpy())
+        b = boxes_input(rng, 33, *s1)
+        add("clip_boxes", dict(shape=list(s0)), b, ops.clip_boxes(torch.from_numpy(b.copy()), s0).numpy())
+        for normalize in (False, True):
+            k = rng.uniform(-30, max(s1) + 30, size=(9, 17, 3)).astype(np.float32)
+            k[..., 2] = rng.uniform(0, 1, size=(9, 17))
+            k[0, 0, 0] = np.nan
+            out = ops.scale_coords(s1, torch.from_numpy(k.copy()), s0, ratio_pad=rp, normalize=normalize)
+            add("scale_coords", dict(img1=list(s1), img0=list(s0), ratio_pad=rp, normalize=normalize, padding=True), k, out.numpy())
+        k = rng.uniform(-30, max(s1) + 30, size=(64, 2)).astype(np.float32)
+        out = ops.scale_coords(s1, torch.from_numpy(k.copy()), s0, ratio_pad=rp, padding=False)
+        add("scale_coords", dict(img1=list(s1), img0=list(s0), ratio_pad=rp, normalize=False, padding=False), k, out.numpy())
+        k = rng.uniform(-30, max(s0[:2]) + 30, size=(5, 17, 2)).astype(np.float32)
+        add("clip_coords", dict(shape=list(s0)), k, ops.clip_coords(torch.from_numpy(k.copy()), s0).numpy())
+
+    # rotated boxes: the OBB head's angle range [-pi/4, 3pi/4) (head.py:1031) plus the branch points of ops.py:631-634
+    n = 200
+    rb = np.concatenate([rng.uniform(0, 1024, (n, 2)), rng.uniform(2, 400, (n, 2)),
+                         rng.uniform(-math.pi / 4, 3 * math.pi / 4, (n, 1))], 1).astype(np.float32)
+    edge = [0.0, -0.0, math.pi / 2, np.float32(math.pi / 2), np.nextafter(np.float32(math.pi / 2), np.float32(0)),
+            math.pi, np.float32(math.pi), -math.pi / 4, 3 * math.pi / 4, -1e-7, 1e-7, 2.0, -2.0, 7.0, -7.0, 1.5707964]
+    rb[: len(edge), 4] = np.asarray(edge, dtype=np.float32)
+    add("regularize_rboxes", {}, rb, ops.regularize_rboxes(torch.from_numpy(rb.copy())).numpy())
+    for s1, s0, _ in SHAPES[:5]:
+        pred = np.concatenate([rb[:, :4], rng.uniform(0.25, 1, (n, 1)), rng.integers(0, 15, (n, 1)), rb[:, 4:5]], 1).astype(np.float32)
+        p = torch.from_numpy(pred.copy())
+        # models/yolo/obb/predict.py:59-61, executed with the reference's own functions
+        r = ops.regularize_rboxes(torch.cat([p[:, :4], p[:, -1:]], dim=-1))
+        r[:, :4] = ops.scale_boxes(s1, r[:, :4], s0, xywh=True)
+        add("obb_result", dict(img1=list(s1), img0=list(s0)), pred, torch.cat([r, p[:, 4:6]], dim=-1).numpy())
+
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT, **blob)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""CPU restatement (numpy, fp32) of the reference's result-side helpers that follow NMS.
+
+TEST INFRASTRUCTURE ONLY - never imported by the product package (see oracle/__init__.py).
+
+Paths are relative to /root/reference/ultralytics/.  Unlike the reference (in-place torch ops) these are pure functions
+on numpy float32 arrays; every arithmetic step is one IEEE fp32 operation, in the reference's order, so results equal the
+reference's CPU results bit for bit.  Pinned by tests/golden/post/result_ops.npz (oracle/make_golden_post.py runs the live
+reference).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+F = np.float32
+
+
+def letterbox_scalars(img1_shape, img0_shape, ratio_pad=None):
+    """gain, box pad (x, y), coord pad (x, y): utils/ops.py:120-127 and :580-587."""
+    h0, w0 = img0_shape[:2]
+    if ratio_pad is None:
+        h1, w1 = img1_shape[:2]
+        gain = min(h1 / h0, w1 / w0)
+        cpad = ((w1 - w0 * gain) / 2, (h1 - h0 * gain) / 2)
+        pad = (round(cpad[0] - 0.1), round(cpad[1] - 0.1))
+    else:
+        gain = ratio_pad[0][0]
+        pad = cpad = tuple(ratio_pad[1])
+    return gain, pad, cpad
+
+
+def _clamp(v, hi):
+    with np.errstate(invalid="ignore"):
+        out = np.minimum(np.maximum(v, F(0)), F(hi))
+    return np.where(np.isnan(v), v, out).astype(F)
+
+
+def clip_boxes_oracle(boxes, shape):
+    """utils/ops.py:152-177: x to [0, w], y to [0, h]."""
+    h, w = shape[:2]
+    b = np.array(boxes, dtype=F, copy=True)
+    for col, hi in ((0, w), (1, h), (2, w), (3, h)):
+        b[..., col] = _clamp(b[..., col], hi)
+    return b
+
+
+def scale_boxes_oracle(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xywh=False):
+    """utils/ops.py:102-135."""
+    gain, pad, _ = letterbox_scalars(img1_shape, img0_shape, ratio_pad)
+    b = np.array(boxes, dtype=F, copy=True)
+    if padding:
+        for col in (0, 1) if xywh else (0, 1, 2, 3):
+            b[..., col] = b[..., col] - F(pad[col & 1])
+    b[..., :4] = b[..., :4] / F(gain)
+    return b if xywh else clip_boxes_oracle(b, img0_shape)
+
+
+def _remainder(a, m):
+    """torch.remainder for fp32 (fmod, then moved into the divisor's sign); fmod is exact."""
+    r = np.fmod(a, F(m)).astype(F)
+    fix = (r != 0) & ((F(m) < 0) != (r < 0))
+    return np.where(fix, r + F(m), r).astype(F)
+
+
+def regularize_rboxes_oracle(rboxes):
+    """utils/ops.py:621-636."""
+    r = np.array(rboxes, dtype=F, copy=True)
+    t = r[..., 4]
+    swap = _remainder(t, math.pi) >= F(math.pi / 2)
+    w, h = r[..., 2].copy(), r[..., 3].copy()
+    r[..., 2] = np.where(swap, h, w)
+    r[..., 3] = np.where(swap, w, h)
+    r[..., 4] = _remainder(t, math.pi / 2)
+    return r
+
+
+def clip_coords_oracle(coords, shape):
+    """utils/ops.py:598-618."""
+    h, w = shape[:2]
+    c = np.array(coords, dtype=F, copy=True)
+    c[..., 0] = _clamp(c[..., 0], w)
+    c[..., 1] = _clamp(c[..., 1], h)
+    return c
+
+
+def scale_coords_oracle(img1_shape, coords, img0_shape, ratio_pad=None, normalize=False, padding=True):
+    """utils/ops.py:562-595."""
+    gain, _, cpad = letterbox_scalars(img1_shape, img0_shape, ratio_pad)
+    h0, w0 = img0_shape[:2]
+    c = np.array(coords, dtype=F, copy=True)
+    if padding:
+        c[..., 0] = c[..., 0] - F(cpad[0])
+        c[..., 1] = c[..., 1] - F(cpad[1])
+    c[..., 0] = c[..., 0] / F(gain)
+    c[..., 1] = c[..., 1] / F(gain)
+    c = clip_coords_oracle(c, img0_shape)
+    if normalize:
+        c[..., 0] = c[..., 0] / F(w0)
+        c[..., 1] = c[..., 1] / F(h0)
+    return c
+
+
+def obb_result_oracle(pred, img1_shape, img0_shape):
+    """models/yolo/obb/predict.py:59-61: rows cx,cy,w,h,conf,cls,angle -> (N, 7) x,y,w,h,angle,conf,cls."""
+    p = np.asarray(pred, dtype=F)
+    rb = regularize_rboxes_oracle(np.concatenate([p[:, :4], p[:, -1:]], -1))
+    rb[:, :4] = scale_boxes_oracle(img1_shape, rb[:, :4], img0_shape, xywh=True)
+    return np.concatenate([rb, p[:, 4:6]], -1)

@@ -182,6 +182,10 @@ def test_patch_points_exist_in_reference_when_mounted():
         assert out[0].shape == (1, 6)
         keep = ref.TorchNMS.nms(torch.tensor([[0.0, 0, 10, 10], [1, 1, 11, 11]]), torch.tensor([0.9, 0.8]), 0.5)
         assert keep.tolist() == [0]
+        assert {f"ultralytics.utils.ops.{n}" for n in ("scale_boxes", "clip_boxes", "scale_coords", "clip_coords", "regularize_rboxes")} <= set(done)
+        bx = ref.ops.scale_boxes((640, 640), torch.tensor([[10.0, 20.0, 700.0, 300.0]]), (480, 640))  # CPU -> reference
+        assert bx.tolist() == [[10.0, 0.0, 640.0, 220.0]]
+        assert ref.ops.regularize_rboxes(torch.tensor([[1.0, 2.0, 3.0, 4.0, 2.0]]))[0, 2].item() == 4.0
     finally:
         patch.uninstall()
     assert ref.nms.non_max_suppression.__name__ == "non_max_suppression" and not hasattr(ref.nms.non_max_suppression, "__wrapped__")

@@ -16,7 +16,7 @@ from . import build as _build
 YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -32,7 +32,11 @@ EXPORTS = (
     "ypb_nms_boxes",
     "ypb_selftest_sigmoid_monotone",
     "ypb_debug_set_phase_buffer",
+    "ypb_scale_rows",
 )
+
+BOXES_NONE, BOXES_XYXY, BOXES_XYWH, BOXES_XYWHR, BOXES_CLIP_ONLY, BOXES_REGULARIZE_ONLY = range(6)
+SCALE_PADDING, SCALE_NORMALIZE, SCALE_COORDS_CLIP_ONLY = 1, 2, 4
 
 
 class HeadDesc(C.Structure):
@@ -87,7 +91,14 @@ class NmsOut(C.Structure):
         ("idx", C.c_void_p),
         ("count", C.c_void_p),
         ("cand_count", C.c_void_p),
+        ("scale_xforms", C.c_void_p),
+        ("scale_padding", C.c_int32),
+        ("reserved", C.c_int32),
     ]
+
+
+class ScaleXform(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("gain", "pad_x", "pad_y", "img_w", "img_h", "cpad_x", "cpad_y", "reserved")]
 
 
 _lib = None
@@ -133,6 +144,10 @@ def load():
     lib.ypb_debug_set_phase_buffer.argtypes = [C.c_void_p]
     lib.ypb_selftest_sigmoid_monotone.restype = C.c_int
     lib.ypb_selftest_sigmoid_monotone.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ypb_scale_rows.restype = C.c_int
+    lib.ypb_scale_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.POINTER(ScaleXform), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyolopost_b200.so")
 STAMP = os.path.join(LIB_DIR, "libyolopost_b200.stamp")
-SOURCES = ("ypb_decode.cu", "ypb_nms.cu", "ypb_abi.cu")
+SOURCES = ("ypb_decode.cu", "ypb_nms.cu", "ypb_post.cu", "ypb_abi.cu")
 HEADERS = ("ypb_common.cuh", os.path.join("..", "..", "include", "yolopost_b200.h"))
 
 NVCC_FLAGS = [
@@ -51,21 +51,57 @@ def is_current() -> bool:
         return fh.read().strip() == _source_digest()
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile the three translation units into one shared object; returns its path."""
-    if not force and is_current():
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("YPB_EXTRA_NVCC", "").split()]
+def _compile_one(nvcc: str, src: str, obj: str, verbose: bool):
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f not in ("-shared",)], *os.environ.get("YPB_EXTRA_NVCC", "").split()]
+    # "-cudart shared" is a link-time option; harmless at compile time
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-o", LIB_PATH]
+    cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
+    return src, cmd, proc
+
+
+def _unit_digest(src: str) -> str:
+    h = hashlib.sha256()
+    for name in (src,) + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("YPB_EXTRA_NVCC", "").encode())
+    return h.hexdigest()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the translation units (in parallel, objects cached per unit under _lib/obj) and link one shared object."""
+    if not force and is_current():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        tag = obj + ".digest"
+        objs.append(obj)
+        digest = _unit_digest(src)
+        fresh = os.path.exists(obj) and os.path.exists(tag) and open(tag).read().strip() == digest
+        if force or verbose or not fresh:
+            jobs.append((src, obj, tag, digest))
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as pool:
+        results = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+    for (src, obj, tag, digest), (_, cmd, proc) in zip(jobs, results):
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+        with open(tag, "w") as fh:
+            fh.write(digest)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", *objs, "-o", LIB_PATH]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
     with open(STAMP, "w") as fh:
         fh.write(_source_digest())
     return LIB_PATH

@@ -114,6 +114,7 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   s.cand_ang = p->rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
   s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
   s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_cand = out->cand_count;
+  s.scale_xforms = out->scale_xforms; s.scale_padding = out->scale_padding;
   return s;
 }
 
@@ -271,6 +272,29 @@ int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t bo
   s.out_rows = nullptr; s.out_idx = reinterpret_cast<long long*>(keep); s.out_count = keep_count; s.idx_as_row = 1;
   e = ypb::launch_sort_suppress(s, st);
   if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  return YPB_OK;
+}
+
+int ypb_scale_rows(float* rows, int64_t image_stride, int64_t row_stride, int32_t batch, int32_t rows_per_image,
+                   const int32_t* count, const ypb_scale_xform* xforms, const ypb_scale_xform* xform, int32_t box_mode,
+                   int32_t flags, int32_t angle_col, float* coords, int64_t coord_image_stride, int64_t coord_row_stride,
+                   int32_t nk, int32_t ndim, void* stream) {
+  if (batch < 0 || rows_per_image < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d rows_per_image=%d invalid", batch, rows_per_image);
+  if (box_mode < YPB_BOXES_NONE || box_mode > YPB_BOXES_REGULARIZE_ONLY) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown box mode %d", box_mode);
+  if (box_mode != YPB_BOXES_NONE && !rows && batch * rows_per_image > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "rows is NULL");
+  if (!xforms && !xform) return fail(YPB_ERR_INVALID_ARGUMENT, "neither a transform array nor a single transform given");
+  if ((box_mode == YPB_BOXES_XYWHR || box_mode == YPB_BOXES_REGULARIZE_ONLY) && angle_col < 4)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "angle_col=%d must be >= 4", angle_col);
+  if (nk < 0 || (nk > 0 && (ndim < 2 || !coords))) return fail(YPB_ERR_INVALID_ARGUMENT, "nk=%d ndim=%d coords=%p invalid", nk, ndim, (void*)coords);
+  if (box_mode == YPB_BOXES_NONE && nk == 0) return YPB_OK;
+  ypb::ScaleArgs s{};
+  s.rows = rows; s.image_stride = image_stride; s.row_stride = row_stride; s.batch = batch; s.rows_per_image = rows_per_image;
+  s.count = count; s.xforms = xforms;
+  if (xform) s.xform = *xform;
+  s.box_mode = box_mode; s.flags = flags; s.angle_col = angle_col;
+  s.coords = coords; s.coord_image_stride = coord_image_stride; s.coord_row_stride = coord_row_stride; s.nk = nk; s.ndim = ndim;
+  cudaError_t e = ypb::launch_scale_rows(s, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_scale_rows");
   return YPB_OK;
 }
 

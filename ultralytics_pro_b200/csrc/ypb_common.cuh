@@ -203,6 +203,47 @@ __device__ __forceinline__ BoxXYWH decode_rotated(float dl, float dt, float dr, 
 __device__ __forceinline__ float activate_angle(float t) { return (sigmoid_f(t) - 0.25f) * 3.14159265358979323846f; }
 
 // ---------------------------------------------------------------------------------------------------------------
+// result-side rescale (utils/ops.py:102-135 scale_boxes, :152-177 clip_boxes, :621-636 regularize_rboxes): shared by
+// scale_rows_kernel and the fused gather of sort_suppress_kernel.  Every step is one separately rounded fp32 operation.
+// ---------------------------------------------------------------------------------------------------------------
+// torch.remainder on fp32 (ATen cpu/BinaryOpsKernel.cpp remainder_kernel): fmod, then shifted into the sign of b.
+__device__ __forceinline__ float torch_remainder(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.f && ((b < 0.f) != (m < 0.f))) m = __fadd_rn(m, b);
+  return m;
+}
+
+// torch.clamp_(lo, hi) on fp32: NaN propagates.
+__device__ __forceinline__ float torch_clamp(float x, float lo, float hi) {
+  return x != x ? x : fminf(fmaxf(x, lo), hi);
+}
+
+__device__ __forceinline__ void scale_box(float& x0, float& y0, float& x1, float& y1, float* angle,
+                                          const ypb_scale_xform& xf, int mode, bool padding) {
+  if (mode == YPB_BOXES_XYWHR || mode == YPB_BOXES_REGULARIZE_ONLY) {
+    // ops.py:621-636: swap w/h when (t mod pi) >= pi/2, then t mod pi/2
+    const float PI_F = 3.14159274101257324f, HALF_PI_F = 1.57079637050628662f;  // float32(math.pi), float32(math.pi / 2)
+    const float th = *angle;
+    const bool swap = torch_remainder(th, PI_F) >= HALF_PI_F;
+    const float w = swap ? y1 : x1, h = swap ? x1 : y1;
+    x1 = w; y1 = h;
+    *angle = torch_remainder(th, HALF_PI_F);
+  }
+  if (mode != YPB_BOXES_CLIP_ONLY && mode != YPB_BOXES_REGULARIZE_ONLY) {
+    if (padding) {  // ops.py:128-133
+      x0 = __fsub_rn(x0, xf.pad_x); y0 = __fsub_rn(y0, xf.pad_y);
+      if (mode == YPB_BOXES_XYXY) { x1 = __fsub_rn(x1, xf.pad_x); y1 = __fsub_rn(y1, xf.pad_y); }
+    }
+    x0 = __fdiv_rn(x0, xf.gain); y0 = __fdiv_rn(y0, xf.gain);  // ops.py:134
+    x1 = __fdiv_rn(x1, xf.gain); y1 = __fdiv_rn(y1, xf.gain);
+  }
+  if (mode == YPB_BOXES_XYXY || mode == YPB_BOXES_CLIP_ONLY) {  // ops.py:135 -> :163-177
+    x0 = torch_clamp(x0, 0.f, xf.img_w); y0 = torch_clamp(y0, 0.f, xf.img_h);
+    x1 = torch_clamp(x1, 0.f, xf.img_w); y1 = torch_clamp(y1, 0.f, xf.img_h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // sort keys: 64-bit, unique per image.  hi = ~orderable(score), lo = row id ((anchor << cls_bits) | cls), so an ascending
 // sort is "score descending, then lower row first" == torchvision's stable descending sort (Ties).
 // ---------------------------------------------------------------------------------------------------------------
@@ -331,9 +372,26 @@ struct SuppressArgs {
   int32_t* out_count;
   int32_t* out_cand;
   int idx_as_row;  // ypb_nms_boxes: write the row id itself
+  // optional fused construct_result rescale of the kept rows (ypb_nms_out.scale_*)
+  const ypb_scale_xform* scale_xforms;
+  int scale_padding;
   long long* dbg;  // diagnostic phase timestamps or null
 };
 void set_phase_buffer(long long* p);
+
+struct ScaleArgs {  // ypb_scale_rows: see include/yolopost_b200.h
+  float* rows;
+  long long image_stride, row_stride;  // elements
+  int batch, rows_per_image;
+  const int32_t* count;                // device (B) or null = every row
+  const ypb_scale_xform* xforms;       // device (B) or null = `xform` for every image
+  ypb_scale_xform xform;
+  int box_mode, flags, angle_col;
+  float* coords;                       // first point of row 0 of image 0, or null
+  long long coord_image_stride, coord_row_stride;
+  int nk, ndim;
+};
+cudaError_t launch_scale_rows(const ScaleArgs& s, cudaStream_t st);
 
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,

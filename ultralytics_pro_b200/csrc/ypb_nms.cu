@@ -892,8 +892,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     if (a.out_idx) a.out_idx[static_cast<long long>(b) * a.max_det + k] = a.idx_as_row ? row : anchor;
     if (a.out_rows) {
       float* o = a.out_rows + (static_cast<long long>(b) * a.max_det + k) * cols;
-      const float4 bx = cand_box[anchor];
-      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+      float4 bx = cand_box[anchor];
       o[4] = key_score(key);
       o[5] = static_cast<float>(cls);
       if (a.pred) {
@@ -903,6 +902,16 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       } else if (a.extra == 1 && cand_ang3) {
         o[6] = cand_ang3[anchor];
       }
+      if (a.scale_xforms) {
+        // detect/predict.py:120 (scale_boxes) or obb/predict.py:59-60 (regularize_rboxes + scale_boxes(xywh=True)),
+        // fused into the gather: the angle is the row's last column (nms.py:146)
+        const ypb_scale_xform xf = a.scale_xforms[b];
+        if constexpr (RULE == YPB_NMS_FAST_PROBIOU)
+          scale_box(bx.x, bx.y, bx.z, bx.w, o + cols - 1, xf, YPB_BOXES_XYWHR, a.scale_padding);
+        else
+          scale_box(bx.x, bx.y, bx.z, bx.w, nullptr, xf, YPB_BOXES_XYXY, a.scale_padding);
+      }
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
     }
   }
   __syncthreads();

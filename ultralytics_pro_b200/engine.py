@@ -101,10 +101,12 @@ class NmsPlan:
     packed: torch.Tensor  # rows and count are views of this one fp32 buffer: [B*max_det*cols rows | B counts (int32 bits)]
     scratch: torch.Tensor = None
     keep_alive: tuple = ()
+    xforms: torch.Tensor = None  # (B, 8) ypb_scale_xform array when the gather rescales to the original images
 
 
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
-              max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None) -> NmsPlan:
+              max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
+              scale_padding: bool = True) -> NmsPlan:
     rows_cap = anchors * nc if multi_label else anchors
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))
@@ -127,7 +129,23 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     p.class_mask = mask.data_ptr() if mask is not None else None
     o = _cabi.NmsOut()
     o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
-    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,))
+    xforms = None
+    if with_scale:  # fused construct_result rescale (detect/predict.py:120, obb/predict.py:59-60)
+        xforms = torch.zeros((max(batch, 1), 8), dtype=torch.float32, device=device)
+        xforms[:, 0] = 1.0
+        o.scale_xforms, o.scale_padding = xforms.data_ptr(), int(bool(scale_padding))
+    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,), xforms)
+
+
+def set_transforms(plan: NmsPlan, img1_shape, orig_shapes, ratio_pads=None) -> None:
+    """Load the per-image letterbox transforms of this batch into the plan's static device array (stream-ordered)."""
+    from . import ops
+
+    if plan.xforms is None:
+        raise RuntimeError("the plan was built without with_scale=True")
+    if len(orig_shapes) != plan.xforms.shape[0]:
+        raise ValueError(f"{len(orig_shapes)} original shapes for a batch of {plan.xforms.shape[0]}")
+    plan.xforms.copy_(ops.transforms_tensor(img1_shape, orig_shapes, ratio_pads, plan.xforms.device), non_blocking=True)
 
 
 def fetch_counts(count: torch.Tensor) -> list:

@@ -73,12 +73,16 @@ def detect_inference(self, x: list) -> torch.Tensor:
 def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                           agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                           max_wh: int = 7680, reg_max: int = 16, angle_logits: torch.Tensor | None = None,
-                          return_idxs: bool = False, sync: bool = True):
+                          return_idxs: bool = False, sync: bool = True, img_shape=None, orig_shapes=None,
+                          ratio_pads=None):
     """Fused ``Detect._inference`` + ``non_max_suppression`` (head.py:151-169 then nms.py:13-166).
 
     Bit-identical to ``non_max_suppression(decode_head(levels, ...), ...)`` but reads the head once and never writes
     the (B, 4+nc, A) tensor.  ``angle_logits`` (B, 1, A) switches to the OBB path (rotated decode + ProbIoU Fast-NMS).
     With ``sync=False`` returns the device-resident plan (rows/idx/count tensors) without any host transfer.
+    ``orig_shapes`` (list of per-image (h, w[, c]), with ``img_shape`` = network input (h, w)) additionally folds the
+    predictor's ``construct_result`` rescale into the gather: ``scale_boxes`` (detect/predict.py:120) or, for OBB,
+    ``regularize_rboxes`` + ``scale_boxes(xywh=True)`` (obb/predict.py:59-60); rows stay cx,cy,w,h,conf,cls,angle.
     """
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
@@ -94,7 +98,12 @@ def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, io
     else:
         rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(iou_thres)
     plan = engine.make_plan(lv0.device, b, anchors, nc, 1 if rotated else 0, conf_t, iou_eff, max_det, max_nms,
-                            0.0 if agnostic else float(max_wh), multi_label, rule, classes)
+                            0.0 if agnostic else float(max_wh), multi_label, rule, classes,
+                            with_scale=orig_shapes is not None)
+    if orig_shapes is not None and b:
+        if img_shape is None:
+            img_shape = (lv0.shape[2] * int(strides[0]), lv0.shape[3] * int(strides[0]))
+        engine.set_transforms(plan, img_shape, orig_shapes, ratio_pads)
     if b:
         engine.run_from_head(desc, angle_logits, True, plan, lv0.device)
     else:

@@ -1,0 +1,177 @@
+"""Drop-ins for the result-side helpers of ``ultralytics/utils/ops.py`` that run right after NMS:
+
+  scale_boxes (ops.py:102-135)   clip_boxes (ops.py:152-177)    regularize_rboxes (ops.py:621-636)
+  scale_coords (ops.py:562-595)  clip_coords (ops.py:598-618)
+
+Same names, arguments and in-place behaviour as the reference; each call is ONE launch of ``scale_rows_kernel``
+(libyolopost_b200) instead of the reference's 9-13 ATen launches.  ``scale_results`` applies the same arithmetic to the
+kept rows of a whole batch (per-image transform and count, still one launch, no host synchronisation).
+Arithmetic follows the reference's CPU results bit for bit: fp32, every step separately rounded, IEEE division.
+There is no CPU path: CPU tensors raise (``patch.install`` leaves those with the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+
+_f32 = _cabi.f32_round
+
+
+def letterbox_transform(img1_shape, img0_shape, ratio_pad=None) -> _cabi.ScaleXform:
+    """Host scalars of ops.py:120-127 (boxes) and ops.py:580-587 (coords) for one image, rounded to fp32."""
+    h0, w0 = img0_shape[:2]
+    if ratio_pad is None:
+        h1, w1 = img1_shape[:2]
+        gain = min(h1 / h0, w1 / w0)
+        cpad_x, cpad_y = (w1 - w0 * gain) / 2, (h1 - h0 * gain) / 2
+        pad_x, pad_y = round(cpad_x - 0.1), round(cpad_y - 0.1)
+    else:
+        gain = ratio_pad[0][0]
+        pad_x, pad_y = ratio_pad[1]
+        cpad_x, cpad_y = pad_x, pad_y
+    x = _cabi.ScaleXform()
+    x.gain, x.pad_x, x.pad_y, x.img_w, x.img_h = _f32(gain), _f32(pad_x), _f32(pad_y), _f32(w0), _f32(h0)
+    x.cpad_x, x.cpad_y = _f32(cpad_x), _f32(cpad_y)
+    return x
+
+
+def _rows2d(t: torch.Tensor, min_cols: int, what: str) -> torch.Tensor:
+    _cabi.require_cuda(t, what)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32 result rows (nms.py:116 promotes them), got {t.dtype}")
+    if t.shape[-1] < min_cols:
+        raise ValueError(f"{what}: last dimension {t.shape[-1]} < {min_cols}")
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.dim() > 2:
+        t = t.view(-1, t.shape[-1])  # raises for layouts that are not a uniform stack of rows
+    if t.shape[0] and t.stride(1) != 1:
+        raise ValueError(f"{what}: the coordinates of a row must be contiguous")
+    return t
+
+
+def _launch(rows2d, xf, box_mode, flags=0, angle_col=0, coords=None, coord_row_stride=0, nk=0, ndim=0):
+    lib = _cabi.load()
+    base = rows2d if rows2d is not None else coords
+    n = base.shape[0]
+    if n == 0:
+        return
+    rc = lib.ypb_scale_rows(rows2d.data_ptr() if rows2d is not None else None, 0, rows2d.stride(0) if rows2d is not None else 0,
+                            1, n, None, None, C.byref(xf), box_mode, flags, angle_col,
+                            coords.data_ptr() if coords is not None else None, 0, coord_row_stride, nk, ndim,
+                            _cabi.stream_ptr(base.device))
+    _cabi.check(rc, "ypb_scale_rows")
+
+
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding: bool = True, xywh: bool = False):
+    """Rescale boxes (N, 4) from ``img1_shape`` (network input) to ``img0_shape`` in place; mirror of ops.py:102-135."""
+    r = _rows2d(boxes, 4, "scale_boxes")
+    xf = letterbox_transform(img1_shape, img0_shape, ratio_pad)
+    _launch(r, xf, _cabi.BOXES_XYWH if xywh else _cabi.BOXES_XYXY, _cabi.SCALE_PADDING if padding else 0)
+    return boxes
+
+
+def clip_boxes(boxes, shape):
+    """Clamp xyxy boxes to the image in place; mirror of ops.py:152-177."""
+    r = _rows2d(boxes, 4, "clip_boxes")
+    xf = _cabi.ScaleXform()
+    xf.gain, xf.img_w, xf.img_h = 1.0, _f32(shape[1]), _f32(shape[0])
+    _launch(r, xf, _cabi.BOXES_CLIP_ONLY)
+    return boxes
+
+
+def regularize_rboxes(rboxes):
+    """Angles into [0, pi/2) with w/h swapped where needed; returns a new (N, 5) tensor like ops.py:621-636."""
+    _cabi.require_cuda(rboxes, "regularize_rboxes")
+    out = rboxes.to(torch.float32).clone(memory_format=torch.contiguous_format)
+    r = _rows2d(out, 5, "regularize_rboxes")
+    xf = _cabi.ScaleXform()
+    xf.gain = 1.0
+    _launch(r, xf, _cabi.BOXES_REGULARIZE_ONLY, angle_col=4)
+    return out
+
+
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, normalize: bool = False, padding: bool = True):
+    """Rescale points (..., 2|3) in place (x, y are the first two of the last dimension); mirror of ops.py:562-595."""
+    _cabi.require_cuda(coords, "scale_coords")
+    if coords.dtype != torch.float32:
+        raise TypeError(f"scale_coords: expected float32, got {coords.dtype}")
+    ndim = coords.shape[-1]
+    pts = coords.view(-1, ndim)
+    if pts.shape[0] and pts.stride(1) != 1:
+        raise ValueError("scale_coords: x and y of a point must be adjacent")
+    xf = letterbox_transform(img1_shape, img0_shape, ratio_pad)
+    flags = (_cabi.SCALE_PADDING if padding else 0) | (_cabi.SCALE_NORMALIZE if normalize else 0)
+    _launch(None, xf, _cabi.BOXES_NONE, flags, coords=pts, coord_row_stride=pts.stride(0) if pts.shape[0] else ndim, nk=1, ndim=ndim)
+    return coords
+
+
+def clip_coords(coords, shape):
+    """Clamp points to the image in place; mirror of ops.py:598-618."""
+    _cabi.require_cuda(coords, "clip_coords")
+    if coords.dtype != torch.float32:
+        raise TypeError(f"clip_coords: expected float32, got {coords.dtype}")
+    ndim = coords.shape[-1]
+    pts = coords.view(-1, ndim)
+    xf = _cabi.ScaleXform()
+    xf.gain, xf.img_w, xf.img_h = 1.0, _f32(shape[1]), _f32(shape[0])
+    _launch(None, xf, _cabi.BOXES_NONE, _cabi.SCALE_COORDS_CLIP_ONLY, coords=pts,
+            coord_row_stride=pts.stride(0) if pts.shape[0] else ndim, nk=1, ndim=ndim)
+    return coords
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batched form: the kept rows of a whole batch in one launch
+# ----------------------------------------------------------------------------------------------------------------
+_xform_cache: dict = {}
+
+
+def transforms_tensor(img1_shape, orig_shapes, ratio_pads=None, device=None) -> torch.Tensor:
+    """(B, 8) fp32 device array of ``ypb_scale_xform`` for a batch; cached per (shapes, device)."""
+    key = (tuple(img1_shape[:2]), tuple(tuple(s[:2]) for s in orig_shapes),
+           None if ratio_pads is None else tuple((tuple(r[0]), tuple(r[1])) for r in ratio_pads), str(device))
+    t = _xform_cache.get(key)
+    if t is None:
+        rows = []
+        for i, s0 in enumerate(orig_shapes):
+            x = letterbox_transform(img1_shape, s0, None if ratio_pads is None else ratio_pads[i])
+            rows.append([x.gain, x.pad_x, x.pad_y, x.img_w, x.img_h, x.cpad_x, x.cpad_y, 0.0])
+        t = torch.tensor(rows, dtype=torch.float32).pin_memory().to(device, non_blocking=True)
+        if len(_xform_cache) > 256:
+            _xform_cache.clear()
+        _xform_cache[key] = t
+    return t
+
+
+def scale_results(rows: torch.Tensor, count: torch.Tensor | None, img1_shape, orig_shapes, ratio_pads=None,
+                  padding: bool = True, rotated: bool = False, kpt_shape=None, normalize_kpts: bool = False):
+    """In-place ``construct_result`` scaling (detect/predict.py:120, obb/predict.py:59-60, pose/predict.py:73-75) of the
+    padded result rows ``(B, max_det, 6+extra)`` of a batch, honouring the per-image kept ``count`` (device int32) -
+    one launch, nothing read back.  ``rotated``: rows are cx,cy,w,h,conf,cls,angle -> regularize + xywh scaling;
+    ``kpt_shape``: (nk, ndim) keypoints in columns 6.. are scaled like ``scale_coords``."""
+    _cabi.require_cuda(rows, "scale_results")
+    if rows.dtype != torch.float32 or rows.dim() != 3 or rows.stride(2) != 1:
+        raise ValueError("scale_results: rows must be a (B, max_det, cols) float32 tensor with contiguous columns")
+    b, m, cols = rows.shape
+    if len(orig_shapes) != b:
+        raise ValueError(f"{len(orig_shapes)} original shapes for a batch of {b}")
+    xf = transforms_tensor(img1_shape, orig_shapes, ratio_pads, rows.device)
+    mode = _cabi.BOXES_XYWHR if rotated else _cabi.BOXES_XYXY
+    nk = ndim = 0
+    coords_ptr = None
+    if kpt_shape is not None:
+        nk, ndim = int(kpt_shape[0]), int(kpt_shape[1])
+        if cols < 6 + nk * ndim:
+            raise ValueError(f"rows have {cols} columns, keypoints need {6 + nk * ndim}")
+        coords_ptr = rows.data_ptr() + 6 * 4
+    flags = (_cabi.SCALE_PADDING if padding else 0) | (_cabi.SCALE_NORMALIZE if normalize_kpts else 0)
+    lib = _cabi.load()
+    rc = lib.ypb_scale_rows(rows.data_ptr(), rows.stride(0), rows.stride(1), b, m,
+                            count.data_ptr() if count is not None else None, xf.data_ptr(), None, mode, flags,
+                            cols - 1 if rotated else 0, coords_ptr, rows.stride(0), rows.stride(1), nk, ndim,
+                            _cabi.stream_ptr(rows.device))
+    _cabi.check(rc, "ypb_scale_rows")
+    return rows

@@ -13,6 +13,9 @@ What is rebound (reference paths relative to ultralytics/):
                                                    models/yolo/obb/val.py:14 and engine/exporter.py:122 hold the class by name
   nn/modules/head.py:151   Detect._inference (and the byte-identical copies MAFDetect :340, IDetect :535, DDetect :724);
                                                    Segment/Pose/OBB/World/YOLOE/v10 inherit it
+  utils/ops.py:102,152,562,598,621  scale_boxes / clip_boxes / scale_coords / clip_coords / regularize_rboxes - on the module
+                                                   object (every caller goes through `ops.<name>`: detect/predict.py:120,
+                                                   obb/predict.py:59-60, pose/predict.py:75, detect/val.py:422, engine/results.py:341)
 CUDA tensors take the kernels; anything else (CPU tensors, training mode, export) is handed to the original, untouched
 reference function - that is the reference running, not a fallback of this library.
 """
@@ -58,6 +61,27 @@ def _wrap_static(ref_fn, ours):
     return staticmethod(f)
 
 
+_OPS_NAMES = ("scale_boxes", "clip_boxes", "scale_coords", "clip_coords", "regularize_rboxes")
+
+
+def _wrap_ops(ref_fn, ours, tensor_arg: int):
+    def f(*args, **kwargs):
+        t = args[tensor_arg] if len(args) > tensor_arg else None
+        if t is None:
+            t = kwargs.get("boxes", kwargs.get("coords", kwargs.get("rboxes")))
+        import torch
+
+        if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() <= 2 + (ref_fn.__name__.endswith("coords")) \
+                and (t.numel() == 0 or t.stride(-1) == 1):
+            return ours(*args, **kwargs)
+        return ref_fn(*args, **kwargs)
+
+    f.__wrapped__ = ref_fn
+    f.__name__ = ref_fn.__name__
+    f.__doc__ = ref_fn.__doc__
+    return f
+
+
 def install() -> list:
     """Patch the already-importable `ultralytics` package in place; returns the list of rebound symbols."""
     from . import head as our_head
@@ -82,6 +106,14 @@ def install() -> list:
         _saved[f"ultralytics.utils.nms.TorchNMS.{name}"] = (cls, name, orig)
         setattr(cls, name, _wrap_static(getattr(cls, name), getattr(our_nms.TorchNMS, name)))
         done.append(f"ultralytics.utils.nms.TorchNMS.{name}")
+    from . import ops as our_ops
+
+    ref_ops = importlib.import_module("ultralytics.utils.ops")
+    for name in _OPS_NAMES:
+        orig = getattr(ref_ops, name)
+        _saved[f"ultralytics.utils.ops.{name}"] = (ref_ops, name, orig)
+        setattr(ref_ops, name, _wrap_ops(orig, getattr(our_ops, name), 0 if name in ("clip_boxes", "clip_coords", "regularize_rboxes") else 1))
+        done.append(f"ultralytics.utils.ops.{name}")
     # fast_nms resolves iou_func by __name__, so the reference's own box_iou / batch_probiou callables are recognised
     try:
         ref_head = importlib.import_module("ultralytics.nn.modules.head")

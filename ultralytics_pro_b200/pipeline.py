@@ -18,13 +18,16 @@ from .nms import _greedy_threshold
 class HeadPostProcessor:
     def __init__(self, nc: int, strides, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                  agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
-                 max_wh: int = 7680, reg_max: int = 16, rotated: bool = False):
+                 max_wh: int = 7680, reg_max: int = 16, rotated: bool = False, scale_to_original: bool = False):
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
         self.nc, self.strides, self.reg_max = nc, tuple(float(s) for s in strides), reg_max
         self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
         self.classes, self.agnostic, self.multi_label = classes, agnostic, bool(multi_label) and nc > 1
         self.max_det, self.max_nms, self.max_wh, self.rotated = max_det, max_nms, max_wh, rotated
+        # fold construct_result's scale_boxes / regularize_rboxes (detect/predict.py:120, obb/predict.py:59-60) into the
+        # gather; the per-image transforms are loaded with set_image_shapes() before enqueue() / graph replay
+        self.scale_to_original = bool(scale_to_original)
         self._plans = {}
         self.last = None
 
@@ -40,13 +43,19 @@ class HeadPostProcessor:
                 rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(self.iou_thres)
             plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
                                     iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
-                                    self.multi_label, rule, self.classes)
+                                    self.multi_label, rule, self.classes, with_scale=self.scale_to_original)
             # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
             nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
                                                           plan.params.max_det, plan.params.max_nms, plan.params.rule)
             plan.scratch = torch.empty(nbytes, dtype=torch.uint8, device=lv0.device)
             self._plans[key] = plan
         return plan
+
+    def set_image_shapes(self, levels, img_shape, orig_shapes, ratio_pads=None):
+        """Stream-ordered update of the static per-image transform array of the plan for this geometry (graph-safe:
+        the captured kernels read the array at replay time)."""
+        _, keep, anchors = engine.head_desc(levels, self.strides, self.nc, self.reg_max)
+        engine.set_transforms(self._plan_for(keep, anchors), img_shape, orig_shapes, ratio_pads)
 
     def enqueue(self, levels, angle_logits=None, stage: int = 0):
         """Launch decode+NMS for one batch on the current stream; returns the device-resident plan (no sync)."""
