@@ -159,6 +159,29 @@ YPB_API int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int3
                       const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Riders of the fused path: per-anchor channels produced by a sibling branch of the head that travel with the kept
+ * rows as columns 6.. (nms.py:112 `mask`): Segment mask coefficients (head.py:831,837: (B, nm, A)) are copied, Pose
+ * keypoints (head.py:1248: raw (B, nk*ndim, A)) are decoded on the way (head.py:1254-1273 kpts_decode) - for the kept
+ * anchors only, the dense (B, nk*ndim, A) decode of the reference is never computed. */
+typedef enum { YPB_RIDER_RAW = 0, YPB_RIDER_KEYPOINTS = 1 } ypb_rider_kind;
+typedef struct {
+  const void* ptr;     /* (B, channels, A), anchors contiguous, same dtype as the head */
+  int32_t channels;    /* == ypb_nms_params.extra */
+  int32_t kind;        /* ypb_rider_kind */
+  int32_t kpt_ndim;    /* 2 | 3 (kpt_shape[1]) for YPB_RIDER_KEYPOINTS */
+  int32_t reserved;
+  int64_t stride_b, stride_c; /* elements */
+} ypb_riders_desc;
+
+YPB_API int ypb_nms_from_head_riders(const ypb_head_desc* head, const ypb_riders_desc* riders, int32_t value_dtype,
+                                     const ypb_nms_params* p, const ypb_nms_out* out, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* Pose.kpts_decode (head.py:1254-1273) on the whole (B, nk*ndim, A) tensor: out has the same shape/dtype, contiguous.
+ * Level geometry (grid sizes, strides) is taken from `head` (level pointers are not read). */
+YPB_API int ypb_kpts_decode(const ypb_head_desc* head, const void* kpts, int64_t stride_b, int64_t stride_c,
+                            int32_t channels, int32_t kpt_ndim, void* out, void* stream);
+
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
  * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);

@@ -95,6 +95,42 @@ def main():
     blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(OUT, **blob)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+    make_kpts(ref)
+
+
+def make_kpts(ref):
+    """Pose.kpts_decode (head.py:1254-1273) of the live reference on seeded raw keypoint logits."""
+    out_path = os.path.join(ROOT, "tests", "golden", "post", "kpts.npz")
+    blob, meta = {}, []
+    g = torch.Generator().manual_seed(77)
+    for name, imgsz, strides, kpt_shape, dtype in [
+        ("pose17x3_f32", 96, (8, 16, 32), (17, 3), torch.float32),
+        ("pose5x2_f32", 96, (8, 16, 32), (5, 2), torch.float32),
+        ("pose17x3_p6_f32", 128, (8, 16, 32, 64), (17, 3), torch.float32),
+        ("pose17x3_bf16", 96, (8, 16, 32), (17, 3), torch.bfloat16),
+        ("pose17x3_wide_f16", 1280, (8,), (3, 3), torch.float16),  # 160-wide grid: half-integer anchors round in 16 bit
+    ]:
+        hw = [(imgsz // s, imgsz // s) for s in strides]
+        if name.endswith("wide_f16"):
+            hw = [(2, 160)]
+        a = sum(h * w for h, w in hw)
+        head = ref.head.Pose(nc=1, kpt_shape=kpt_shape, ch=tuple(16 for _ in strides))
+        head.stride = torch.tensor([float(s) for s in strides])
+        feats = [torch.zeros(1, 16, h, w, dtype=dtype) for h, w in hw]
+        anc, st = ref.tal.make_anchors(feats, head.stride, 0.5)
+        head.anchors, head.strides = anc.transpose(0, 1), st.transpose(0, 1)  # head.py:163
+        head.export = False
+        kp = (torch.randn(2, kpt_shape[0] * kpt_shape[1], a, generator=g) * 2.5).to(dtype)
+        with torch.inference_mode():
+            out = head.kpts_decode(2, kp)
+        i = len(meta)
+        blob[f"k{i}_in"] = kp.float().numpy()
+        blob[f"k{i}_out"] = out.float().numpy()
+        meta.append(dict(name=name, level_hw=hw, strides=list(strides), kpt_shape=list(kpt_shape), dtype=str(dtype).split(".")[1]))
+        print(name, tuple(kp.shape))
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
 
 if __name__ == "__main__":

@@ -107,3 +107,22 @@ def obb_result_oracle(pred, img1_shape, img0_shape):
     rb = regularize_rboxes_oracle(np.concatenate([p[:, :4], p[:, -1:]], -1))
     rb[:, :4] = scale_boxes_oracle(img1_shape, rb[:, :4], img0_shape, xywh=True)
     return np.concatenate([rb, p[:, 4:6]], -1)
+
+
+def kpts_decode_oracle(kpts, level_hw, strides, kpt_shape):
+    """nn/modules/head.py:1254-1273 (Pose.kpts_decode, non-export branch) on a torch tensor (B, nk*ndim, A) of any float
+    dtype; every operation runs in that dtype like the reference's.  Anchors/strides as cached by head.py:163-165."""
+    import torch
+
+    from oracle.postproc_oracle import anchor_table
+
+    nk, ndim = kpt_shape
+    b, _, a = kpts.shape
+    anchors, srow = anchor_table(level_hw, strides, kpts.dtype)  # (2, A), (1, A)
+    y = kpts.reshape(b, nk, ndim, a)
+    parts = [(y[:, :, 0] * 2.0 + (anchors[0] - 0.5)) * srow, (y[:, :, 1] * 2.0 + (anchors[1] - 0.5)) * srow]
+    if ndim == 3:
+        parts.append(y[:, :, 2].sigmoid())
+    for d in range(len(parts), ndim):
+        parts.append(y[:, :, d])
+    return torch.stack(parts, 2).reshape(b, nk * ndim, a)

@@ -33,7 +33,10 @@ EXPORTS = (
     "ypb_selftest_sigmoid_monotone",
     "ypb_debug_set_phase_buffer",
     "ypb_scale_rows",
+    "ypb_nms_from_head_riders",
+    "ypb_kpts_decode",
 )
+RIDER_RAW, RIDER_KEYPOINTS = 0, 1
 
 BOXES_NONE, BOXES_XYXY, BOXES_XYWH, BOXES_XYWHR, BOXES_CLIP_ONLY, BOXES_REGULARIZE_ONLY = range(6)
 SCALE_PADDING, SCALE_NORMALIZE, SCALE_COORDS_CLIP_ONLY = 1, 2, 4
@@ -97,6 +100,18 @@ class NmsOut(C.Structure):
     ]
 
 
+class RidersDesc(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("channels", C.c_int32),
+        ("kind", C.c_int32),
+        ("kpt_ndim", C.c_int32),
+        ("reserved", C.c_int32),
+        ("stride_b", C.c_int64),
+        ("stride_c", C.c_int64),
+    ]
+
+
 class ScaleXform(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("gain", "pad_x", "pad_y", "img_w", "img_h", "cpad_x", "cpad_y", "reserved")]
 
@@ -148,6 +163,12 @@ def load():
     lib.ypb_scale_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.POINTER(ScaleXform), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ypb_nms_from_head_riders.restype = C.c_int
+    lib.ypb_nms_from_head_riders.argtypes = [C.POINTER(HeadDesc), C.POINTER(RidersDesc), C.c_int32, C.POINTER(NmsParams),
+                                             C.POINTER(NmsOut), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ypb_kpts_decode.restype = C.c_int
+    lib.ypb_kpts_decode.argtypes = [C.POINTER(HeadDesc), C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

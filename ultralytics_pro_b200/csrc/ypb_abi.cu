@@ -156,9 +156,26 @@ int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int32_t angl
   return ypb_nms_from_head_stage(head, angle, angle_is_logit, value_dtype, p, out, workspace, workspace_bytes, stream, 0);
 }
 
+static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
+                              const ypb_riders_desc* riders, const ypb_nms_params* p, const ypb_nms_out* out,
+                              void* workspace, size_t workspace_bytes, void* stream, int32_t stage);
+
 int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
                             const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
                             void* stream, int32_t stage) {
+  return nms_from_head_impl(head, angle, angle_is_logit, value_dtype, nullptr, p, out, workspace, workspace_bytes, stream, stage);
+}
+
+int ypb_nms_from_head_riders(const ypb_head_desc* head, const ypb_riders_desc* riders, int32_t value_dtype,
+                             const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!riders) return fail(YPB_ERR_INVALID_ARGUMENT, "riders descriptor is NULL");
+  return nms_from_head_impl(head, nullptr, 0, value_dtype, riders, p, out, workspace, workspace_bytes, stream, 0);
+}
+
+static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
+                              const ypb_riders_desc* riders, const ypb_nms_params* p, const ypb_nms_out* out,
+                              void* workspace, size_t workspace_bytes, void* stream, int32_t stage) {
   if (stage < 0 || stage > 7) return fail(YPB_ERR_INVALID_ARGUMENT, "stage mask=%d outside [0,7]", stage);
   if (stage == 0) stage = 7;
   ypb::HeadGeom g;
@@ -172,7 +189,18 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
   const bool rotated = p->rule == YPB_NMS_FAST_PROBIOU;
   if (rotated && !angle) return fail(YPB_ERR_INVALID_ARGUMENT, "rotated rule needs the angle channel");
   if (!rotated && angle) return fail(YPB_ERR_INVALID_ARGUMENT, "angle given but rule is not FAST_PROBIOU");
-  if (p->extra != (rotated ? 1 : 0)) return fail(YPB_ERR_INVALID_ARGUMENT, "fused path carries extra=%d only", rotated ? 1 : 0);
+  if (riders) {
+    if (rotated) return fail(YPB_ERR_UNSUPPORTED, "riders with the rotated rule");
+    if (!riders->ptr && head->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "riders pointer is NULL");
+    if (riders->channels < 1 || riders->channels != p->extra)
+      return fail(YPB_ERR_INVALID_ARGUMENT, "riders.channels=%d must equal params.extra=%d", riders->channels, p->extra);
+    if (riders->kind != YPB_RIDER_RAW && riders->kind != YPB_RIDER_KEYPOINTS) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown rider kind %d", riders->kind);
+    if (riders->kind == YPB_RIDER_KEYPOINTS && (riders->kpt_ndim < 2 || riders->channels % riders->kpt_ndim))
+      return fail(YPB_ERR_INVALID_ARGUMENT, "keypoint riders: channels=%d not a multiple of ndim=%d", riders->channels, riders->kpt_ndim);
+    if (riders->stride_c < g.anchors) return fail(YPB_ERR_INVALID_ARGUMENT, "riders channel stride < anchors");
+  } else if (p->extra != (rotated ? 1 : 0)) {
+    return fail(YPB_ERR_INVALID_ARGUMENT, "fused path carries extra=%d only (pass riders for more)", rotated ? 1 : 0);
+  }
   if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
   ypb::Workspace w = ypb::carve_workspace(workspace, head->batch, g.anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
   if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
@@ -202,9 +230,48 @@ int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_
   }
   if (stage & 4) {
     ypb::SuppressArgs s = suppress_args(p, out, w, head->batch, g.anchors);
+    if (riders) {
+      s.rider = riders->ptr; s.rider_dtype = head->dtype; s.rider_kind = riders->kind; s.rider_ndim = riders->kpt_ndim > 0 ? riders->kpt_ndim : 1;
+      s.rider_sb = riders->stride_b; s.rider_sc = riders->stride_c;
+      s.lv_n = g.num_levels;
+      for (int l = 0; l < g.num_levels; ++l) { s.lv_start[l] = g.anchor_start[l]; s.lv_w[l] = g.w[l]; s.lv_stride[l] = g.stride[l]; }
+      s.lv_start[g.num_levels] = g.anchors;
+    }
     e = ypb::launch_sort_suppress(s, st);
     if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
   }
+  return YPB_OK;
+}
+
+int ypb_kpts_decode(const ypb_head_desc* head, const void* kpts, int64_t stride_b, int64_t stride_c, int32_t channels,
+                    int32_t kpt_ndim, void* out, void* stream) {
+  if (!head) return fail(YPB_ERR_INVALID_ARGUMENT, "head descriptor is NULL");
+  if (head->num_levels < 1 || head->num_levels > YPB_MAX_LEVELS) return fail(YPB_ERR_INVALID_ARGUMENT, "num_levels=%d invalid", head->num_levels);
+  if (!dtype_ok(head->dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", head->dtype);
+  if (head->batch < 0 || channels < 1 || kpt_ndim < 2 || channels % kpt_ndim)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d channels=%d ndim=%d invalid", head->batch, channels, kpt_ndim);
+  if (head->batch == 0) return YPB_OK;
+  if (!kpts || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "kpts / out is NULL");
+  const int wide = 16 / static_cast<int>(dtype_size(head->dtype));
+  int vec = wide;
+  ypb::KptArgs a{};
+  a.src = kpts; a.dst = out; a.sb = stride_b; a.sc = stride_c; a.batch = head->batch; a.channels = channels; a.ndim = kpt_ndim;
+  a.num_levels = head->num_levels;
+  int as = 0;
+  for (int l = 0; l < head->num_levels; ++l) {
+    if (head->level_h[l] < 1 || head->level_w[l] < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "level %d has empty grid", l);
+    if ((head->level_h[l] * head->level_w[l]) % wide) vec = 1;
+    a.w[l] = head->level_w[l]; a.stride[l] = head->level_stride[l]; a.anchor_start[l] = as;
+    as += head->level_h[l] * head->level_w[l];
+  }
+  a.anchors = as;
+  if (stride_c < as) return fail(YPB_ERR_INVALID_ARGUMENT, "kpts channel stride < anchors");
+  if (stride_b % wide || stride_c % wide || !aligned(kpts, 16) || !aligned(out, 16) || as % wide) vec = 1;
+  int gs = 0;
+  for (int l = 0; l < head->num_levels; ++l) { a.group_start[l] = gs; gs += head->level_h[l] * head->level_w[l] / vec; }
+  for (int l = head->num_levels; l <= YPB_MAX_LEVELS; ++l) { a.anchor_start[l] = as; a.group_start[l] = gs; }
+  cudaError_t e = ypb::launch_kpts_decode(a, head->dtype, vec, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_kpts_decode");
   return YPB_OK;
 }
 

@@ -243,6 +243,28 @@ __device__ __forceinline__ void scale_box(float& x0, float& y0, float& x1, float
   }
 }
 
+// Pose.kpts_decode (head.py:1254-1273), one value: channel e of the (nk*ndim) keypoint block, d = e % ndim.
+// x/y: (v*2 + (anchor - 0.5)) * stride, visibility (ndim == 3): sigmoid.  Every torch op rounds to the tensor dtype T.
+// ax, ay = the anchor centre as cached in dtype T (head.py:163: arange(w, dtype=T) + 0.5).
+template <int DT>
+__device__ __forceinline__ float kpt_value(float v, int d, float ax, float ay, float stride) {
+  using D = DType<DT>;
+  if (d == 2) return D::rnd(sigmoid_f(v));
+  if (d > 2) return v;
+  const float a = D::rnd(__fsub_rn(d == 0 ? ax : ay, 0.5f));
+  float t = D::rnd(__fmul_rn(v, 2.0f));
+  t = D::rnd(__fadd_rn(t, a));
+  return D::rnd(__fmul_rn(t, stride));
+}
+
+// scale_coords (ops.py:562-595) on one coordinate of a keypoint: d = 0 -> x, 1 -> y, else untouched.
+__device__ __forceinline__ float scale_coord(float v, int d, const ypb_scale_xform& xf, bool padding) {
+  if (d > 1) return v;
+  if (padding) v = __fsub_rn(v, d == 0 ? xf.cpad_x : xf.cpad_y);
+  v = __fdiv_rn(v, xf.gain);
+  return torch_clamp(v, 0.f, d == 0 ? xf.img_w : xf.img_h);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // sort keys: 64-bit, unique per image.  hi = ~orderable(score), lo = row id ((anchor << cls_bits) | cls), so an ascending
 // sort is "score descending, then lower row first" == torchvision's stable descending sort (Ties).
@@ -372,6 +394,13 @@ struct SuppressArgs {
   int32_t* out_count;
   int32_t* out_cand;
   int idx_as_row;  // ypb_nms_boxes: write the row id itself
+  // riders of the fused path (ypb_riders_desc): per-anchor channels that follow the kept rows as extras
+  const void* rider;
+  int rider_dtype, rider_kind, rider_ndim;
+  long long rider_sb, rider_sc;
+  int lv_n;                                 // anchor index -> level / grid cell (keypoint riders)
+  int lv_start[YPB_MAX_LEVELS + 1], lv_w[YPB_MAX_LEVELS];
+  float lv_stride[YPB_MAX_LEVELS];
   // optional fused construct_result rescale of the kept rows (ypb_nms_out.scale_*)
   const ypb_scale_xform* scale_xforms;
   int scale_padding;
@@ -392,6 +421,17 @@ struct ScaleArgs {  // ypb_scale_rows: see include/yolopost_b200.h
   int nk, ndim;
 };
 cudaError_t launch_scale_rows(const ScaleArgs& s, cudaStream_t st);
+
+struct KptArgs {  // ypb_kpts_decode
+  const void* src;
+  void* dst;
+  long long sb, sc;
+  int batch, channels, ndim, anchors, num_levels;
+  int w[YPB_MAX_LEVELS];
+  float stride[YPB_MAX_LEVELS];
+  int anchor_start[YPB_MAX_LEVELS + 1], group_start[YPB_MAX_LEVELS + 1];
+};
+cudaError_t launch_kpts_decode(const KptArgs& a, int dtype, int vec, cudaStream_t st);
 
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,

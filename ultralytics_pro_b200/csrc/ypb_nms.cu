@@ -902,6 +902,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       } else if (a.extra == 1 && cand_ang3) {
         o[6] = cand_ang3[anchor];
       }
+      // (riders of the fused path are gathered below, one (row, channel) pair per thread)
       if (a.scale_xforms) {
         // detect/predict.py:120 (scale_boxes) or obb/predict.py:59-60 (regularize_rboxes + scale_boxes(xywh=True)),
         // fused into the gather: the angle is the row's last column (nms.py:146)
@@ -912,6 +913,32 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
           scale_box(bx.x, bx.y, bx.z, bx.w, nullptr, xf, YPB_BOXES_XYXY, a.scale_padding);
       }
       o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    }
+  }
+  if (a.rider && a.out_rows) {
+    // Segment / Pose riders (head.py:837 mask coefficients, head.py:1252 decoded keypoints): only the kept anchors'
+    // values are ever read.  Keypoints are decoded here (head.py:1254-1273) and, when the gather rescales to the original
+    // image, scaled like pose/predict.py:73-75 (scale_coords).
+    const int total = kept_n * a.extra;
+    for (int t = tid; t < total; t += NT) {
+      const int k = t / a.extra, e = t - k * a.extra;
+      const uint32_t anchor = key_row(kk[k]) >> cbits;
+      float v = load_pred(a.rider, a.rider_dtype, static_cast<long long>(b) * a.rider_sb + static_cast<long long>(e) * a.rider_sc + anchor);
+      if (a.rider_kind == YPB_RIDER_KEYPOINTS) {
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+          if (i < a.lv_n && static_cast<int>(anchor) >= a.lv_start[i]) l = i;
+        const int loc = static_cast<int>(anchor) - a.lv_start[l];
+        const int gy = loc / a.lv_w[l], gx = loc - gy * a.lv_w[l];
+        const int d = e % a.rider_ndim;
+        const float fx = static_cast<float>(gx) + 0.5f, fy = static_cast<float>(gy) + 0.5f;
+        if (a.rider_dtype == YPB_F32) v = kpt_value<YPB_F32>(v, d, fx, fy, a.lv_stride[l]);
+        else if (a.rider_dtype == YPB_F16) v = kpt_value<YPB_F16>(v, d, DType<YPB_F16>::rnd(fx), DType<YPB_F16>::rnd(fy), a.lv_stride[l]);
+        else v = kpt_value<YPB_BF16>(v, d, DType<YPB_BF16>::rnd(fx), DType<YPB_BF16>::rnd(fy), a.lv_stride[l]);
+        if (a.scale_xforms) v = scale_coord(v, d, a.scale_xforms[b], a.scale_padding);
+      }
+      a.out_rows[(static_cast<long long>(b) * a.max_det + k) * cols + 6 + e] = v;
     }
   }
   __syncthreads();

@@ -43,7 +43,50 @@ scale_rows_kernel(const ScaleArgs s) {
   }
 }
 
+// Pose.kpts_decode (head.py:1254-1273) over the whole (B, nk*ndim, A) tensor: thread = VEC consecutive anchors of one
+// channel, 128-bit streaming loads/stores; HBM-bound (2 * B * C * A * s bytes).
+template <int DT, int VEC>
+__global__ void __launch_bounds__(256)
+kpts_decode_kernel(const __grid_constant__ KptArgs a) {
+  using T = typename DType<DT>::type;
+  const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp >= a.group_start[a.num_levels]) return;
+  const int c = blockIdx.y, b = blockIdx.z;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+    if (i < a.num_levels && grp >= a.group_start[i]) l = i;
+  const int a_local = (grp - a.group_start[l]) * VEC;
+  const int a_glob = a.anchor_start[l] + a_local;
+  const T* src = static_cast<const T*>(a.src) + static_cast<long long>(b) * a.sb + static_cast<long long>(c) * a.sc + a_glob;
+  T* dst = static_cast<T*>(a.dst) + (static_cast<long long>(b) * a.channels + c) * a.anchors + a_glob;
+  const int d = c % a.ndim;
+  const int W = a.w[l];
+  const float stride = a.stride[l];
+  int gy = a_local / W, gx = a_local - gy * W;
+  Pack<T, VEC> p = load_pack<T, VEC>(src), q;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float ax = DType<DT>::rnd(static_cast<float>(gx) + 0.5f), ay = DType<DT>::rnd(static_cast<float>(gy) + 0.5f);
+    q.v[i] = DType<DT>::from_f(kpt_value<DT>(DType<DT>::to_f(p.v[i]), d, ax, ay, stride));
+    if (++gx == W) { gx = 0; ++gy; }
+  }
+  store_pack<T, VEC>(dst, q);
+}
+
 }  // namespace
+
+cudaError_t launch_kpts_decode(const KptArgs& a, int dtype, int vec, cudaStream_t st) {
+  const int groups = a.group_start[a.num_levels];
+  if (groups <= 0 || a.batch <= 0 || a.channels <= 0) return cudaSuccess;
+  dim3 grid((groups + 255) / 256, a.channels, a.batch);
+#define YPB_KPT(DT, V) kpts_decode_kernel<DT, V><<<grid, 256, 0, st>>>(a)
+  if (dtype == YPB_F32) { if (vec == 4) YPB_KPT(YPB_F32, 4); else YPB_KPT(YPB_F32, 1); }
+  else if (dtype == YPB_F16) { if (vec == 8) YPB_KPT(YPB_F16, 8); else YPB_KPT(YPB_F16, 1); }
+  else { if (vec == 8) YPB_KPT(YPB_BF16, 8); else YPB_KPT(YPB_BF16, 1); }
+#undef YPB_KPT
+  return cudaGetLastError();
+}
 
 cudaError_t launch_scale_rows(const ScaleArgs& s, cudaStream_t st) {
   const long long n = static_cast<long long>(s.batch) * s.rows_per_image;

@@ -175,6 +175,37 @@ def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:
     _cabi.check(rc, "ypb_nms_from_dense")
 
 
+def geometry_desc(level_hw, strides, batch: int, dtype):
+    """ypb_head_desc carrying only the level geometry (no tensors): for calls that need anchors -> grid cells."""
+    d = _cabi.HeadDesc()
+    d.num_levels, d.batch, d.nc, d.reg_max, d.dtype = len(level_hw), batch, 1, 16, _cabi.dtype_code(dtype)
+    for i, ((h, w), s) in enumerate(zip(level_hw, strides)):
+        d.level_h[i], d.level_w[i], d.level_stride[i] = int(h), int(w), float(s)
+    return d
+
+
+def riders_desc(t: torch.Tensor, batch: int, anchors: int, dtype, kind: int, kpt_ndim: int = 0):
+    """ypb_riders_desc for a (B, E, A) tensor of per-anchor channels (mask coefficients / raw keypoints)."""
+    _cabi.require_cuda(t, "riders")
+    if t.dim() != 3 or t.shape[0] != batch or t.shape[2] != anchors:
+        raise ValueError(f"riders must be (B={batch}, E, A={anchors}), got {tuple(t.shape)}")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.stride(2) != 1:
+        t = t.contiguous()
+    r = _cabi.RidersDesc()
+    r.ptr, r.channels, r.kind, r.kpt_ndim = t.data_ptr(), t.shape[1], kind, kpt_ndim
+    r.stride_b, r.stride_c = t.stride(0), t.stride(1)
+    return r, t
+
+
+def run_from_head_riders(desc, riders, plan: NmsPlan, device) -> None:
+    lib = _cabi.load()
+    rc = lib.ypb_nms_from_head_riders(C.byref(desc), C.byref(riders), desc.dtype, C.byref(plan.params), C.byref(plan.out),
+                                      plan.scratch.data_ptr(), plan.scratch.numel(), _cabi.stream_ptr(device))
+    _cabi.check(rc, "ypb_nms_from_head_riders")
+
+
 def run_from_head(desc, angle, angle_is_logit: bool, plan: NmsPlan, device) -> None:
     lib = _cabi.load()
     rc = lib.ypb_nms_from_head(C.byref(desc), angle.data_ptr() if angle is not None else None, int(angle_is_logit),

@@ -62,6 +62,7 @@ def detect_inference(self, x: list) -> torch.Tensor:
     """``Detect._inference`` drop-in (head.py:151-169).  Reads the same module attributes, keeps caching
     ``self.anchors/self.strides/self.shape`` and returns the dense (B, 4+nc, A) tensor in the input dtype."""
     shape = x[0].shape  # BCHW
+    self._ypb_level_hw = [(int(lv.shape[2]), int(lv.shape[3])) for lv in x]  # read by pose_kpts_decode
     if self.dynamic or self.shape != shape:
         self.anchors, self.strides = _anchor_cache(x, self.stride, x[0].dtype, x[0].device)
         self.shape = shape
@@ -70,11 +71,45 @@ def detect_inference(self, x: list) -> torch.Tensor:
                        append_angle=False, xyxy=bool(self.end2end or self.xyxy))
 
 
+def decode_keypoints(kpts: torch.Tensor, level_hw, strides, kpt_shape) -> torch.Tensor:
+    """``Pose.kpts_decode`` (head.py:1254-1273, non-export branch) on raw (B, nk*ndim, A) keypoint logits:
+    x,y -> (v*2 + (anchor - 0.5)) * stride, visibility -> sigmoid.  Returns a new tensor of the same shape and dtype."""
+    _cabi.require_cuda(kpts, "decode_keypoints")
+    b, ch, a = kpts.shape
+    nk, ndim = int(kpt_shape[0]), int(kpt_shape[1])
+    if ch != nk * ndim or a != sum(int(h) * int(w) for h, w in level_hw):
+        raise ValueError(f"kpts {tuple(kpts.shape)} inconsistent with kpt_shape {tuple(kpt_shape)} / levels {list(level_hw)}")
+    if kpts.stride(2) != 1:
+        kpts = kpts.contiguous()
+    out = torch.empty((b, ch, a), dtype=kpts.dtype, device=kpts.device)
+    desc = engine.geometry_desc(level_hw, strides, b, kpts.dtype)
+    rc = _cabi.load().ypb_kpts_decode(C.byref(desc), kpts.data_ptr(), kpts.stride(0), kpts.stride(1), ch, ndim,
+                                      out.data_ptr(), _cabi.stream_ptr(kpts.device))
+    _cabi.check(rc, "ypb_kpts_decode")
+    return out
+
+
+def pose_kpts_decode(self, bs: int, kpts: torch.Tensor) -> torch.Tensor:
+    """``Pose.kpts_decode`` drop-in (head.py:1254; identical copies :1322, :1390, :1459).  The level grid sizes come from
+    the level list seen by ``detect_inference`` (``Pose.forward`` runs ``Detect.forward`` first, head.py:1249-1252)."""
+    hw = getattr(self, "_ypb_level_hw", None)
+    if hw is None or sum(h * w for h, w in hw) != kpts.shape[-1]:
+        # _inference ran through the reference (not patched): recover the grids from the cached stride row (head.py:163-165)
+        srow = self.strides.view(-1)
+        hw = []
+        for s in self.stride:
+            sel = srow == float(s)
+            w = int(self.anchors[0, sel].max().item() + 0.5)
+            hw.append((int(sel.sum()) // w, w))
+    return decode_keypoints(kpts.view(bs, self.nk, -1), hw, [float(s) for s in self.stride], self.kpt_shape)
+
+
 def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                           agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                           max_wh: int = 7680, reg_max: int = 16, angle_logits: torch.Tensor | None = None,
                           return_idxs: bool = False, sync: bool = True, img_shape=None, orig_shapes=None,
-                          ratio_pads=None):
+                          ratio_pads=None, mask_coeffs: torch.Tensor | None = None,
+                          kpt_logits: torch.Tensor | None = None, kpt_shape=None):
     """Fused ``Detect._inference`` + ``non_max_suppression`` (head.py:151-169 then nms.py:13-166).
 
     Bit-identical to ``non_max_suppression(decode_head(levels, ...), ...)`` but reads the head once and never writes
@@ -97,14 +132,28 @@ def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, io
         angle_logits = angle_logits.to(lv0.dtype).reshape(b, anchors).contiguous()
     else:
         rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(iou_thres)
-    plan = engine.make_plan(lv0.device, b, anchors, nc, 1 if rotated else 0, conf_t, iou_eff, max_det, max_nms,
+    riders = None
+    if mask_coeffs is not None or kpt_logits is not None:
+        if rotated or (mask_coeffs is not None and kpt_logits is not None):
+            raise ValueError("one rider at a time, and none with the rotated path")
+        if kpt_logits is not None:
+            if kpt_shape is None:
+                raise ValueError("kpt_logits needs kpt_shape")
+            riders, rider_keep = engine.riders_desc(kpt_logits.reshape(b, -1, anchors), b, anchors, lv0.dtype,
+                                                    _cabi.RIDER_KEYPOINTS, int(kpt_shape[1]))
+        else:
+            riders, rider_keep = engine.riders_desc(mask_coeffs, b, anchors, lv0.dtype, _cabi.RIDER_RAW)
+    extra = riders.channels if riders is not None else (1 if rotated else 0)
+    plan = engine.make_plan(lv0.device, b, anchors, nc, extra, conf_t, iou_eff, max_det, max_nms,
                             0.0 if agnostic else float(max_wh), multi_label, rule, classes,
                             with_scale=orig_shapes is not None)
     if orig_shapes is not None and b:
         if img_shape is None:
             img_shape = (lv0.shape[2] * int(strides[0]), lv0.shape[3] * int(strides[0]))
         engine.set_transforms(plan, img_shape, orig_shapes, ratio_pads)
-    if b:
+    if b and riders is not None:
+        engine.run_from_head_riders(desc, riders, plan, lv0.device)
+    elif b:
         engine.run_from_head(desc, angle_logits, True, plan, lv0.device)
     else:
         plan.count.zero_()

@@ -27,6 +27,7 @@ import sys
 _saved: dict = {}
 
 _HEAD_CLASSES = ("Detect", "MAFDetect", "IDetect", "DDetect")
+_POSE_CLASSES = ("Pose", "MAFPose", "IPose", "DPose")
 
 
 def _wrap_nms(ref_fn, ours):
@@ -49,6 +50,16 @@ def _wrap_inference(ref_fn, ours):
 
     _inference.__wrapped__ = ref_fn
     return _inference
+
+
+def _wrap_kpts(ref_fn, ours):
+    def kpts_decode(self, bs, kpts):
+        if kpts.is_cuda and not getattr(self, "export", False):
+            return ours(self, bs, kpts)
+        return ref_fn(self, bs, kpts)
+
+    kpts_decode.__wrapped__ = ref_fn
+    return kpts_decode
 
 
 def _wrap_static(ref_fn, ours):
@@ -127,6 +138,13 @@ def install() -> list:
             _saved[f"ultralytics.nn.modules.head.{cname}._inference"] = (c, "_inference", c.__dict__["_inference"])
             c._inference = _wrap_inference(c.__dict__["_inference"], our_head.detect_inference)
             done.append(f"ultralytics.nn.modules.head.{cname}._inference")
+        for cname in _POSE_CLASSES:  # head.py:1254, :1322, :1390, :1459
+            c = getattr(ref_head, cname, None)
+            if c is None or "kpts_decode" not in c.__dict__:
+                continue
+            _saved[f"ultralytics.nn.modules.head.{cname}.kpts_decode"] = (c, "kpts_decode", c.__dict__["kpts_decode"])
+            c.kpts_decode = _wrap_kpts(c.__dict__["kpts_decode"], our_head.pose_kpts_decode)
+            done.append(f"ultralytics.nn.modules.head.{cname}.kpts_decode")
     return done
 
 
