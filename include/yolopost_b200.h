@@ -182,6 +182,31 @@ YPB_API int ypb_nms_from_head_riders(const ypb_head_desc* head, const ypb_riders
 YPB_API int ypb_kpts_decode(const ypb_head_desc* head, const void* kpts, int64_t stride_b, int64_t stride_c,
                             int32_t channels, int32_t kpt_ndim, void* out, void* stream);
 
+/* process_mask / process_mask_native (utils/ops.py:489-541), batched over the kept rows of a batch.
+ *   protos        : (B, C, mh, mw) prototype masks of the Segment head (head.py:830), fp32/fp16/bf16, pixels contiguous
+ *   coeffs, boxes : per detection C mask coefficients (columns 6.. of the NMS rows) and the xyxy box (columns 0..3), fp32;
+ *                   detection r of image b at ptr + b*image_stride + r*row_stride (elements)
+ *   offsets       : device (B+1) int32 exclusive prefix of the per-image detection counts, or NULL when batch == 1
+ *   total         : detections in the batch (== offsets[B]); out is (total, out_h, out_w) uint8, packed in image order
+ *   window        : rows [win_top, win_top+win_h) x cols [win_left, win_left+win_w) of the prototype grid are resized to
+ *                   (out_h, out_w) - the whole grid for process_mask, the un-padded part for scale_masks (ops.py:544-559)
+ *   crop_mode     : YPB_MASK_CROP_PROTO  = crop at prototype resolution with boxes*(ratio_w, ratio_h) BEFORE resizing
+ *                                          (process_mask, ops.py:505-510; out == (mh, mw) gives upsample=False)
+ *                   YPB_MASK_CROP_OUTPUT = crop at output resolution with the boxes as given, AFTER resizing
+ *                                          (process_mask_native, ops.py:538-540) */
+typedef enum { YPB_MASK_CROP_PROTO = 1, YPB_MASK_CROP_OUTPUT = 2 } ypb_mask_crop;
+typedef struct {
+  const void* ptr;
+  int32_t dtype;
+  int32_t channels, mh, mw;
+  int64_t stride_b, stride_c; /* elements */
+} ypb_protos_desc;
+YPB_API int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t coef_image_stride,
+                             int64_t coef_row_stride, const float* boxes, int64_t box_image_stride, int64_t box_row_stride,
+                             const int32_t* offsets, int32_t batch, int32_t total, int32_t out_h, int32_t out_w,
+                             int32_t win_top, int32_t win_left, int32_t win_h, int32_t win_w, int32_t crop_mode,
+                             float ratio_w, float ratio_h, uint8_t* out, void* stream);
+
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
  * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);

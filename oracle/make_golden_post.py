@@ -96,6 +96,53 @@ def main():
     np.savez_compressed(OUT, **blob)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
     make_kpts(ref)
+    make_masks(ref)
+
+
+def make_masks(ref):
+    """process_mask / process_mask_native (ops.py:489-541) of the live reference; n >= 50 so that the CPU run takes the
+    same crop_mask branch as CUDA tensors do (ops.py:482-486)."""
+    out_path = os.path.join(ROOT, "tests", "golden", "post", "masks.npz")
+    ops = ref.ops
+    g = torch.Generator().manual_seed(4242)
+    blob, meta = {}, []
+    for name, (mh, mw), shape, n, kind, dtype in [
+        ("up_4x", (40, 40), (160, 160), 56, "process_mask_up", torch.float32),
+        ("low_res", (40, 40), (160, 160), 56, "process_mask", torch.float32),
+        ("up_rect_f16", (24, 40), (96, 160), 50, "process_mask_up", torch.float16),
+        ("native_letterbox", (40, 40), (120, 213), 52, "process_mask_native", torch.float32),
+        ("native_tall", (40, 40), (333, 250), 50, "process_mask_native", torch.float32),
+    ]:
+        # smooth prototypes (sums of a few low-frequency waves) so that masks look like blobs, plus noise
+        yy, xx = torch.meshgrid(torch.linspace(0, 1, mh), torch.linspace(0, 1, mw), indexing="ij")
+        protos = torch.stack([torch.sin(6.28 * (torch.rand(1, generator=g) * 3 * xx + torch.rand(1, generator=g) * 3 * yy
+                                                + torch.rand(1, generator=g))) for _ in range(32)])
+        protos = (protos + 0.05 * torch.randn(32, mh, mw, generator=g)).to(dtype)
+        coef = torch.randn(n, 32, generator=g)
+        H, W = (mh * 4, mw * 4) if kind != "process_mask_native" else shape
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.8, H * 0.8])
+        wh = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.5, H * 0.5]) + 2
+        boxes = torch.cat([xy, xy + wh], 1)
+        boxes[0] = torch.tensor([0.0, 0.0, float(W), float(H)])
+        boxes[1] = torch.tensor([8.0, 12.0, 8.0, 40.0])       # empty in x
+        boxes[2] = torch.tensor([-30.0, -30.0, W + 30.0, 16.0])
+        boxes[3] = torch.tensor([10.5, 10.5, 11.5, 11.5])     # inside one prototype cell
+        if kind == "process_mask_up":
+            out = ops.process_mask(protos, coef.clone(), boxes.clone(), shape, upsample=True)
+        elif kind == "process_mask":
+            out = ops.process_mask(protos, coef.clone(), boxes.clone(), shape, upsample=False)
+        else:
+            out = ops.process_mask_native(protos, coef.clone(), boxes.clone(), shape)
+        i = len(meta)
+        blob[f"m{i}_protos"] = protos.float().numpy()
+        blob[f"m{i}_coef"] = coef.numpy()
+        blob[f"m{i}_boxes"] = boxes.numpy()
+        blob[f"m{i}_out"] = np.packbits(out.numpy().astype(bool))
+        meta.append(dict(name=name, kind=kind, shape=list(shape), out_shape=list(out.shape), dtype=str(dtype).split(".")[1]))
+        print(name, tuple(out.shape), int(out.sum()))
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
 
 def make_kpts(ref):

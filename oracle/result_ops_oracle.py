@@ -126,3 +126,54 @@ def kpts_decode_oracle(kpts, level_hw, strides, kpt_shape):
     for d in range(len(parts), ndim):
         parts.append(y[:, :, d])
     return torch.stack(parts, 2).reshape(b, nk * ndim, a)
+
+
+def crop_mask_oracle(masks, boxes):
+    """utils/ops.py:464-486, the comparison branch (taken for CUDA tensors and for n >= 50): pixel (row c, col r) survives
+    iff x1 <= r < x2 and y1 <= c < y2.  (For n < 50 on the CPU the reference instead slices at ``boxes.round().int()``,
+    ops.py:476-481 - a different rounding that the CUDA path of the reference never takes.)"""
+    import torch
+
+    n, h, w = masks.shape
+    x1, y1, x2, y2 = (boxes[:, i].reshape(n, 1, 1) for i in range(4))
+    cols = torch.arange(w, dtype=boxes.dtype).reshape(1, 1, w)
+    rows = torch.arange(h, dtype=boxes.dtype).reshape(1, h, 1)
+    inside = (cols >= x1) & (cols < x2) & (rows >= y1) & (rows < y2)
+    return masks * inside
+
+
+def process_mask_oracle(protos, masks_in, bboxes, shape, upsample=False):
+    """utils/ops.py:489-513.  Returns (uint8 masks, the float values that were thresholded)."""
+    import torch
+    import torch.nn.functional as F
+
+    c, mh, mw = protos.shape
+    low = (masks_in @ protos.float().reshape(c, mh * mw)).reshape(-1, mh, mw)
+    rw, rh = mw / shape[1], mh / shape[0]
+    low = crop_mask_oracle(low, bboxes * torch.tensor([[rw, rh, rw, rh]]))
+    if upsample:
+        low = F.interpolate(low[None], tuple(shape), mode="bilinear")[0]
+    return (low > 0).to(torch.uint8), low
+
+
+def scale_masks_window(mh, mw, shape, padding=True):
+    """utils/ops.py:544-559: the un-padded window of the mask grid."""
+    gain = min(mh / shape[0], mw / shape[1])
+    pad_w, pad_h = mw - shape[1] * gain, mh - shape[0] * gain
+    if padding:
+        pad_w, pad_h = pad_w / 2, pad_h / 2
+    top, left = (round(pad_h - 0.1), round(pad_w - 0.1)) if padding else (0, 0)
+    return top, left, mh - round(pad_h + 0.1), mw - round(pad_w + 0.1)
+
+
+def process_mask_native_oracle(protos, masks_in, bboxes, shape):
+    """utils/ops.py:516-541."""
+    import torch
+    import torch.nn.functional as F
+
+    c, mh, mw = protos.shape
+    low = (masks_in @ protos.float().reshape(c, mh * mw)).reshape(-1, mh, mw)
+    top, left, bottom, right = scale_masks_window(mh, mw, shape)
+    up = F.interpolate(low[None, :, top:bottom, left:right], tuple(shape), mode="bilinear")[0]
+    up = crop_mask_oracle(up, bboxes)
+    return (up > 0).to(torch.uint8), up

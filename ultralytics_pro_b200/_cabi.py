@@ -35,7 +35,9 @@ EXPORTS = (
     "ypb_scale_rows",
     "ypb_nms_from_head_riders",
     "ypb_kpts_decode",
+    "ypb_process_mask",
 )
+MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
 
 BOXES_NONE, BOXES_XYXY, BOXES_XYWH, BOXES_XYWHR, BOXES_CLIP_ONLY, BOXES_REGULARIZE_ONLY = range(6)
@@ -112,6 +114,18 @@ class RidersDesc(C.Structure):
     ]
 
 
+class ProtosDesc(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("dtype", C.c_int32),
+        ("channels", C.c_int32),
+        ("mh", C.c_int32),
+        ("mw", C.c_int32),
+        ("stride_b", C.c_int64),
+        ("stride_c", C.c_int64),
+    ]
+
+
 class ScaleXform(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("gain", "pad_x", "pad_y", "img_w", "img_h", "cpad_x", "cpad_y", "reserved")]
 
@@ -169,6 +183,11 @@ def load():
     lib.ypb_kpts_decode.restype = C.c_int
     lib.ypb_kpts_decode.argtypes = [C.POINTER(HeadDesc), C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p]
+    lib.ypb_process_mask.restype = C.c_int
+    lib.ypb_process_mask.argtypes = [C.POINTER(ProtosDesc), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p,
+                                     C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -365,6 +365,40 @@ int ypb_scale_rows(float* rows, int64_t image_stride, int64_t row_stride, int32_
   return YPB_OK;
 }
 
+int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t coef_image_stride, int64_t coef_row_stride,
+                     const float* boxes, int64_t box_image_stride, int64_t box_row_stride, const int32_t* offsets,
+                     int32_t batch, int32_t total, int32_t out_h, int32_t out_w, int32_t win_top, int32_t win_left,
+                     int32_t win_h, int32_t win_w, int32_t crop_mode, float ratio_w, float ratio_h, uint8_t* out,
+                     void* stream) {
+  if (!protos) return fail(YPB_ERR_INVALID_ARGUMENT, "protos descriptor is NULL");
+  if (!dtype_ok(protos->dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", protos->dtype);
+  if (protos->channels < 1 || protos->mh < 1 || protos->mw < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "empty prototypes");
+  if (batch < 1 || total < 0 || out_h < 1 || out_w < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d total=%d out=%dx%d invalid", batch, total, out_h, out_w);
+  if (batch > 1 && !offsets) return fail(YPB_ERR_INVALID_ARGUMENT, "offsets is NULL for a batch of %d", batch);
+  if (crop_mode != YPB_MASK_CROP_PROTO && crop_mode != YPB_MASK_CROP_OUTPUT) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown crop mode %d", crop_mode);
+  if (win_top < 0 || win_left < 0 || win_h < 1 || win_w < 1 || win_top + win_h > protos->mh || win_left + win_w > protos->mw)
+    return fail(YPB_ERR_INVALID_ARGUMENT, "window (%d,%d,%d,%d) outside the %dx%d prototype grid", win_top, win_left, win_h, win_w, protos->mh, protos->mw);
+  if (protos->stride_c < static_cast<int64_t>(protos->mh) * protos->mw) return fail(YPB_ERR_INVALID_ARGUMENT, "prototype channel stride < mh*mw");
+  if (total == 0) return YPB_OK;
+  if (!protos->ptr || !coeffs || !boxes || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "protos / coeffs / boxes / out is NULL");
+  if (total > 65535) return fail(YPB_ERR_UNSUPPORTED, "more than 65535 detections in one call (split the batch)");
+  ypb::MaskArgs a{};
+  a.protos = protos->ptr; a.proto_dtype = protos->dtype; a.proto_sb = protos->stride_b; a.proto_sc = protos->stride_c;
+  a.C = protos->channels; a.mh = protos->mh; a.mw = protos->mw;
+  a.coeffs = coeffs; a.coef_image_stride = coef_image_stride; a.coef_row_stride = coef_row_stride;
+  a.boxes = boxes; a.box_image_stride = box_image_stride; a.box_row_stride = box_row_stride;
+  a.offsets = batch > 1 ? offsets : nullptr; a.batch = batch; a.total = total;
+  a.ih = out_h; a.iw = out_w; a.win_top = win_top; a.win_left = win_left; a.win_h = win_h; a.win_w = win_w;
+  // ATen area_pixel_compute_scale<float>: static_cast<float>(input_size) / output_size
+  a.scale_h = static_cast<float>(win_h) / static_cast<float>(out_h);
+  a.scale_w = static_cast<float>(win_w) / static_cast<float>(out_w);
+  a.ratio_w = ratio_w; a.ratio_h = ratio_h; a.crop_mode = crop_mode; a.out = out;
+  cudaError_t e = ypb::launch_process_mask(a, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidConfiguration) return fail(YPB_ERR_UNSUPPORTED, "resize ratio %dx%d -> %dx%d needs too large a shared-memory footprint", win_h, win_w, out_h, out_w);
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_process_mask");
+  return YPB_OK;
+}
+
 void ypb_debug_set_phase_buffer(void* device_buffer) { ypb::set_phase_buffer(static_cast<long long*>(device_buffer)); }
 
 int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream) {

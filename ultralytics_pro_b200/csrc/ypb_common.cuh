@@ -433,6 +433,25 @@ struct KptArgs {  // ypb_kpts_decode
 };
 cudaError_t launch_kpts_decode(const KptArgs& a, int dtype, int vec, cudaStream_t st);
 
+struct MaskArgs {  // ypb_process_mask
+  const void* protos;
+  int proto_dtype;
+  long long proto_sb, proto_sc;  // elements; rows of mw contiguous pixels
+  int C, mh, mw;
+  const float* coeffs;
+  long long coef_image_stride, coef_row_stride;
+  const float* boxes;
+  long long box_image_stride, box_row_stride;
+  const int32_t* offsets;  // device (B+1) exclusive prefix of the per-image detection counts, or null (one image)
+  int batch, total;
+  int ih, iw;
+  int win_top, win_left, win_h, win_w;
+  float scale_h, scale_w, ratio_w, ratio_h;
+  int crop_mode;
+  uint8_t* out;
+};
+cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st);
+
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
                                 int vec, cudaStream_t st);

@@ -74,7 +74,167 @@ kpts_decode_kernel(const __grid_constant__ KptArgs a) {
   store_pack<T, VEC>(dst, q);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// process_mask / process_mask_native (utils/ops.py:489-541): per kept detection, mask = coeffs . protos (32-term dot
+// product per prototype pixel), cropped to the box, bilinearly resized (F.interpolate, align_corners=False) and
+// thresholded at 0 -> uint8.  One CTA = one detection x one output tile of MT_W x MT_H pixels:
+//   1. the prototype-resolution values the tile's bilinear taps touch (<= (MT_H/scale+2) x (MT_W/scale+2)) are computed into
+//      shared memory straight from the (L2-resident) prototypes - the (n, mh, mw) fp32 intermediate of the reference is
+//      never written;
+//   2. every thread resizes + thresholds 16 consecutive pixels of one row and stores them with one 128-bit store.
+// Tiles that cannot see the box are zero-filled without touching the prototypes.  The kernel is bound by the HBM write
+// of the (n, H, W) uint8 result: algorithmic bytes = n*H*W.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MT_W = 128, MT_H = 32, MT_THREADS = 256;
+
+// ATen UpSampleKernel / UpSample.h area_pixel_compute_source_index (align_corners=False) + guard_index_and_lambda
+__device__ __forceinline__ void bilinear_tap(float scale, int dst, int in_size, int& i0, int& i1, float& w0, float& w1) {
+  float src = __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f);
+  if (src < 0.f) src = 0.f;
+  i0 = min(static_cast<int>(floorf(src)), in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  w1 = fminf(fmaxf(__fsub_rn(src, static_cast<float>(i0)), 0.f), 1.f);
+  w0 = __fsub_rn(1.f, w1);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(MT_THREADS)
+process_mask_kernel(const __grid_constant__ MaskArgs a) {
+  using T = typename DType<DT>::type;
+  extern __shared__ __align__(16) float sm_f[];
+  float* coef = sm_f;                 // [C]
+  float* reg = sm_f + ((a.C + 3) & ~3);  // [rh][rw] prototype-resolution values of this tile's footprint
+  __shared__ int s_img[2];
+  const int tid = threadIdx.x;
+  const int d = blockIdx.z;
+  const int X0 = blockIdx.x * MT_W, Y0 = blockIdx.y * MT_H;
+  const int X1 = min(X0 + MT_W, a.iw) - 1, Y1 = min(Y0 + MT_H, a.ih) - 1;  // inclusive
+
+  // detection -> (image, row)
+  int b = 0, k = d;
+  if (a.offsets) {
+    if (tid == 0) {
+      int lo = 0, hi = a.batch;  // offsets[lo] <= d < offsets[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.offsets[mid] <= d) lo = mid; else hi = mid; }
+      s_img[0] = lo; s_img[1] = d - a.offsets[lo];
+    }
+    __syncthreads();
+    b = s_img[0]; k = s_img[1];
+  }
+  const float* bp = a.boxes + static_cast<long long>(b) * a.box_image_stride + static_cast<long long>(k) * a.box_row_stride;
+  float bx1 = bp[0], by1 = bp[1], bx2 = bp[2], by2 = bp[3];
+  if (a.crop_mode == YPB_MASK_CROP_PROTO) {  // ops.py:505-510: boxes * (mw/W, mh/H, mw/W, mh/H)
+    bx1 = __fmul_rn(bx1, a.ratio_w); by1 = __fmul_rn(by1, a.ratio_h); bx2 = __fmul_rn(bx2, a.ratio_w); by2 = __fmul_rn(by2, a.ratio_h);
+  }
+
+  // footprint of the tile in the (windowed) prototype grid
+  int ry0, ry1, rx0, rx1, t0, t1;
+  float f0, f1;
+  bilinear_tap(a.scale_h, Y0, a.win_h, ry0, t1, f0, f1);
+  bilinear_tap(a.scale_h, Y1, a.win_h, t0, ry1, f0, f1);
+  bilinear_tap(a.scale_w, X0, a.win_w, rx0, t1, f0, f1);
+  bilinear_tap(a.scale_w, X1, a.win_w, t0, rx1, f0, f1);
+  const int rh = ry1 - ry0 + 1, rw = rx1 - rx0 + 1;
+
+  // can the tile see the box at all?  (crop_mask keeps column r iff x1 <= r < x2, row c iff y1 <= c < y2, ops.py:464-486)
+  bool empty;
+  if (a.crop_mode == YPB_MASK_CROP_PROTO)
+    empty = !(static_cast<float>(rx1 + a.win_left) >= bx1 && static_cast<float>(rx0 + a.win_left) < bx2 &&
+              static_cast<float>(ry1 + a.win_top) >= by1 && static_cast<float>(ry0 + a.win_top) < by2);
+  else
+    empty = !(static_cast<float>(X1) >= bx1 && static_cast<float>(X0) < bx2 && static_cast<float>(Y1) >= by1 && static_cast<float>(Y0) < by2);
+
+  uint8_t* out = a.out + static_cast<long long>(d) * a.ih * a.iw;
+  const int row = tid >> 3, seg = tid & 7;  // 32 rows x 8 segments of 16 pixels
+  const int Y = Y0 + row, XS = X0 + seg * 16;
+  const bool vec_ok = (a.iw & 15) == 0;
+
+  if (!empty) {
+    const float* cp = a.coeffs + static_cast<long long>(b) * a.coef_image_stride + static_cast<long long>(k) * a.coef_row_stride;
+    for (int c = tid; c < a.C; c += MT_THREADS) coef[c] = cp[c];
+    __syncthreads();
+    const T* pr = static_cast<const T*>(a.protos) + static_cast<long long>(b) * a.proto_sb;
+    for (int i = tid; i < rh * rw; i += MT_THREADS) {
+      const int y = i / rw, x = i - y * rw;
+      const int py = ry0 + y + a.win_top, px = rx0 + x + a.win_left;
+      const T* p = pr + static_cast<long long>(py) * a.mw + px;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < a.C; ++c) acc = fmaf(coef[c], DType<DT>::to_f(p[static_cast<long long>(c) * a.proto_sc]), acc);
+      if (a.crop_mode == YPB_MASK_CROP_PROTO) {
+        const float fx = static_cast<float>(px), fy = static_cast<float>(py);
+        const bool in = fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2;
+        acc = __fmul_rn(acc, in ? 1.f : 0.f);  // ops.py:486 masks * bool
+      }
+      reg[i] = acc;
+    }
+    __syncthreads();
+  }
+
+  if (Y > Y1 || XS > X1) return;
+  uint32_t w4[4] = {0u, 0u, 0u, 0u};
+  if (!empty) {
+    int y0, y1;
+    float wy0, wy1;
+    bilinear_tap(a.scale_h, Y, a.win_h, y0, y1, wy0, wy1);
+    const float* r0 = reg + (y0 - ry0) * rw - rx0;
+    const float* r1 = reg + (y1 - ry0) * rw - rx0;
+    const bool row_in = a.crop_mode != YPB_MASK_CROP_OUTPUT || (static_cast<float>(Y) >= by1 && static_cast<float>(Y) < by2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int X = XS + i;
+      if (X > X1) break;
+      int x0, x1;
+      float wx0, wx1;
+      bilinear_tap(a.scale_w, X, a.win_w, x0, x1, wx0, wx1);
+      // ATen upsample_bilinear2d: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)
+      const float top = __fadd_rn(__fmul_rn(wx0, r0[x0]), __fmul_rn(wx1, r0[x1]));
+      const float bot = __fadd_rn(__fmul_rn(wx0, r1[x0]), __fmul_rn(wx1, r1[x1]));
+      float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+      if (a.crop_mode == YPB_MASK_CROP_OUTPUT) {
+        const bool in = row_in && static_cast<float>(X) >= bx1 && static_cast<float>(X) < bx2;
+        v = __fmul_rn(v, in ? 1.f : 0.f);
+      }
+      if (v > 0.f) w4[i >> 2] |= 1u << ((i & 3) * 8);  // ops.py:513 masks.gt_(0.0).byte()
+    }
+  }
+  uint8_t* o = out + static_cast<long long>(Y) * a.iw + XS;
+  if (vec_ok && XS + 15 <= X1) {
+    __stcs(reinterpret_cast<uint4*>(o), make_uint4(w4[0], w4[1], w4[2], w4[3]));
+  } else {
+    for (int i = 0; i < 16 && XS + i <= X1; ++i) o[i] = static_cast<uint8_t>((w4[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
+  if (a.total <= 0 || a.ih <= 0 || a.iw <= 0) return cudaSuccess;
+  // worst-case footprint of a tile in the prototype grid
+  auto span = [](float scale, int n_out, int tile, int in) {
+    long long s = static_cast<long long>(scale * tile) + 3;
+    (void)n_out;
+    return static_cast<int>(s < in ? s : in);
+  };
+  const int rh = span(a.scale_h, a.ih, MT_H, a.win_h), rw = span(a.scale_w, a.iw, MT_W, a.win_w);
+  const size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  dim3 grid((a.iw + MT_W - 1) / MT_W, (a.ih + MT_H - 1) / MT_H, a.total);
+  if (grid.z > 65535u || grid.y > 65535u) return cudaErrorInvalidConfiguration;
+#define YPB_PM(DT)                                                                                                  \
+  do {                                                                                                              \
+    if (smem > 48 * 1024) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(process_mask_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                               \
+    }                                                                                                               \
+    process_mask_kernel<DT><<<grid, MT_THREADS, smem, st>>>(a);                                                     \
+  } while (0)
+  if (a.proto_dtype == YPB_F32) YPB_PM(YPB_F32);
+  else if (a.proto_dtype == YPB_F16) YPB_PM(YPB_F16);
+  else YPB_PM(YPB_BF16);
+#undef YPB_PM
+  return cudaGetLastError();
+}
 
 cudaError_t launch_kpts_decode(const KptArgs& a, int dtype, int vec, cudaStream_t st) {
   const int groups = a.group_start[a.num_levels];

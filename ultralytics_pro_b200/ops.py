@@ -175,3 +175,108 @@ def scale_results(rows: torch.Tensor, count: torch.Tensor | None, img1_shape, or
                             _cabi.stream_ptr(rows.device))
     _cabi.check(rc, "ypb_scale_rows")
     return rows
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Segment masks (utils/ops.py:489-559)
+# ----------------------------------------------------------------------------------------------------------------
+def _protos_desc(protos: torch.Tensor):
+    _cabi.require_cuda(protos, "process_mask")
+    if protos.dim() == 3:
+        protos = protos.unsqueeze(0)
+    if protos.dim() != 4:
+        raise ValueError(f"protos must be (C, mh, mw) or (B, C, mh, mw), got {tuple(protos.shape)}")
+    if protos.stride(3) != 1 or protos.stride(2) != protos.shape[3]:
+        protos = protos.contiguous()
+    d = _cabi.ProtosDesc()
+    d.ptr, d.dtype = protos.data_ptr(), _cabi.dtype_code(protos.dtype)
+    _, d.channels, d.mh, d.mw = protos.shape
+    d.stride_b, d.stride_c = protos.stride(0), protos.stride(1)
+    return d, protos
+
+
+def _f32_rows(t: torch.Tensor, cols: int, what: str) -> torch.Tensor:
+    _cabi.require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2 or t.shape[1] != cols:
+        raise ValueError(f"{what}: expected (n, {cols}), got {tuple(t.shape)}")
+    if t.shape[0] and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _scale_masks_window(mh: int, mw: int, shape, padding: bool = True):
+    """Rows / columns of the prototype grid that scale_masks resizes (ops.py:544-559)."""
+    gain = min(mh / shape[0], mw / shape[1])
+    pad_w, pad_h = mw - shape[1] * gain, mh - shape[0] * gain
+    if padding:
+        pad_w /= 2
+        pad_h /= 2
+    top, left = (round(pad_h - 0.1), round(pad_w - 0.1)) if padding else (0, 0)
+    bottom, right = mh - round(pad_h + 0.1), mw - round(pad_w + 0.1)
+    return top, left, bottom - top, right - left
+
+
+def _run_masks(pd, coeffs, cis, crs, boxes, bis, brs, offsets, batch, total, out_hw, window, crop_mode, ratios, device):
+    out = torch.empty((total, out_hw[0], out_hw[1]), dtype=torch.uint8, device=device)
+    if total:
+        rc = _cabi.load().ypb_process_mask(C.byref(pd), coeffs.data_ptr(), cis, crs, boxes.data_ptr(), bis, brs,
+                                           offsets.data_ptr() if offsets is not None else None, batch, total,
+                                           out_hw[0], out_hw[1], window[0], window[1], window[2], window[3], crop_mode,
+                                           ratios[0], ratios[1], out.data_ptr(), _cabi.stream_ptr(device))
+        _cabi.check(rc, "ypb_process_mask")
+    return out
+
+
+def process_mask(protos, masks_in, bboxes, shape, upsample: bool = False):
+    """Mirror of ops.py:489-513: (n, H, W) uint8 masks of one image - ``masks_in @ protos`` cropped to the boxes at
+    prototype resolution, bilinearly upsampled to ``shape`` when ``upsample``, thresholded at 0.  One fused kernel;
+    follows the reference's CUDA / n >= 50 ``crop_mask`` branch (ops.py:482-486)."""
+    pd, keep = _protos_desc(protos)
+    c, mh, mw = pd.channels, pd.mh, pd.mw
+    co, bx = _f32_rows(masks_in, c, "process_mask coefficients"), _f32_rows(bboxes, 4, "process_mask boxes")
+    n = co.shape[0]
+    out_hw = (int(shape[0]), int(shape[1])) if upsample else (mh, mw)
+    ratios = (_f32(mw / shape[1]), _f32(mh / shape[0]))
+    return _run_masks(pd, co, 0, co.stride(0) if n else c, bx, 0, bx.stride(0) if n else 4, None, 1, n, out_hw,
+                      (0, 0, mh, mw), _cabi.MASK_CROP_PROTO, ratios, keep.device)
+
+
+def process_mask_native(protos, masks_in, bboxes, shape):
+    """Mirror of ops.py:516-541: masks resized to ``shape`` with the letterbox padding removed (scale_masks, ops.py:544-559),
+    then cropped to the boxes at that resolution, thresholded at 0."""
+    pd, keep = _protos_desc(protos)
+    c, mh, mw = pd.channels, pd.mh, pd.mw
+    co, bx = _f32_rows(masks_in, c, "process_mask_native coefficients"), _f32_rows(bboxes, 4, "process_mask_native boxes")
+    n = co.shape[0]
+    win = _scale_masks_window(mh, mw, shape)
+    return _run_masks(pd, co, 0, co.stride(0) if n else c, bx, 0, bx.stride(0) if n else 4, None, 1, n,
+                      (int(shape[0]), int(shape[1])), win, _cabi.MASK_CROP_OUTPUT, (1.0, 1.0), keep.device)
+
+
+def process_masks_batched(protos, rows, counts, shape, upsample: bool = True):
+    """``process_mask`` for every image of a batch in ONE launch (segment/predict.py:84-103 loops over images).
+
+    protos (B, C, mh, mw); rows (B, max_det, 6+C) padded NMS result rows (boxes in columns 0..3 in network-input pixels,
+    coefficients in 6..); counts: per-image kept counts on the HOST (``engine.fetch_counts``).  Returns the list of
+    (n_i, H, W) uint8 views of one packed buffer."""
+    pd, keep = _protos_desc(protos)
+    c, mh, mw = pd.channels, pd.mh, pd.mw
+    _cabi.require_cuda(rows, "process_masks_batched")
+    if rows.dtype != torch.float32 or rows.dim() != 3 or rows.shape[2] != 6 + c or rows.stride(2) != 1:
+        raise ValueError(f"rows must be (B, max_det, {6 + c}) float32 with contiguous columns, got {tuple(rows.shape)}")
+    b = rows.shape[0]
+    if len(counts) != b or keep.shape[0] != b:
+        raise ValueError("counts / protos do not match the batch")
+    offs = [0]
+    for n in counts:
+        offs.append(offs[-1] + int(n))
+    total = offs[-1]
+    offsets = torch.tensor(offs, dtype=torch.int32).pin_memory().to(rows.device, non_blocking=True)
+    out_hw = (int(shape[0]), int(shape[1])) if upsample else (mh, mw)
+    ratios = (_f32(mw / shape[1]), _f32(mh / shape[0]))
+    coeffs = rows[:, :, 6:]
+    packed = _run_masks(pd, coeffs, rows.stride(0), rows.stride(1), rows, rows.stride(0), rows.stride(1), offsets, b, total,
+                        out_hw, (0, 0, mh, mw), _cabi.MASK_CROP_PROTO, ratios, rows.device)
+    return [packed[offs[i]:offs[i + 1]] for i in range(b)]
