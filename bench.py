@@ -231,6 +231,11 @@ def run_ours(args):
     # HBM-bound class scan of one batch overlaps the latency-bound survivor decode / suppression of the previous one.
     LANES = max(1, args.lanes)
     NSETS = 2 * LANES
+    # one NCCL communicator PER LANE: collectives of different lanes are then unordered with respect to each other, so
+    # each lane's all_gather can be captured inside that lane's CUDA graph and replayed concurrently with the others
+    # (on ONE communicator, replays from several streams have no defined cross-rank order and can deadlock)
+    lane_groups = [dist.new_group(backend="nccl") for _ in range(LANES)] if world > 1 else [None] * LANES
+    graph_gather = world > 1 and not args.eager_gather
     sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B)[0]
             for s in range(NSETS)]
     use_graph = not args.no_graph
@@ -246,9 +251,10 @@ def run_ours(args):
             gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev) if world > 1 else None
             gr, gather_in_graph = None, False
             if use_graph:
-                if world > 1 and args.graph_gather:
+                if graph_gather:
                     try:  # the collective rides inside the graph: zero host work per step
-                        gr = [pp.capture(lv, after=lambda: ypb_dist.gather_packed(pl.packed, gb)) for lv in my_sets]
+                        grp = lane_groups[ln]
+                        gr = [pp.capture(lv, after=lambda: ypb_dist.gather_packed(pl.packed, gb, group=grp)) for lv in my_sets]
                         gather_in_graph = True
                     except Exception as exc:  # older NCCL/torch: capture of collectives unsupported
                         sys.stderr.write(f"[bench] NCCL capture failed ({exc}); gathering eagerly\n")
@@ -257,7 +263,7 @@ def run_ours(args):
                     gr = [pp.capture(lv) for lv in my_sets]
         st.synchronize()
         lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": gr, "plan": pl, "gather": gb,
-                      "gather_in_graph": gather_in_graph})
+                      "gather_in_graph": gather_in_graph, "group": lane_groups[ln]})
     post, plan = lanes[0]["post"], lanes[0]["plan"]
 
     def step(i):
@@ -271,7 +277,7 @@ def run_ours(args):
             if world > 1 and not ln["gather_in_graph"]:
                 # the only collective of the path: ONE all_gather of the plan's packed rows+counts buffer (the analogue
                 # of gather_object(stats), detect/val.py:226-240); it overlaps the other lanes' compute
-                ypb_dist.gather_packed(ln["plan"].packed, ln["gather"])
+                ypb_dist.gather_packed(ln["plan"].packed, ln["gather"], group=ln["group"])
 
     def fork():
         for ln in lanes:
@@ -427,7 +433,7 @@ def run_ours(args):
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
                        "cuda_graph": use_graph, "lanes": LANES,
                        "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
-                                      "of counts+rows per step" + (" captured in the CUDA graph" if lanes[0]["gather_in_graph"] else "")
+                                      "of counts+rows per step (one communicator per lane)" + (" captured in the lane's CUDA graph" if lanes[0]["gather_in_graph"] else ", issued eagerly")
                                       + ", overlapped with the other lanes" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
             "gpu_launches": (2 if os.environ.get("YPB_FUSE_DECODE") == "1" else 3) * K,
@@ -457,9 +463,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--graph-gather", action="store_true",
-                    help="EXPERIMENTAL: capture the NCCL all_gather inside each lane's CUDA graph (needs --lanes 1: "
-                         "collectives replayed from several streams have no defined cross-rank order and can deadlock)")
+    ap.add_argument("--eager-gather", action="store_true",
+                    help="issue the per-step NCCL all_gather eagerly from the host instead of capturing it in each lane's "
+                         "CUDA graph (default: captured, one communicator per lane)")
     ap.add_argument("--lanes", type=int, default=3, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -207,6 +207,20 @@ YPB_API int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs,
                              int32_t win_top, int32_t win_left, int32_t win_h, int32_t win_w, int32_t crop_mode,
                              float ratio_w, float ratio_h, uint8_t* out, void* stream);
 
+/* Validator matching: engine/validator.py:267-307 match_predictions (non-scipy branch) with, optionally, the pairwise
+ * metrics.py:54 box_iou of detect/val.py:287 computed on the fly.  correct: (B, rows_per_image, nthr) uint8.
+ *   boxes mode : preds = result rows (x1,y1,x2,y2 in columns 0..3, class in column cls_col), labels = (sum M, 5) fp32
+ *                rows cls,x1,y1,x2,y2 of all images, label_offsets = device (B+1) int32 prefix (NULL: one image, m labels)
+ *   matrix mode: iou = (m, n) fp32 matrix iou[l*iou_stride + d] of ONE image (obb/val.py, segment/val.py, pose/val.py
+ *                compute their own), preds = the n predicted classes (pred_row_stride 1, cls_col 0), true_cls = (m)
+ *   thresholds : HOST array of nthr <= 16 IoU levels (validator iouv); count: device (B) kept rows or NULL
+ *   workspace  : needed only when nthr * max_labels * 4 exceeds 200 KB of shared memory: nthr * sum M int32 */
+YPB_API int ypb_match_predictions(const float* preds, int64_t pred_image_stride, int64_t pred_row_stride, int32_t cls_col,
+                                  int32_t batch, int32_t rows_per_image, const int32_t* count, const float* labels,
+                                  const int32_t* label_offsets, int32_t m, int32_t max_labels, const float* iou,
+                                  int64_t iou_stride, const float* true_cls, const float* thresholds, int32_t nthr,
+                                  uint8_t* correct, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
  * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);

@@ -97,6 +97,40 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
     make_kpts(ref)
     make_masks(ref)
+    make_matching(ref)
+
+
+def make_matching(ref):
+    """BaseValidator.match_predictions + box_iou of the live reference (engine/validator.py:267-307, utils/metrics.py:54)."""
+    import types
+
+    from ultralytics.engine.validator import BaseValidator
+
+    out_path = os.path.join(ROOT, "tests", "golden", "post", "matching.npz")
+    iouv = torch.linspace(0.5, 0.95, 10)
+    ns = types.SimpleNamespace(iouv=iouv)
+    g = torch.Generator().manual_seed(99)
+    blob, meta = {}, []
+    for name, m, n, nc, jitter in [("few", 6, 20, 3, 3.0), ("crowd", 120, 300, 5, 6.0), ("one_class", 40, 90, 1, 10.0),
+                                   ("no_match", 10, 30, 4, 400.0), ("many_labels", 700, 300, 2, 4.0)]:
+        xy = torch.rand(m, 2, generator=g) * 500
+        wh = torch.rand(m, 2, generator=g) * 120 + 8
+        gt = torch.cat([xy, xy + wh], 1)
+        gcls = torch.randint(0, nc, (m,), generator=g).float()
+        src = torch.randint(0, m, (n,), generator=g)
+        pred = gt[src] + torch.randn(n, 4, generator=g) * jitter
+        pcls = torch.where(torch.rand(n, generator=g) < 0.8, gcls[src], torch.randint(0, nc, (n,), generator=g).float())
+        iou = ref.metrics.box_iou(gt, pred)
+        tp = BaseValidator.match_predictions(ns, pcls, gcls, iou)
+        i = len(meta)
+        blob[f"q{i}_gt"], blob[f"q{i}_gcls"], blob[f"q{i}_pred"], blob[f"q{i}_pcls"] = gt.numpy(), gcls.numpy(), pred.numpy(), pcls.numpy()
+        blob[f"q{i}_iou"], blob[f"q{i}_tp"] = iou.numpy(), tp.numpy()
+        meta.append(dict(name=name, m=m, n=n))
+        print(name, tuple(tp.shape), int(tp.sum()))
+    blob["iouv"] = iouv.numpy()
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
 
 def make_masks(ref):

@@ -177,3 +177,37 @@ def process_mask_native_oracle(protos, masks_in, bboxes, shape):
     up = F.interpolate(low[None, :, top:bottom, left:right], tuple(shape), mode="bilinear")[0]
     up = crop_mask_oracle(up, bboxes)
     return (up > 0).to(torch.uint8), up
+
+
+def box_iou_oracle(box1, box2, eps=1e-7):
+    """utils/metrics.py:54-75 on numpy fp32: (N, 4) x (M, 4) xyxy -> (N, M)."""
+    a = np.asarray(box1, dtype=F)[:, None, :]
+    b = np.asarray(box2, dtype=F)[None, :, :]
+    wh = np.maximum(np.minimum(a[..., 2:], b[..., 2:]) - np.maximum(a[..., :2], b[..., :2]), F(0))
+    inter = wh[..., 0] * wh[..., 1]
+    area_a = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
+    area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    return (inter / (area_a + area_b - inter + F(eps))).astype(F)
+
+
+def match_predictions_oracle(pred_classes, true_classes, iou, iouv):
+    """engine/validator.py:267-307, the non-scipy branch, restated without the sort: per IoU level a detection is correct
+    iff (a) its best same-class label reaches the level and (b) it is the lowest-index detection among those sharing that
+    best label at this level.  (The reference sorts the candidate pairs by IoU, keeps the first pair of every detection and
+    then - the pairs now being in detection order - the first pair of every label.)  Scores must be tie-free."""
+    pc = np.asarray(pred_classes, dtype=F)
+    tc = np.asarray(true_classes, dtype=F)
+    m = np.asarray(iou, dtype=F) * (tc[:, None] == pc[None, :]).astype(F)  # (labels, detections)
+    n = pc.shape[0]
+    correct = np.zeros((n, len(iouv)), dtype=bool)
+    if m.size == 0:
+        return correct
+    best_label = m.argmax(0)
+    best = m.max(0)
+    for i, t in enumerate(iouv):
+        taken = set()
+        for d in range(n):
+            if best[d] > 0 and best[d] >= F(t) and best_label[d] not in taken:
+                taken.add(best_label[d])
+                correct[d, i] = True
+    return correct

@@ -36,6 +36,7 @@ EXPORTS = (
     "ypb_nms_from_head_riders",
     "ypb_kpts_decode",
     "ypb_process_mask",
+    "ypb_match_predictions",
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
@@ -188,6 +189,11 @@ def load():
                                      C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p,
                                      C.c_void_p]
+    lib.ypb_match_predictions.restype = C.c_int
+    lib.ypb_match_predictions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -399,6 +399,41 @@ int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t
   return YPB_OK;
 }
 
+int ypb_match_predictions(const float* preds, int64_t pred_image_stride, int64_t pred_row_stride, int32_t cls_col,
+                          int32_t batch, int32_t rows_per_image, const int32_t* count, const float* labels,
+                          const int32_t* label_offsets, int32_t m, int32_t max_labels, const float* iou, int64_t iou_stride,
+                          const float* true_cls, const float* thresholds, int32_t nthr, uint8_t* correct, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (batch < 0 || rows_per_image < 0 || m < 0 || max_labels < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "negative size");
+  if (nthr < 1 || nthr > 16 || !thresholds) return fail(YPB_ERR_INVALID_ARGUMENT, "nthr=%d outside [1,16] or thresholds NULL", nthr);
+  if (batch == 0 || rows_per_image == 0) return YPB_OK;
+  if (!preds || !correct) return fail(YPB_ERR_INVALID_ARGUMENT, "preds / correct is NULL");
+  if (iou) {
+    if (batch != 1 || label_offsets) return fail(YPB_ERR_INVALID_ARGUMENT, "matrix mode handles one image per call");
+    if (!true_cls && m > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "matrix mode needs true_cls");
+    if (iou_stride < rows_per_image) return fail(YPB_ERR_INVALID_ARGUMENT, "iou row stride < n");
+  } else {
+    if (!labels && (m > 0 || label_offsets)) return fail(YPB_ERR_INVALID_ARGUMENT, "labels is NULL");
+    if (batch > 1 && !label_offsets) return fail(YPB_ERR_INVALID_ARGUMENT, "label_offsets is NULL for a batch of %d", batch);
+    if (cls_col < 4) return fail(YPB_ERR_INVALID_ARGUMENT, "cls_col=%d must be >= 4 in boxes mode", cls_col);
+  }
+  const int ml = label_offsets ? max_labels : m;
+  ypb::MatchArgs a{};
+  a.preds = preds; a.pred_image_stride = pred_image_stride; a.pred_row_stride = pred_row_stride; a.cls_col = cls_col;
+  a.batch = batch; a.rows_per_image = rows_per_image; a.count = count; a.labels = labels; a.label_offsets = label_offsets;
+  a.m = m; a.iou = iou; a.iou_stride = iou_stride; a.true_cls = true_cls; a.nthr = nthr; a.correct = correct;
+  for (int i = 0; i < nthr; ++i) a.thr[i] = thresholds[i];
+  if (static_cast<size_t>(nthr) * ml * sizeof(int) > 200 * 1024) {
+    // sum M is only known on the device in the batched form: the caller sizes the scratch for nthr * (total labels)
+    if (!workspace || workspace_bytes < static_cast<size_t>(nthr) * ml * sizeof(int))
+      return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "%d labels need a workspace of nthr * total_labels * 4 bytes", ml);
+    a.win_global = static_cast<int*>(workspace);
+  }
+  cudaError_t e = ypb::launch_match_predictions(a, ml, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_match_predictions");
+  return YPB_OK;
+}
+
 void ypb_debug_set_phase_buffer(void* device_buffer) { ypb::set_phase_buffer(static_cast<long long*>(device_buffer)); }
 
 int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream) {

@@ -452,6 +452,24 @@ struct MaskArgs {  // ypb_process_mask
 };
 cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st);
 
+struct MatchArgs {  // ypb_match_predictions
+  const float* preds;      // rows: x1,y1,x2,y2,...,cls at cls_col
+  long long pred_image_stride, pred_row_stride;
+  int cls_col, batch, rows_per_image;
+  const int32_t* count;    // device (B) or null
+  const float* labels;     // (sum M, 5) cls,x1,y1,x2,y2 - or null when iou + true_cls are given
+  const int32_t* label_offsets;  // device (B+1) or null (single image: m labels)
+  int m;
+  const float* iou;        // optional precomputed (M, N) matrix (single image)
+  long long iou_stride;
+  const float* true_cls;   // with iou
+  float thr[16];
+  int nthr;
+  uint8_t* correct;        // (B, rows_per_image, nthr)
+  int* win_global;         // optional scratch [nthr * sum M] when the labels do not fit shared memory
+};
+cudaError_t launch_match_predictions(const MatchArgs& a, int max_labels, cudaStream_t st);
+
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
                                 int vec, cudaStream_t st);

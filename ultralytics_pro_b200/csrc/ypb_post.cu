@@ -206,7 +206,80 @@ process_mask_kernel(const __grid_constant__ MaskArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Validator matching (engine/validator.py:267-307 match_predictions, non-scipy branch, fed by detect/val.py:274-288
+// _process_batch with metrics.py:54 box_iou).  Restated: with iou'[l, d] = iou[l, d] * (cls_l == cls_d),
+//   best(d) = the label with the largest iou'[., d]            (first np.unique: one label per detection)
+//   for a threshold t, detection d is a true positive iff iou'[best(d), d] >= t and d is the LOWEST-index detection among
+//   those whose best label is best(d) and that reach t         (second np.unique: one detection per label, in d order)
+// One CTA per image; thread = detection; the per-(threshold, label) winners are an atomicMin table in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MATCH_THREADS = 256;
+
+__device__ __forceinline__ float box_iou_eps(const float4 a, const float4 b) {  // metrics.py:54-75, eps = 1e-7
+  const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+  const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  const float inter = __fmul_rn(iw, ih);
+  const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-7f));
+}
+
+__global__ void __launch_bounds__(MATCH_THREADS)
+match_predictions_kernel(const __grid_constant__ MatchArgs a) {
+  extern __shared__ int s_win[];  // [nthr][m]: lowest detection index claiming label l at threshold i
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.count ? min(a.count[b], a.rows_per_image) : a.rows_per_image;
+  const int l0 = a.label_offsets ? a.label_offsets[b] : 0;
+  const int m = a.label_offsets ? a.label_offsets[b + 1] - l0 : a.m;
+  uint8_t* out = a.correct + static_cast<long long>(b) * a.rows_per_image * a.nthr;
+  int* win = a.win_global ? a.win_global + static_cast<long long>(l0) * a.nthr : s_win;
+  for (int i = tid; i < a.nthr * m; i += MATCH_THREADS) win[i] = 0x7fffffff;
+  __syncthreads();
+  const float* labels = a.labels + static_cast<long long>(l0) * 5;  // cls, x1, y1, x2, y2
+  for (int d0 = 0; d0 < n; d0 += MATCH_THREADS) {
+    const int d = d0 + tid;
+    float best = 0.f;
+    int bl = -1;
+    if (d < n) {
+      const float* pr = a.preds + static_cast<long long>(b) * a.pred_image_stride + static_cast<long long>(d) * a.pred_row_stride;
+      const float4 pb = a.iou ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(pr[0], pr[1], pr[2], pr[3]);
+      const float pc = pr[a.cls_col];
+      for (int l = 0; l < m; ++l) {
+        float v;
+        if (a.iou) {
+          v = a.iou[static_cast<long long>(l) * a.iou_stride + d];
+        } else {
+          const float* g = labels + l * 5;
+          v = box_iou_eps(make_float4(g[1], g[2], g[3], g[4]), pb);
+        }
+        const float tc = a.true_cls ? a.true_cls[l] : labels[l * 5];
+        v = __fmul_rn(v, tc == pc ? 1.f : 0.f);  // validator.py:285
+        if (v > best) { best = v; bl = l; }
+      }
+      if (bl >= 0)
+        for (int i = 0; i < a.nthr; ++i)
+          if (best >= a.thr[i]) atomicMin(&win[i * m + bl], d);
+    }
+    __syncthreads();
+    if (d < n)
+      for (int i = 0; i < a.nthr; ++i) out[d * a.nthr + i] = (bl >= 0 && best >= a.thr[i] && win[i * m + bl] == d) ? 1 : 0;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_match_predictions(const MatchArgs& a, int max_labels, cudaStream_t st) {
+  if (a.batch <= 0 || a.rows_per_image <= 0) return cudaSuccess;
+  const size_t smem = a.win_global ? 0 : static_cast<size_t>(a.nthr) * (max_labels > 0 ? max_labels : 1) * sizeof(int);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(match_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  match_predictions_kernel<<<a.batch, MATCH_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
   if (a.total <= 0 || a.ih <= 0 || a.iw <= 0) return cudaSuccess;

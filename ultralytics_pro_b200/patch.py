@@ -93,6 +93,37 @@ def _wrap_ops(ref_fn, ours, tensor_arg: int):
     return f
 
 
+def _wrap_masks(ref_fn, ours):
+    def f(protos, masks_in, bboxes, shape, *args, **kwargs):
+        if getattr(protos, "is_cuda", False) and getattr(masks_in, "is_cuda", False) and protos.dim() == 3:
+            return ours(protos, masks_in, bboxes, shape, *args, **kwargs)
+        return ref_fn(protos, masks_in, bboxes, shape, *args, **kwargs)
+
+    f.__wrapped__ = ref_fn
+    f.__name__ = ref_fn.__name__
+    return f
+
+
+def _wrap_match(ref_fn, ours):
+    def match_predictions(self, pred_classes, true_classes, iou, use_scipy=False):
+        if getattr(iou, "is_cuda", False) and not use_scipy and len(self.iouv) <= 16:
+            return ours(self, pred_classes, true_classes, iou)
+        return ref_fn(self, pred_classes, true_classes, iou, use_scipy)
+
+    match_predictions.__wrapped__ = ref_fn
+    return match_predictions
+
+
+def _wrap_process_batch(ref_fn, ours):
+    def _process_batch(self, preds, batch):
+        if getattr(preds["bboxes"], "is_cuda", False) and len(self.iouv) <= 16:
+            return ours(self, preds, batch)
+        return ref_fn(self, preds, batch)
+
+    _process_batch.__wrapped__ = ref_fn
+    return _process_batch
+
+
 def install() -> list:
     """Patch the already-importable `ultralytics` package in place; returns the list of rebound symbols."""
     from . import head as our_head
@@ -125,6 +156,25 @@ def install() -> list:
         _saved[f"ultralytics.utils.ops.{name}"] = (ref_ops, name, orig)
         setattr(ref_ops, name, _wrap_ops(orig, getattr(our_ops, name), 0 if name in ("clip_boxes", "clip_coords", "regularize_rboxes") else 1))
         done.append(f"ultralytics.utils.ops.{name}")
+    for name in ("process_mask", "process_mask_native"):  # utils/ops.py:489, :516 (segment/predict.py:101-103, segment/val.py:76)
+        orig = getattr(ref_ops, name)
+        _saved[f"ultralytics.utils.ops.{name}"] = (ref_ops, name, orig)
+        setattr(ref_ops, name, _wrap_masks(orig, getattr(our_ops, name)))
+        done.append(f"ultralytics.utils.ops.{name}")
+    try:  # engine/validator.py:267, models/yolo/detect/val.py:274
+        from . import val as our_val
+
+        ref_validator = importlib.import_module("ultralytics.engine.validator")
+        ref_detval = importlib.import_module("ultralytics.models.yolo.detect.val")
+        bv, dv = ref_validator.BaseValidator, ref_detval.DetectionValidator
+        _saved["ultralytics.engine.validator.BaseValidator.match_predictions"] = (bv, "match_predictions", bv.__dict__["match_predictions"])
+        bv.match_predictions = _wrap_match(bv.__dict__["match_predictions"], our_val.match_predictions)
+        done.append("ultralytics.engine.validator.BaseValidator.match_predictions")
+        _saved["ultralytics.models.yolo.detect.val.DetectionValidator._process_batch"] = (dv, "_process_batch", dv.__dict__["_process_batch"])
+        dv._process_batch = _wrap_process_batch(dv.__dict__["_process_batch"], our_val.process_batch)
+        done.append("ultralytics.models.yolo.detect.val.DetectionValidator._process_batch")
+    except Exception:  # validator stack not importable in this environment: matching stays with the reference
+        pass
     # fast_nms resolves iou_func by __name__, so the reference's own box_iou / batch_probiou callables are recognised
     try:
         ref_head = importlib.import_module("ultralytics.nn.modules.head")
