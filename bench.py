@@ -234,8 +234,10 @@ def run_ours(args):
     # one NCCL communicator PER LANE: collectives of different lanes are then unordered with respect to each other, so
     # each lane's all_gather can be captured inside that lane's CUDA graph and replayed concurrently with the others
     # (on ONE communicator, replays from several streams have no defined cross-rank order and can deadlock)
-    lane_groups = [dist.new_group(backend="nccl") for _ in range(LANES)] if world > 1 else [None] * LANES
-    graph_gather = world > 1 and not args.eager_gather
+    gather_mode = args.gather if world > 1 else "none"
+    lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager")
+                   else [None] * LANES)
+    graph_gather = gather_mode == "nccl"
     sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B)[0]
             for s in range(NSETS)]
     use_graph = not args.no_graph
@@ -245,12 +247,21 @@ def run_ours(args):
         st = torch.cuda.Stream(dev)
         st.wait_stream(main)
         with torch.cuda.stream(st):
-            pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
+            pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms,
+                                   peer_gather_group=True if gather_mode == "peer" else None)
             my_sets = [sets[ln + LANES * j] for j in range(2)]
-            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers
-            gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev) if world > 1 else None
+            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers (collective when the peer gather is on)
+            gb = (torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
+                  if gather_mode in ("nccl", "nccl-eager") else None)
             gr, gather_in_graph = None, False
             if use_graph:
+                if gather_mode == "peer":
+                    # the suppression kernel itself stores the results into every rank's buffer; the graph ends with the
+                    # consumer-side wait, so at step end every rank holds everyone's detections (all_gather semantics)
+                    # (--gather-lag 1, default: the wait is for the lane's PREVIOUS batch, which has long arrived, so no rank
+                    # ever stalls on a slower one inside a step; the lanes are drained with lag 0 before the timed region ends)
+                    gr = [pp.capture(lv, after=lambda: pp.wait_gather(args.gather_lag)) for lv in my_sets]
+                    gather_in_graph = True
                 if graph_gather:
                     try:  # the collective rides inside the graph: zero host work per step
                         grp = lane_groups[ln]
@@ -274,7 +285,9 @@ def run_ours(args):
                 ln["graphs"][j].replay()
             else:
                 ln["post"].enqueue(ln["sets"][j])
-            if world > 1 and not ln["gather_in_graph"]:
+            if gather_mode == "peer" and not use_graph:
+                ln["post"].wait_gather(args.gather_lag)
+            elif gather_mode in ("nccl", "nccl-eager") and not ln["gather_in_graph"]:
                 # the only collective of the path: ONE all_gather of the plan's packed rows+counts buffer (the analogue
                 # of gather_object(stats), detect/val.py:226-240); it overlaps the other lanes' compute
                 ypb_dist.gather_packed(ln["plan"].packed, ln["gather"], group=ln["group"])
@@ -292,17 +305,23 @@ def run_ours(args):
         step(i)
     join()
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-
+    # everything with a variable host cost (NVML init of the clock sampler, event creation) happens BEFORE the barrier, so
+    # that the ranks enter the timed region together: the peer gather couples them, and a rank that starts late would be
+    # waited for by the others inside THEIR timed regions
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
     ev0.record()
     fork()
     for i in range(K):
         step(i)
+    if gather_mode == "peer" and args.gather_lag > 0:  # drain: every result of every rank has landed before the clock stops
+        for ln in lanes:
+            with torch.cuda.stream(ln["stream"]):
+                ln["post"].wait_gather(0)
     join()
     ev1.record()
     torch.cuda.synchronize(dev)
@@ -310,12 +329,33 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    sys.stderr.write(f"[bench] rank {rank}: {float(ms.item()) / K * 1e3:.2f} us/step, kept {int(plan.count.sum())} cand {int(plan.cand.sum())}\n")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     value = world * B * K / (total_ms * 1e-3)
     kept = plan.count.sum().item()
     cand = plan.cand.sum().item()
+
+    # ---- multi-GPU: check the one-sided gather against an NCCL all_gather of the same result buffers ------------------
+    gather_verified = None
+    if gather_mode == "peer":
+        ln0 = lanes[0]
+        with torch.cuda.stream(ln0["stream"]):
+            ln0["graphs"][0].replay() if use_graph else ln0["post"].enqueue(ln0["sets"][0])
+            ln0["post"].wait_gather(0)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        pl0 = ln0["plan"]
+        ref = torch.empty((world, pl0.packed.numel()), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref, pl0.packed.clone())
+        ref_rows, ref_cnt = ypb_dist.split_packed(ref, B, pl0.rows.shape[1], pl0.rows.shape[2])
+        got_rows, got_cnt = ln0["post"].gathered()
+        valid = (torch.arange(pl0.rows.shape[1], device=dev)[None, :] < ref_cnt[:, None]).unsqueeze(-1)
+        ok = bool(torch.equal(ref_cnt, got_cnt)) and bool(torch.equal(ref_rows * valid, got_rows * valid)) and int(ref_cnt.sum()) > 0
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(flag.item())
 
     # ---- per-kernel timing with CUDA events on the launching stream (roofline of the dominant kernel) ---------------
     # Each prefix of the step (scan | scan+decode | scan+decode+suppress) is captured as a CUDA graph of R back-to-back
@@ -432,11 +472,15 @@ def run_ours(args):
             "config": {"workload": WORKLOAD_DESC, "batch_per_gpu": B, "global_batch": B * world,
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
                        "cuda_graph": use_graph, "lanes": LANES,
-                       "parallelism": "images sharded across ranks, no data-path collective; one packed NCCL all_gather "
-                                      "of counts+rows per step (one communicator per lane)" + (" captured in the lane's CUDA graph" if lanes[0]["gather_in_graph"] else ", issued eagerly")
-                                      + ", overlapped with the other lanes" if world > 1 else "single GPU"},
+                       "parallelism": ("images sharded across ranks, no data-path collective; results gathered on every rank each step by "
+                                       + {"peer": f"one-sided NVLink peer-memory stores issued by the suppression kernel + an arrival-flag wait (lag {args.gather_lag} batch per lane, drained before the clock stops), all inside the lane's CUDA graph",
+                                          "nccl": "one packed NCCL all_gather (one communicator per lane) captured in the lane's CUDA graph",
+                                          "nccl-eager": "one packed NCCL all_gather (one communicator per lane) issued from the host",
+                                          "none": "NOTHING (diagnostic: independent replicas)"}[gather_mode]
+                                       + ", overlapped with the other lanes") if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
-            "gpu_launches": (2 if os.environ.get("YPB_FUSE_DECODE") == "1" else 3) * K,
+            "gpu_launches": ((2 if os.environ.get("YPB_FUSE_DECODE") == "1" else 3) + (1 if gather_mode == "peer" else 0)) * K,
+            "gather_verified_against_nccl": gather_verified,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
                     "note": "postprocess_from_head on pinned HOST head tensors: H2D + decode+NMS + D2H of rows and counts, "
                             "synchronised every step"},
@@ -450,8 +494,12 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line))
     if world > 1:
+        # leave without tearing the communicators down: destroy_process_group() was seen to hang with CUDA graphs that
+        # hold captured collectives; every rank has finished its device work here
+        sys.stdout.flush()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        os._exit(0)
     return 0
 
 
@@ -463,10 +511,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--eager-gather", action="store_true",
-                    help="issue the per-step NCCL all_gather eagerly from the host instead of capturing it in each lane's "
-                         "CUDA graph (default: captured, one communicator per lane)")
-    ap.add_argument("--lanes", type=int, default=3, help="independent pipelines (streams) the steps are spread over")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "nccl-eager", "none"],
+                    help="multi-GPU result gather: peer = one-sided stores over NVLink peer memory from the suppression kernel "
+                         "(default); nccl = one all_gather per step captured in each lane's CUDA graph (one communicator per "
+                         "lane); nccl-eager = the same issued from the host")
+    ap.add_argument("--gather-lag", type=int, default=1,
+                    help="peer gather: each step waits for the arrival of the results of the lane's batch this many batches back "
+                         "(0 = the batch just processed); the lanes are drained with lag 0 before the timed region ends")
+    ap.add_argument("--lanes", type=int, default=5, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -35,8 +35,9 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 2
+#define YPB_ABI_VERSION 3
 #define YPB_MAX_LEVELS 8
+#define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
 typedef enum { YPB_F32 = 0, YPB_F16 = 1, YPB_BF16 = 2 } ypb_dtype;
 
@@ -133,7 +134,22 @@ typedef struct {
   int32_t* cand_count;
   const ypb_scale_xform* scale_xforms;
   int32_t scale_padding;
+  /* One-sided result gather over NVLink peer memory (multi-GPU): when num_peers > 0 the gather stage of
+   * the suppression kernel also stores this rank's kept rows and counts straight into every peer's result buffer
+   * (peer-mapped device pointers, e.g. torch symmetric memory / CUDA IPC) - the analogue of dist.gather_object(stats),
+   * detect/val.py:226-240, without a collective: no rank ever waits for another inside the step.
+   *   peer_rows[p] / peer_count[p] : where THIS rank's (B, max_det, cols) rows / (B) counts live in peer p's buffer
+   *   peer_flag[p]                 : peer p's arrival flags, one int32 per rank; flag[my_rank] is set to the launch
+   *                                  sequence number (system-scope release) once all images of the launch are stored
+   *   peer_state                   : local device int32[4], zero-initialised once by the caller ([0] CTAs done,
+   *                                  [1] launches sent so far = the sequence number ypb_peer_wait waits for) */
+  int32_t num_peers;
+  int32_t my_rank;
   int32_t reserved;
+  float* peer_rows[YPB_MAX_PEERS];
+  int32_t* peer_count[YPB_MAX_PEERS];
+  int32_t* peer_flag[YPB_MAX_PEERS];
+  int32_t* peer_state;
 } ypb_nms_out;
 
 YPB_API int ypb_abi_version(void);
@@ -220,6 +236,13 @@ YPB_API int ypb_match_predictions(const float* preds, int64_t pred_image_stride,
                                   const int32_t* label_offsets, int32_t m, int32_t max_labels, const float* iou,
                                   int64_t iou_stride, const float* true_cls, const float* thresholds, int32_t nthr,
                                   uint8_t* correct, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Consumer side of the one-sided gather: enqueues a one-thread kernel that spins (system-scope acquire) until every one
+ * of the `world` arrival flags of THIS rank has reached the sequence number of this rank's own latest launch (state[1];
+ * all ranks run the same launch sequence), i.e. until the results of the matching launch of every rank have landed in
+ * this rank's buffer.  lag > 0 waits for the launch `lag` launches back instead (a pipelined gather: the step never
+ * stalls on a slower rank, results of launch i are complete everywhere once launch i+lag has been waited for). */
+YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, void* stream);
 
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode

@@ -16,7 +16,8 @@ from . import build as _build
 YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
-ABI_VERSION = 2
+MAX_PEERS = 8
+ABI_VERSION = 3
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -37,6 +38,7 @@ EXPORTS = (
     "ypb_kpts_decode",
     "ypb_process_mask",
     "ypb_match_predictions",
+    "ypb_peer_wait",
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
@@ -99,7 +101,13 @@ class NmsOut(C.Structure):
         ("cand_count", C.c_void_p),
         ("scale_xforms", C.c_void_p),
         ("scale_padding", C.c_int32),
+        ("num_peers", C.c_int32),
+        ("my_rank", C.c_int32),
         ("reserved", C.c_int32),
+        ("peer_rows", C.c_void_p * MAX_PEERS),
+        ("peer_count", C.c_void_p * MAX_PEERS),
+        ("peer_flag", C.c_void_p * MAX_PEERS),
+        ("peer_state", C.c_void_p),
     ]
 
 
@@ -194,6 +202,8 @@ def load():
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]
+    lib.ypb_peer_wait.restype = C.c_int
+    lib.ypb_peer_wait.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

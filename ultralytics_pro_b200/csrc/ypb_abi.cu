@@ -100,6 +100,12 @@ int check_params(const ypb_nms_params* p, const ypb_nms_out* out) {
   if (!(p->conf_thres >= 0.f) || !(p->iou_thres_eff >= 0.f) || p->iou_thres_eff > 1.f)
     return fail(YPB_ERR_INVALID_ARGUMENT, "conf/iou threshold outside [0,1] (nms.py:59-60)");
   if (!out->rows || !out->count) return fail(YPB_ERR_INVALID_ARGUMENT, "out.rows / out.count is NULL");
+  if (out->num_peers < 0 || out->num_peers > YPB_MAX_PEERS) return fail(YPB_ERR_INVALID_ARGUMENT, "num_peers=%d outside [0,%d]", out->num_peers, YPB_MAX_PEERS);
+  if (out->num_peers > 0) {
+    if (out->my_rank < 0 || out->my_rank >= out->num_peers || !out->peer_state) return fail(YPB_ERR_INVALID_ARGUMENT, "peer gather: my_rank / peer_state invalid");
+    for (int i = 0; i < out->num_peers; ++i)
+      if (!out->peer_rows[i] || !out->peer_count[i] || !out->peer_flag[i]) return fail(YPB_ERR_INVALID_ARGUMENT, "peer gather: pointer of peer %d is NULL", i);
+  }
   return YPB_OK;
 }
 
@@ -115,6 +121,10 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
   s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_cand = out->cand_count;
   s.scale_xforms = out->scale_xforms; s.scale_padding = out->scale_padding;
+  s.num_peers = out->num_peers; s.my_rank = out->my_rank; s.peer_state = out->peer_state;
+  for (int i = 0; i < YPB_MAX_PEERS; ++i) {
+    s.peer_rows[i] = out->peer_rows[i]; s.peer_count[i] = out->peer_count[i]; s.peer_flag[i] = out->peer_flag[i];
+  }
   return s;
 }
 
@@ -431,6 +441,13 @@ int ypb_match_predictions(const float* preds, int64_t pred_image_stride, int64_t
   }
   cudaError_t e = ypb::launch_match_predictions(a, ml, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "ypb_match_predictions");
+  return YPB_OK;
+}
+
+int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, void* stream) {
+  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
+  cudaError_t e = ypb::launch_peer_wait(flags, world, state, lag, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_peer_wait");
   return YPB_OK;
 }
 

@@ -404,6 +404,12 @@ struct SuppressArgs {
   // optional fused construct_result rescale of the kept rows (ypb_nms_out.scale_*)
   const ypb_scale_xform* scale_xforms;
   int scale_padding;
+  // one-sided gather over peer memory (ypb_nms_out.peer_*)
+  int num_peers, my_rank;
+  float* peer_rows[YPB_MAX_PEERS];
+  int32_t* peer_count[YPB_MAX_PEERS];
+  int32_t* peer_flag[YPB_MAX_PEERS];
+  int32_t* peer_state;
   long long* dbg;  // diagnostic phase timestamps or null
 };
 void set_phase_buffer(long long* p);
@@ -480,6 +486,7 @@ cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& 
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,
                               float4* cand_box, float* cand_ang, int32_t* row_count, cudaStream_t st);
+cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, cudaStream_t st);
 cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st);
 
 }  // namespace ypb

@@ -941,8 +941,57 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       a.out_rows[(static_cast<long long>(b) * a.max_det + k) * cols + 6 + e] = v;
     }
   }
+  if (a.num_peers > 0 && a.out_rows) {
+    // ---- one-sided gather over NVLink (ypb_nms_out.peer_*): the kept rows of this image are contiguous floats in the
+    //      local result buffer; copy them and the count into every peer's buffer with plain (peer-mapped) stores, then
+    //      the last CTA of the launch publishes the launch sequence number in every peer's arrival flag.
+    __syncthreads();  // the local rows of this image are complete
+    const int nfl = kept_n * cols;
+    const long long img_off = static_cast<long long>(b) * a.max_det * cols;
+    const float* src = a.out_rows + img_off;
+    for (int p = 0; p < a.num_peers; ++p) {
+      float* dst = a.peer_rows[p] + img_off;
+      if (dst != src) {
+        if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+          for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+          for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
+        } else {
+          for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
+        }
+      }
+      if (tid == 0 && a.peer_count[p] + b != a.out_count + b) a.peer_count[p][b] = kept_n;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(&a.peer_state[0], 1);
+      if (prev == static_cast<int>(gridDim.x) - 1) {  // last image of the launch
+        a.peer_state[0] = 0;
+        const int seq = a.peer_state[1] + 1;
+        a.peer_state[1] = seq;
+        __threadfence_system();
+        for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
+      }
+    }
+  }
   __syncthreads();
   YPB_MARK(31);
+}
+
+__global__ void peer_wait_kernel(const int32_t* flags, int world, int32_t* state, int lag) {
+  // the sequence number of this rank's own latest launch (set by its last CTA, earlier on this stream): every rank runs
+  // the same launch sequence, so the peers' matching launch carries the same number
+  const int want = state[1] - lag;
+  for (int r = 0; r < world; ++r) {
+    const volatile int32_t* f = flags + r;
+    while (*f - want < 0) __nanosleep(100);
+  }
+  __threadfence_system();
+}
+
+cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, cudaStream_t st) {
+  peer_wait_kernel<<<1, 1, 0, st>>>(flags, world, state, lag);
+  return cudaGetLastError();
 }
 
 __global__ void boxes_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, int box_dim,

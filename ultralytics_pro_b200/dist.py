@@ -77,3 +77,68 @@ def split_packed(out: torch.Tensor, batch_per_rank: int, max_det: int, cols: int
     rows = out[:, :nrow].reshape(world * batch_per_rank, max_det, cols)
     count = out[:, nrow:].contiguous().view(torch.int32).reshape(world * batch_per_rank)
     return rows, count
+
+
+class PeerGather:
+    """One-sided gather of the result buffers over NVLink peer memory (``ypb_nms_out.peer_*``).
+
+    Every rank owns a symmetric buffer ``[world x packed | world arrival flags]`` that all ranks of the node map
+    (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged once at construction).  Rank s's suppression kernel
+    stores its kept rows + counts directly into slot s of EVERY rank's buffer and then raises flag s there; nothing on the
+    step's critical path waits for another rank, unlike an all_gather whose kernels rendezvous.  ``wait()`` enqueues the
+    consumer-side spin (``ypb_peer_wait``) after which ``gathered()`` holds the results of the matching launch of all ranks.
+    Construction is collective (same order on every rank).  One instance serves one stream / lane.
+    Consumer contract: slot contents are overwritten by the owner's next launch on this lane; consume (or copy out) on the
+    lane's stream before enqueueing the launch after next.
+    """
+
+    def __init__(self, packed_numel: int, nrow: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        from . import _cabi
+
+        if self.world > _cabi.MAX_PEERS:
+            raise ValueError(f"peer gather spans one node: world {self.world} > {_cabi.MAX_PEERS}")
+        self.numel, self.nrow = int(packed_numel), int(nrow)
+        self.slot = (self.numel + 3) // 4 * 4  # 16-byte aligned slots
+        total = self.world * self.slot + 16
+        self.buf = symm.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        try:
+            self.handle = symm.rendezvous(self.buf, group)
+        except Exception:
+            symm.enable_symm_mem_for_group(group.group_name)
+            self.handle = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.flags = self.buf[self.world * self.slot: self.world * self.slot + 16].view(torch.int32)
+        self.my_packed = self.buf[self.rank * self.slot: self.rank * self.slot + self.numel]
+        self.peer_rows = [p + self.rank * self.slot * 4 for p in ptrs]
+        self.peer_count = [p + self.nrow * 4 for p in self.peer_rows]
+        self.peer_flag = [p + self.world * self.slot * 4 for p in ptrs]
+        dist.barrier(group)  # every rank has zeroed its buffer before anyone stores into it
+
+    def bind(self, out) -> None:
+        """Fill the peer fields of a ``_cabi.NmsOut``."""
+        out.num_peers, out.my_rank = self.world, self.rank
+        for i in range(self.world):
+            out.peer_rows[i], out.peer_count[i], out.peer_flag[i] = self.peer_rows[i], self.peer_count[i], self.peer_flag[i]
+        out.peer_state = self.state.data_ptr()
+
+    def wait(self, lag: int = 0) -> None:
+        """lag=0: the latest launch of every rank has landed; lag=k: the launch k launches back (pipelined gather)."""
+        from . import _cabi
+
+        rc = _cabi.load().ypb_peer_wait(self.flags.data_ptr(), self.world, self.state.data_ptr(), int(lag),
+                                        _cabi.stream_ptr(self.buf.device))
+        _cabi.check(rc, "ypb_peer_wait")
+
+    def gathered(self, batch_per_rank: int, max_det: int, cols: int):
+        """(world*B, max_det, cols) rows and (world*B,) int32 counts of the last waited-for launch (views / small copy)."""
+        g = self.buf[: self.world * self.slot].view(self.world, self.slot)[:, : self.numel]
+        rows = g[:, : self.nrow].reshape(self.world * batch_per_rank, max_det, cols)
+        count = g[:, self.nrow:].contiguous().view(torch.int32).reshape(self.world * batch_per_rank)
+        return rows, count

@@ -102,11 +102,12 @@ class NmsPlan:
     scratch: torch.Tensor = None
     keep_alive: tuple = ()
     xforms: torch.Tensor = None  # (B, 8) ypb_scale_xform array when the gather rescales to the original images
+    peers: object = None         # dist.PeerGather when the kernel also stores the results into every peer's buffer
 
 
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
-              scale_padding: bool = True) -> NmsPlan:
+              scale_padding: bool = True, peer_gather_group=None) -> NmsPlan:
     rows_cap = anchors * nc if multi_label else anchors
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))
@@ -116,7 +117,14 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     scratch = _scratch(device, nbytes)
     cols = 6 + extra
     nrow = batch * max_det * cols
-    packed = torch.empty((nrow + batch,), dtype=torch.float32, device=device)
+    peers = None
+    if peer_gather_group is not None:  # results land in slot `rank` of the node-wide symmetric buffer (dist.PeerGather)
+        from .dist import PeerGather
+
+        peers = PeerGather(nrow + batch, nrow, device, None if peer_gather_group is True else peer_gather_group)
+        packed = peers.my_packed
+    else:
+        packed = torch.empty((nrow + batch,), dtype=torch.float32, device=device)
     rows = packed[:nrow].view(batch, max_det, cols)
     count = packed[nrow:].view(torch.int32)
     idx = torch.empty((batch, max_det), dtype=torch.int64, device=device)
@@ -134,7 +142,9 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         xforms = torch.zeros((max(batch, 1), 8), dtype=torch.float32, device=device)
         xforms[:, 0] = 1.0
         o.scale_xforms, o.scale_padding = xforms.data_ptr(), int(bool(scale_padding))
-    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,), xforms)
+    if peers is not None:
+        peers.bind(o)
+    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,), xforms, peers)
 
 
 def set_transforms(plan: NmsPlan, img1_shape, orig_shapes, ratio_pads=None) -> None:

@@ -18,7 +18,8 @@ from .nms import _greedy_threshold
 class HeadPostProcessor:
     def __init__(self, nc: int, strides, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                  agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
-                 max_wh: int = 7680, reg_max: int = 16, rotated: bool = False, scale_to_original: bool = False):
+                 max_wh: int = 7680, reg_max: int = 16, rotated: bool = False, scale_to_original: bool = False,
+                 peer_gather_group=None):
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
         self.nc, self.strides, self.reg_max = nc, tuple(float(s) for s in strides), reg_max
@@ -28,6 +29,9 @@ class HeadPostProcessor:
         # fold construct_result's scale_boxes / regularize_rboxes (detect/predict.py:120, obb/predict.py:59-60) into the
         # gather; the per-image transforms are loaded with set_image_shapes() before enqueue() / graph replay
         self.scale_to_original = bool(scale_to_original)
+        # multi-GPU: True / a process group = one-sided gather of every rank's results over NVLink peer memory
+        # (dist.PeerGather); plans are then created collectively, in the same order on every rank
+        self.peer_gather_group = peer_gather_group
         self._plans = {}
         self.last = None
 
@@ -43,7 +47,8 @@ class HeadPostProcessor:
                 rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(self.iou_thres)
             plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
                                     iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
-                                    self.multi_label, rule, self.classes, with_scale=self.scale_to_original)
+                                    self.multi_label, rule, self.classes, with_scale=self.scale_to_original,
+                                    peer_gather_group=self.peer_gather_group)
             # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
             nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
                                                           plan.params.max_det, plan.params.max_nms, plan.params.rule)
@@ -94,6 +99,18 @@ class HeadPostProcessor:
             if after is not None:
                 after()
         return graph
+
+    def wait_gather(self, lag: int = 0):
+        """Enqueue the consumer-side wait of the one-sided gather (graph-capturable): lag=0 for the last enqueued batch,
+        lag=k for the batch k enqueues back on this processor (pipelined: never stalls on a slower rank)."""
+        if self.last is None or self.last.peers is None:
+            raise RuntimeError("no peer gather attached to the last plan")
+        self.last.peers.wait(lag)
+
+    def gathered(self):
+        """(world*B, max_det, cols) rows and (world*B,) counts of all ranks for the last waited-for batch."""
+        pl = self.last
+        return pl.peers.gathered(pl.rows.shape[0], pl.rows.shape[1], pl.rows.shape[2])
 
     def __call__(self, levels, angle_logits=None, return_idxs: bool = False):
         return engine.split_results(self.enqueue(levels, angle_logits), return_idxs)
