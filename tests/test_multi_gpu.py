@@ -1,0 +1,73 @@
+"""One-sided peer-memory gather (dist.PeerGather, ypb_nms_out.peer_*) against an NCCL all_gather of the same results.
+
+Needs >= 2 GPUs on the box (skipped otherwise; the world-size-2 host logic is covered on CPU with gloo in
+tests/test_host_logic.py).  Two ranks, one process per GPU, each post-processes its own shard through
+HeadPostProcessor(peer_gather_group=True) - eagerly, with lag, and replayed from a CUDA graph."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SCRIPT = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, os.environ["YPB_ROOT"])
+    import torch, torch.distributed as dist
+    from ultralytics_pro_b200 import dist as ypb_dist
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+    from ultralytics_pro_b200.synth import HeadConfig, make_head_batch
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device("cuda", rank); torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = HeadConfig("mg", 160, (8, 16, 32), 80, 4, objects=6)
+    B = 4
+    pp = HeadPostProcessor(cfg.nc, cfg.strides, 0.25, 0.7, peer_gather_group=True)
+    st = torch.cuda.Stream(dev)
+    def check(levels, tag):
+        pl = pp.last
+        torch.cuda.synchronize(dev); dist.barrier()
+        ref = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref, pl.packed.clone())
+        rr, rc = ypb_dist.split_packed(ref, B, pl.rows.shape[1], pl.rows.shape[2])
+        gr, gc = pp.gathered()
+        valid = (torch.arange(pl.rows.shape[1], device=dev)[None, :] < rc[:, None]).unsqueeze(-1)
+        assert torch.equal(rc, gc), (tag, rc.tolist(), gc.tolist())
+        assert torch.equal(rr * valid, gr * valid), tag
+        assert int(rc.sum()) > 0, tag
+    with torch.cuda.stream(st):
+        for step in range(3):  # eager, different data each step and rank
+            lv = [t.to(dev) for t in make_head_batch(cfg, batch=B, seed=10 * step + rank, first_image=rank * B)[0]]
+            pp.enqueue(lv); pp.wait_gather(0)
+            check(lv, f"eager {step}")
+        lv = [t.to(dev) for t in make_head_batch(cfg, batch=B, seed=77 + rank)[0]]
+        g = pp.capture(lv, after=lambda: pp.wait_gather(1))
+        for _ in range(4):
+            g.replay()
+        pp.wait_gather(0)
+        check(lv, "graph, lag 1 + drain")
+    print("ok", rank, flush=True)
+    dist.barrier(); torch.cuda.synchronize(dev); os._exit(0)
+''')
+
+
+def test_peer_gather_matches_nccl_all_gather(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "peer.py"
+    script.write_text(SCRIPT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577", WORLD_SIZE="2", YPB_ROOT=root)
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    try:
+        outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs), outs
