@@ -43,35 +43,48 @@ scale_rows_kernel(const ScaleArgs s) {
   }
 }
 
-// Pose.kpts_decode (head.py:1254-1273) over the whole (B, nk*ndim, A) tensor: thread = VEC consecutive anchors of one
-// channel, 128-bit streaming loads/stores; HBM-bound (2 * B * C * A * s bytes).
+// Pose.kpts_decode (head.py:1254-1273) over the whole (B, nk*ndim, A) tensor: thread = VEC consecutive anchors of
+// KPT_CH channels (KPT_CH independent 128-bit streaming loads in flight); HBM-bound (2 * B * C * A * s bytes).
+constexpr int KPT_CH = 8;
+
 template <int DT, int VEC>
 __global__ void __launch_bounds__(256)
 kpts_decode_kernel(const __grid_constant__ KptArgs a) {
   using T = typename DType<DT>::type;
   const int grp = blockIdx.x * blockDim.x + threadIdx.x;
   if (grp >= a.group_start[a.num_levels]) return;
-  const int c = blockIdx.y, b = blockIdx.z;
+  const int c0 = blockIdx.y * KPT_CH, b = blockIdx.z;
   int l = 0;
 #pragma unroll
   for (int i = 1; i < YPB_MAX_LEVELS; ++i)
     if (i < a.num_levels && grp >= a.group_start[i]) l = i;
   const int a_local = (grp - a.group_start[l]) * VEC;
   const int a_glob = a.anchor_start[l] + a_local;
-  const T* src = static_cast<const T*>(a.src) + static_cast<long long>(b) * a.sb + static_cast<long long>(c) * a.sc + a_glob;
-  T* dst = static_cast<T*>(a.dst) + (static_cast<long long>(b) * a.channels + c) * a.anchors + a_glob;
-  const int d = c % a.ndim;
+  const T* src = static_cast<const T*>(a.src) + static_cast<long long>(b) * a.sb + a_glob;
+  T* dst = static_cast<T*>(a.dst) + static_cast<long long>(b) * a.channels * a.anchors + a_glob;
   const int W = a.w[l];
   const float stride = a.stride[l];
-  int gy = a_local / W, gx = a_local - gy * W;
-  Pack<T, VEC> p = load_pack<T, VEC>(src), q;
+  const int gy0 = a_local / W, gx0 = a_local - gy0 * W;
+  Pack<T, VEC> p[KPT_CH];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const float ax = DType<DT>::rnd(static_cast<float>(gx) + 0.5f), ay = DType<DT>::rnd(static_cast<float>(gy) + 0.5f);
-    q.v[i] = DType<DT>::from_f(kpt_value<DT>(DType<DT>::to_f(p.v[i]), d, ax, ay, stride));
-    if (++gx == W) { gx = 0; ++gy; }
+  for (int j = 0; j < KPT_CH; ++j)
+    if (c0 + j < a.channels) p[j] = load_pack<T, VEC>(src + static_cast<long long>(c0 + j) * a.sc);
+#pragma unroll
+  for (int j = 0; j < KPT_CH; ++j) {
+    const int c = c0 + j;
+    if (c < a.channels) {
+      const int d = c % a.ndim;
+      int gy = gy0, gx = gx0;
+      Pack<T, VEC> q;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float ax = DType<DT>::rnd(static_cast<float>(gx) + 0.5f), ay = DType<DT>::rnd(static_cast<float>(gy) + 0.5f);
+        q.v[i] = DType<DT>::from_f(kpt_value<DT>(DType<DT>::to_f(p[j].v[i]), d, ax, ay, stride));
+        if (++gx == W) { gx = 0; ++gy; }
+      }
+      store_pack<T, VEC>(dst + static_cast<long long>(c) * a.anchors, q);
+    }
   }
-  store_pack<T, VEC>(dst, q);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -85,7 +98,7 @@ kpts_decode_kernel(const __grid_constant__ KptArgs a) {
 // Tiles that cannot see the box are zero-filled without touching the prototypes.  The kernel is bound by the HBM write
 // of the (n, H, W) uint8 result: algorithmic bytes = n*H*W.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int MT_W = 128, MT_H = 32, MT_THREADS = 256;
+constexpr int MT_W = 128, MT_H = 128, MT_THREADS = 256;  // 16 KB of output per CTA: the grid is not CTA-launch bound
 
 // ATen UpSampleKernel / UpSample.h area_pixel_compute_source_index (align_corners=False) + guard_index_and_lambda
 __device__ __forceinline__ void bilinear_tap(float scale, int dst, int in_size, int& i0, int& i1, float& w0, float& w1) {
@@ -103,7 +116,9 @@ process_mask_kernel(const __grid_constant__ MaskArgs a) {
   using T = typename DType<DT>::type;
   extern __shared__ __align__(16) float sm_f[];
   float* coef = sm_f;                 // [C]
-  float* reg = sm_f + ((a.C + 3) & ~3);  // [rh][rw] prototype-resolution values of this tile's footprint
+  float4* xtap = reinterpret_cast<float4*>(sm_f + ((a.C + 3) & ~3));  // [MT_W] (x0, x1 as int bits, w0, w1) of every tile column
+  float4* ytap = xtap + MT_W;                                          // [MT_H] the same for every tile row
+  float* reg = reinterpret_cast<float*>(ytap + MT_H);  // [rh][rw] prototype-resolution values of this tile's footprint
   __shared__ int s_img[2];
   const int tid = threadIdx.x;
   const int d = blockIdx.z;
@@ -145,64 +160,96 @@ process_mask_kernel(const __grid_constant__ MaskArgs a) {
     empty = !(static_cast<float>(X1) >= bx1 && static_cast<float>(X0) < bx2 && static_cast<float>(Y1) >= by1 && static_cast<float>(Y0) < by2);
 
   uint8_t* out = a.out + static_cast<long long>(d) * a.ih * a.iw;
-  const int row = tid >> 3, seg = tid & 7;  // 32 rows x 8 segments of 16 pixels
-  const int Y = Y0 + row, XS = X0 + seg * 16;
+  const int row = tid >> 3, seg = tid & 7;  // 32 rows x 8 segments of 16 pixels per pass, MT_H / 32 passes
+  const int XS = X0 + seg * 16;
   const bool vec_ok = (a.iw & 15) == 0;
 
   if (!empty) {
     const float* cp = a.coeffs + static_cast<long long>(b) * a.coef_image_stride + static_cast<long long>(k) * a.coef_row_stride;
     for (int c = tid; c < a.C; c += MT_THREADS) coef[c] = cp[c];
+    if (tid < MT_W) {  // bilinear taps of every column / row of the tile, computed once
+      int i0, i1; float w0, w1;
+      bilinear_tap(a.scale_w, min(X0 + tid, a.iw - 1), a.win_w, i0, i1, w0, w1);
+      xtap[tid] = make_float4(__int_as_float(i0), __int_as_float(i1), w0, w1);
+    } else if (tid < MT_W + MT_H) {
+      int i0, i1; float w0, w1;
+      bilinear_tap(a.scale_h, min(Y0 + tid - MT_W, a.ih - 1), a.win_h, i0, i1, w0, w1);
+      ytap[tid - MT_W] = make_float4(__int_as_float(i0), __int_as_float(i1), w0, w1);
+    }
     __syncthreads();
     const T* pr = static_cast<const T*>(a.protos) + static_cast<long long>(b) * a.proto_sb;
     for (int i = tid; i < rh * rw; i += MT_THREADS) {
       const int y = i / rw, x = i - y * rw;
       const int py = ry0 + y + a.win_top, px = rx0 + x + a.win_left;
+      if (a.crop_mode == YPB_MASK_CROP_PROTO) {
+        // ops.py:486 masks * bool: outside the box the product is zero whatever the mask value - skip the dot product
+        const float fx = static_cast<float>(px), fy = static_cast<float>(py);
+        if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) { reg[i] = 0.f; continue; }
+      }
       const T* p = pr + static_cast<long long>(py) * a.mw + px;
       float acc = 0.f;
-#pragma unroll 8
-      for (int c = 0; c < a.C; ++c) acc = fmaf(coef[c], DType<DT>::to_f(p[static_cast<long long>(c) * a.proto_sc]), acc);
-      if (a.crop_mode == YPB_MASK_CROP_PROTO) {
-        const float fx = static_cast<float>(px), fy = static_cast<float>(py);
-        const bool in = fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2;
-        acc = __fmul_rn(acc, in ? 1.f : 0.f);  // ops.py:486 masks * bool
+      int c = 0;
+      for (; c + 16 <= a.C; c += 16) {  // 16 independent loads in flight, then the sum in channel order
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = DType<DT>::to_f(p[static_cast<long long>(c + j) * a.proto_sc]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc = fmaf(coef[c + j], v[j], acc);
       }
+      for (; c < a.C; ++c) acc = fmaf(coef[c], DType<DT>::to_f(p[static_cast<long long>(c) * a.proto_sc]), acc);
       reg[i] = acc;
     }
     __syncthreads();
   }
 
-  if (Y > Y1 || XS > X1) return;
-  uint32_t w4[4] = {0u, 0u, 0u, 0u};
-  if (!empty) {
-    int y0, y1;
-    float wy0, wy1;
-    bilinear_tap(a.scale_h, Y, a.win_h, y0, y1, wy0, wy1);
-    const float* r0 = reg + (y0 - ry0) * rw - rx0;
-    const float* r1 = reg + (y1 - ry0) * rw - rx0;
-    const bool row_in = a.crop_mode != YPB_MASK_CROP_OUTPUT || (static_cast<float>(Y) >= by1 && static_cast<float>(Y) < by2);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int X = XS + i;
-      if (X > X1) break;
-      int x0, x1;
-      float wx0, wx1;
-      bilinear_tap(a.scale_w, X, a.win_w, x0, x1, wx0, wx1);
-      // ATen upsample_bilinear2d: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)
-      const float top = __fadd_rn(__fmul_rn(wx0, r0[x0]), __fmul_rn(wx1, r0[x1]));
-      const float bot = __fadd_rn(__fmul_rn(wx0, r1[x0]), __fmul_rn(wx1, r1[x1]));
-      float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
-      if (a.crop_mode == YPB_MASK_CROP_OUTPUT) {
-        const bool in = row_in && static_cast<float>(X) >= bx1 && static_cast<float>(X) < bx2;
-        v = __fmul_rn(v, in ? 1.f : 0.f);
-      }
-      if (v > 0.f) w4[i >> 2] |= 1u << ((i & 3) * 8);  // ops.py:513 masks.gt_(0.0).byte()
-    }
+  if (XS > X1) return;
+  const int XE = min(XS + 15, X1);
+  // a segment / row whose taps all fall outside the crop box is zero (PROTO mode: the footprint values are zero there)
+  bool seg_live = !empty;
+  if (seg_live && a.crop_mode == YPB_MASK_CROP_PROTO) {
+    const float4 tl = xtap[XS - X0], tr = xtap[XE - X0];
+    seg_live = static_cast<float>(__float_as_int(tr.y) + a.win_left) >= bx1 && static_cast<float>(__float_as_int(tl.x) + a.win_left) < bx2;
+  } else if (seg_live) {
+    seg_live = static_cast<float>(XE) >= bx1 && static_cast<float>(XS) < bx2;
   }
-  uint8_t* o = out + static_cast<long long>(Y) * a.iw + XS;
-  if (vec_ok && XS + 15 <= X1) {
-    __stcs(reinterpret_cast<uint4*>(o), make_uint4(w4[0], w4[1], w4[2], w4[3]));
-  } else {
-    for (int i = 0; i < 16 && XS + i <= X1; ++i) o[i] = static_cast<uint8_t>((w4[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+  for (int Y = Y0 + row; Y <= Y1; Y += MT_THREADS / 8) {
+    uint32_t w4[4] = {0u, 0u, 0u, 0u};
+    bool live = seg_live;
+    float4 ty = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      ty = ytap[Y - Y0];
+      if (a.crop_mode == YPB_MASK_CROP_PROTO)
+        live = static_cast<float>(__float_as_int(ty.y) + a.win_top) >= by1 && static_cast<float>(__float_as_int(ty.x) + a.win_top) < by2;
+      else
+        live = static_cast<float>(Y) >= by1 && static_cast<float>(Y) < by2;
+    }
+    if (live) {
+      const float wy0 = ty.z, wy1 = ty.w;
+      const float* r0 = reg + (__float_as_int(ty.x) - ry0) * rw - rx0;
+      const float* r1 = reg + (__float_as_int(ty.y) - ry0) * rw - rx0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int X = XS + i;
+        if (X > X1) break;
+        const float4 tx = xtap[X - X0];
+        const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
+        // ATen upsample_bilinear2d: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)
+        const float top = __fadd_rn(__fmul_rn(tx.z, r0[x0]), __fmul_rn(tx.w, r0[x1]));
+        const float bot = __fadd_rn(__fmul_rn(tx.z, r1[x0]), __fmul_rn(tx.w, r1[x1]));
+        float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+        if (a.crop_mode == YPB_MASK_CROP_OUTPUT) {
+          const bool in = static_cast<float>(X) >= bx1 && static_cast<float>(X) < bx2;
+          v = __fmul_rn(v, in ? 1.f : 0.f);
+        }
+        if (v > 0.f) w4[i >> 2] |= 1u << ((i & 3) * 8);  // ops.py:513 masks.gt_(0.0).byte()
+      }
+    }
+    uint8_t* o = out + static_cast<long long>(Y) * a.iw + XS;
+    if (vec_ok && XS + 15 <= X1) {
+      __stcs(reinterpret_cast<uint4*>(o), make_uint4(w4[0], w4[1], w4[2], w4[3]));
+    } else {
+      for (int i = 0; i < 16 && XS + i <= X1; ++i) o[i] = static_cast<uint8_t>((w4[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+    }
   }
 }
 
@@ -290,7 +337,7 @@ cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
     return static_cast<int>(s < in ? s : in);
   };
   const int rh = span(a.scale_h, a.ih, MT_H, a.win_h), rw = span(a.scale_w, a.iw, MT_W, a.win_w);
-  const size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float);
+  const size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float) + (MT_W + MT_H) * sizeof(float4);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   dim3 grid((a.iw + MT_W - 1) / MT_W, (a.ih + MT_H - 1) / MT_H, a.total);
   if (grid.z > 65535u || grid.y > 65535u) return cudaErrorInvalidConfiguration;
@@ -312,7 +359,7 @@ cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
 cudaError_t launch_kpts_decode(const KptArgs& a, int dtype, int vec, cudaStream_t st) {
   const int groups = a.group_start[a.num_levels];
   if (groups <= 0 || a.batch <= 0 || a.channels <= 0) return cudaSuccess;
-  dim3 grid((groups + 255) / 256, a.channels, a.batch);
+  dim3 grid((groups + 255) / 256, (a.channels + KPT_CH - 1) / KPT_CH, a.batch);
 #define YPB_KPT(DT, V) kpts_decode_kernel<DT, V><<<grid, 256, 0, st>>>(a)
   if (dtype == YPB_F32) { if (vec == 4) YPB_KPT(YPB_F32, 4); else YPB_KPT(YPB_F32, 1); }
   else if (dtype == YPB_F16) { if (vec == 8) YPB_KPT(YPB_F16, 8); else YPB_KPT(YPB_F16, 1); }

@@ -273,7 +273,7 @@ def process_masks_batched(protos, rows, counts, shape, upsample: bool = True):
     for n in counts:
         offs.append(offs[-1] + int(n))
     total = offs[-1]
-    offsets = torch.tensor(offs, dtype=torch.int32).pin_memory().to(rows.device, non_blocking=True)
+    offsets = torch.tensor(offs, dtype=torch.int32, device=rows.device)  # small pageable H2D: staged by the driver, no pinned alloc
     out_hw = (int(shape[0]), int(shape[1])) if upsample else (mh, mw)
     ratios = (_f32(mw / shape[1]), _f32(mh / shape[0]))
     coeffs = rows[:, :, 6:]

@@ -105,7 +105,7 @@ def match_batch(iouv, rows: torch.Tensor, count: torch.Tensor | None, labels: to
     labels = _f32c(labels.to(rows.device))
     if labels.shape != (offs[-1], 5):
         raise ValueError(f"labels must be ({offs[-1]}, 5), got {tuple(labels.shape)}")
-    offsets = torch.tensor(offs, dtype=torch.int32).pin_memory().to(rows.device, non_blocking=True)
+    offsets = torch.tensor(offs, dtype=torch.int32, device=rows.device)
     max_m = max(int(c) for c in label_counts)
     need = nthr * offs[-1] * 4
     ws = engine._scratch(rows.device, need) if nthr * max_m * 4 > 200 * 1024 else None
