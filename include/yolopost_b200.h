@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 3
+#define YPB_ABI_VERSION 4
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -97,6 +97,15 @@ typedef struct {
   int32_t rule;         /* ypb_nms_rule; FAST_PROBIOU == rotated=True (boxes stay xywh + angle = last channel) */
   int32_t rows_cap;     /* candidate rows reserved per image in the workspace (A, or A*nc for multi_label) */
   const uint32_t* class_mask; /* device bitmask of allowed classes (nms.py:127-131) or NULL */
+  /* The exporter's NMSModel flavour (engine/exporter.py:1389-1481; ypb_nms_from_dense only):
+   *   nms_box_divisor > 0 : suppression runs on multiplier * (box / divisor) [+ cls * max_wh, with max_wh = multiplier]
+   *                         (exporter.py:1437-1452: boxes normalised by the larger image side, class offset in units of 1/nc);
+   *   boxes_xyxy          : columns 0..3 of the prediction are already corners (the export decode, head.py:189) - no nms.py:86;
+   *   pad_output          : rows past the kept count are written as zeros (exporter.py:1478-1479 zero padding). */
+  float nms_box_divisor;
+  float nms_box_multiplier;
+  int32_t boxes_xyxy;
+  int32_t pad_output;
 } ypb_nms_params;
 
 /* Per-image letterbox transform, values exactly as the reference computes them on the host:

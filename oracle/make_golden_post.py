@@ -98,6 +98,48 @@ def main():
     make_kpts(ref)
     make_masks(ref)
     make_matching(ref)
+    make_nms_model(ref)
+
+
+def make_nms_model(ref):
+    """NMSModel.forward of the live reference (engine/exporter.py:1389-1481) fed by a stub model that returns a decoded tensor."""
+    import types
+
+    from ultralytics.engine.exporter import NMSModel
+
+    from tests.helpers import make_scores_unique
+    from oracle.postproc_oracle import decode_oracle
+    from ultralytics_pro_b200.synth import HeadConfig, make_head_batch
+
+    out_path = os.path.join(ROOT, "tests", "golden", "post", "nms_model.npz")
+    blob, meta = {}, []
+    for name, imgsz, nc, extra, kw in [("detect", 160, 80, 0, dict(conf=0.25, iou=0.45, max_det=20, agnostic_nms=False)),
+                                       ("detect_agnostic", 160, 80, 0, dict(conf=0.1, iou=0.6, max_det=300, agnostic_nms=True)),
+                                       ("segment_extras", 128, 20, 32, dict(conf=0.25, iou=0.7, max_det=50, agnostic_nms=False))]:
+        cfg = HeadConfig(name, imgsz, (8, 16, 32), nc, 2, objects=7)
+        levels, _ = make_head_batch(cfg, batch=2, seed=len(meta) + 11)
+        y = decode_oracle(levels, cfg.strides, nc, xyxy=True)  # the export decode: corners (head.py:189)
+        y = make_scores_unique(y, nc, kw["conf"])
+        if extra:
+            y = torch.cat([y, torch.randn(2, extra, y.shape[2], generator=torch.Generator().manual_seed(5))], 1)
+
+        class Stub(torch.nn.Module):
+            task = "detect"
+            names = {i: str(i) for i in range(nc)}
+
+            def forward(self, x):
+                return y.clone()
+
+        args = types.SimpleNamespace(format="torchscript", dynamic=False, batch=2, opset=None, int8=False, **kw)
+        with torch.inference_mode():
+            out = NMSModel(Stub(), args)(torch.zeros(2, 3, imgsz, imgsz))
+        i = len(meta)
+        blob[f"n{i}_pred"], blob[f"n{i}_out"] = y.numpy(), out.numpy()
+        meta.append(dict(name=name, imgsz=imgsz, nc=nc, extra=extra, **kw))
+        print(name, tuple(out.shape), int((out[..., 4] > 0).sum()))
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
 
 def make_matching(ref):

@@ -211,3 +211,29 @@ def match_predictions_oracle(pred_classes, true_classes, iou, iouv):
                 taken.add(best_label[d])
                 correct[d, i] = True
     return correct
+
+
+def nms_model_oracle(pred, image_hw, nc, conf, iou, max_det, agnostic_nms=False):
+    """engine/exporter.py:1417-1481 (NMSModel.forward after self.model(x); detect / segment / pose, non-TF formats): torch CPU,
+    torchvision.ops.nms on the normalised + class-offset boxes.  pred (B, 4+nc+extra, A), boxes xyxy.  -> (B, max_det', 6+extra)."""
+    import torch
+    from torchvision.ops import nms
+
+    p = pred.transpose(-1, -2)
+    extra = p.shape[-1] - 4 - nc
+    boxes, scores, extras = p.split([4, nc, extra], dim=2)
+    scores, classes = scores.max(dim=-1)
+    max_det = min(p.shape[1], max_det)
+    out = torch.zeros(p.shape[0], max_det, 6 + extra, dtype=p.dtype)
+    mult = 1 / max(nc, 1)
+    side = torch.tensor(tuple(image_hw), dtype=p.dtype).max()
+    for i in range(p.shape[0]):
+        keep_mask = scores[i] > conf
+        box, score, cls, ext = boxes[i][keep_mask], scores[i][keep_mask], classes[i][keep_mask], extras[i][keep_mask]
+        nb = mult * (box / side)
+        if not agnostic_nms:
+            nb = nb + (cls.view(-1, 1) * mult)
+        keep = nms(nb, score, iou)[:max_det]
+        dets = torch.cat([box[keep], score[keep].view(-1, 1), cls[keep].view(-1, 1).to(out.dtype), ext[keep]], dim=-1)
+        out[i, : dets.shape[0]] = dets
+    return out

@@ -116,6 +116,7 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   s.rule = p->rule; s.rows_cap = p->rows_cap; s.multi_label = p->multi_label;
   s.cls_bits = ypb::bits_for(p->nc); s.anchor_bits = ypb::bits_for(anchors);
   s.iou_thr = p->iou_thres_eff; s.max_wh = p->max_wh;
+  s.box_div = p->nms_box_divisor; s.box_mult = p->nms_box_multiplier; s.pad_zero = p->pad_output;
   s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
   s.cand_ang = p->rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
   s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
@@ -212,6 +213,7 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     return fail(YPB_ERR_INVALID_ARGUMENT, "fused path carries extra=%d only (pass riders for more)", rotated ? 1 : 0);
   }
   if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
+  if (p->nms_box_divisor != 0.f || p->boxes_xyxy) return fail(YPB_ERR_UNSUPPORTED, "the exporter flavour (nms_box_divisor / boxes_xyxy) is served by ypb_nms_from_dense");
   ypb::Workspace w = ypb::carve_workspace(workspace, head->batch, g.anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
   if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
     return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
@@ -300,6 +302,8 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   if (ypb::bits_for(pred->anchors) + ypb::bits_for(p->nc) > 31)
     return fail(YPB_ERR_UNSUPPORTED, "anchor and class index do not fit the 31-bit row id");
   if (!pred->ptr && pred->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "prediction pointer is NULL");
+  if (p->nms_box_divisor < 0.f || (p->nms_box_divisor > 0.f && rotated))
+    return fail(YPB_ERR_UNSUPPORTED, "normalised NMS boxes (exporter flavour) are built for the axis-aligned rule only");
   ypb::Workspace w = ypb::carve_workspace(workspace, pred->batch, pred->anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
   if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
     return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
@@ -310,6 +314,7 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   ypb::FilterArgs f{};
   f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
   f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+  f.boxes_xyxy = p->boxes_xyxy;
   e = ypb::launch_filter_from_dense(*pred, f, st);
   if (e != cudaSuccess) return cuda_fail(e, "filter_from_dense");
   ypb::SuppressArgs s = suppress_args(p, out, w, pred->batch, pred->anchors);

@@ -365,6 +365,7 @@ struct FilterArgs {
   int32_t* tile_list;
   uint8_t* tile_flags;
   int tile_cap;
+  int boxes_xyxy;   // filter_from_dense: columns 0..3 are corners already (no nms.py:86 conversion)
   int fuse_decode;  // 1: the class-scan kernel decodes the boxes of its own survivors; 0: separate decode_tiles kernel
   uint64_t* keys;
   float4* cand_box;
@@ -404,6 +405,9 @@ struct SuppressArgs {
   // optional fused construct_result rescale of the kept rows (ypb_nms_out.scale_*)
   const ypb_scale_xform* scale_xforms;
   int scale_padding;
+  // exporter NMSModel flavour (ypb_nms_params.nms_box_*): suppression on box_mult * (box / box_div); zero padding
+  float box_div, box_mult;
+  int pad_zero;
   // one-sided gather over peer memory (ypb_nms_out.peer_*)
   int num_peers, my_rank;
   float* peer_rows[YPB_MAX_PEERS];

@@ -525,7 +525,7 @@ filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_
         f.cand_box[slot] = make_float4(cx, cy, w, h);
         f.cand_ang[slot] = D::to_f(p[static_cast<long long>(d.channels - 1) * sc]);  // nms.py:146 x[:, -1:]
       } else {
-        f.cand_box[slot] = corners_in_dtype<DT>(cx, cy, w, h);  // nms.py:86
+        f.cand_box[slot] = f.boxes_xyxy ? make_float4(cx, cy, w, h) : corners_in_dtype<DT>(cx, cy, w, h);  // nms.py:86
       }
     }
   }

@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   // ---- fast path: class-wise walk (class-aware greedy rule, everything fits shared memory) ----------------------------
   bool done = false;
   if constexpr (RULE == YPB_NMS_GREEDY) {
-    if (a.max_wh > 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && (1 << a.cls_bits) <= CW_CLASS_MAX &&
+    if (a.max_wh > 0.f && a.box_div == 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && (1 << a.cls_bits) <= CW_CLASS_MAX &&
         a.anchor_bits <= 20 && n > 0) {
       const int r = classwise_greedy(sm, a, ka, n, cand_box, gthr);
       if (r >= 0) { kept_n = r; kk = reinterpret_cast<const uint64_t*>(sm.cbox); done = true; }
@@ -723,7 +723,11 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
         if (q == 0) me = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, ang);  // nms.py:146
       } else {
-        ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // nms.py:149
+        float4 nb = bx;
+        if (a.box_div > 0.f)  // exporter.py:1444: multiplier * (box / max(imgsz))
+          nb = make_float4(__fmul_rn(a.box_mult, __fdiv_rn(bx.x, a.box_div)), __fmul_rn(a.box_mult, __fdiv_rn(bx.y, a.box_div)),
+                           __fmul_rn(a.box_mult, __fdiv_rn(bx.z, a.box_div)), __fmul_rn(a.box_mult, __fdiv_rn(bx.w, a.box_div)));
+        ob = make_float4(__fadd_rn(nb.x, off), __fadd_rn(nb.y, off), __fadd_rn(nb.z, off), __fadd_rn(nb.w, off));  // nms.py:149
         area = box_area(ob);
       }
     }
@@ -914,6 +918,10 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
       }
       o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
     }
+  }
+  if (a.pad_zero && a.out_rows) {  // exporter.py:1478-1479: rows past the kept count are zeros
+    float* o = a.out_rows + static_cast<long long>(b) * a.max_det * cols;
+    for (int i = kept_n * cols + tid; i < a.max_det * cols; i += NT) o[i] = 0.f;
   }
   if (a.rider && a.out_rows) {
     // Segment / Pose riders (head.py:837 mask coefficients, head.py:1252 decoded keypoints): only the kept anchors'

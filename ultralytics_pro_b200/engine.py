@@ -107,7 +107,8 @@ class NmsPlan:
 
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
-              scale_padding: bool = True, peer_gather_group=None) -> NmsPlan:
+              scale_padding: bool = True, peer_gather_group=None, nms_box=None, boxes_xyxy: bool = False,
+              pad_output: bool = False) -> NmsPlan:
     rows_cap = anchors * nc if multi_label else anchors
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))
@@ -135,6 +136,9 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     p.nc, p.extra, p.max_det, p.max_nms = nc, extra, max_det, max_nms
     p.max_wh, p.multi_label, p.rule, p.rows_cap = float(max_wh), int(bool(multi_label)), rule, rows_cap
     p.class_mask = mask.data_ptr() if mask is not None else None
+    if nms_box is not None:  # exporter NMSModel flavour: suppression on multiplier * (box / divisor)
+        p.nms_box_divisor, p.nms_box_multiplier = float(nms_box[0]), float(nms_box[1])
+    p.boxes_xyxy, p.pad_output = int(bool(boxes_xyxy)), int(bool(pad_output))
     o = _cabi.NmsOut()
     o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
     xforms = None
