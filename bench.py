@@ -235,6 +235,18 @@ def run_ours(args):
     # each lane's all_gather can be captured inside that lane's CUDA graph and replayed concurrently with the others
     # (on ONE communicator, replays from several streams have no defined cross-rank order and can deadlock)
     gather_mode = args.gather if world > 1 else "none"
+    if gather_mode == "peer":
+        # collective probe: if the symmetric-memory mapping is unavailable on this box on ANY rank, all ranks fall back together
+        ok = 1
+        try:
+            ypb_dist.PeerGather(1024, 1000, dev)
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"[bench] rank {rank}: peer-memory gather unavailable ({type(exc).__name__}: {exc}); falling back to NCCL\n")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            gather_mode = "nccl-eager"
     lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager")
                    else [None] * LANES)
     graph_gather = gather_mode == "nccl"

@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 4
+#define YPB_ABI_VERSION 5
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -106,6 +106,9 @@ typedef struct {
   float nms_box_multiplier;
   int32_t boxes_xyxy;
   int32_t pad_output;
+  /* Optional device array of B per-image confidence thresholds replacing conf_thres (ypb_nms_from_dense only): the
+   * second pass of the end2end top-k (head.py:193-214 Detect.postprocess) thresholds each image at its own K-th score. */
+  const float* conf_per_image;
 } ypb_nms_params;
 
 /* Per-image letterbox transform, values exactly as the reference computes them on the host:

@@ -99,6 +99,37 @@ def main():
     make_masks(ref)
     make_matching(ref)
     make_nms_model(ref)
+    make_topk(ref)
+
+
+def make_topk(ref):
+    """Detect.postprocess of the live reference (nn/modules/head.py:193-214) on tie-free sigmoid scores."""
+    out_path = os.path.join(ROOT, "tests", "golden", "post", "topk.npz")
+    g = torch.Generator().manual_seed(31)
+    blob, meta = {}, []
+    for name, b, a, nc, max_det in [("v10_small", 2, 525, 80, 300), ("few_anchors", 3, 40, 5, 300), ("nc1", 2, 300, 1, 50)]:
+        boxes = torch.rand(b, a, 4, generator=g) * 160
+        scores = torch.sigmoid(torch.randn(b, a, nc, generator=g) * 2 - 3)
+        flat = scores.reshape(b, -1)
+        for i in range(b):  # make every score of an image distinct
+            srt, idx = torch.sort(flat[i])
+            for _ in range(4):
+                dup = torch.zeros_like(srt, dtype=torch.bool)
+                dup[1:] = srt[1:] <= srt[:-1]
+                if not dup.any():
+                    break
+                srt = torch.where(dup, torch.nextafter(torch.roll(srt, 1), torch.full_like(srt, 2.0)), srt)
+                srt = torch.cummax(srt, 0).values
+            flat[i, idx] = srt
+        preds = torch.cat([boxes, flat.reshape(b, a, nc)], -1)
+        out = ref.Detect.postprocess(preds.clone(), max_det, nc)
+        i = len(meta)
+        blob[f"t{i}_preds"], blob[f"t{i}_out"] = preds.numpy(), out.numpy()
+        meta.append(dict(name=name, max_det=max_det, nc=nc))
+        print(name, tuple(out.shape))
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
 
 def make_nms_model(ref):

@@ -237,3 +237,17 @@ def nms_model_oracle(pred, image_hw, nc, conf, iou, max_det, agnostic_nms=False)
         dets = torch.cat([box[keep], score[keep].view(-1, 1), cls[keep].view(-1, 1).to(out.dtype), ext[keep]], dim=-1)
         out[i, : dets.shape[0]] = dets
     return out
+
+
+def detect_postprocess_oracle(preds, max_det, nc):
+    """nn/modules/head.py:193-214 (Detect.postprocess) restated as ONE global ranking: the K = min(max_det, A) best
+    (anchor, class) pairs by score (stable: lower flat index first), rows box(4), score, class.  Equal to the reference's
+    two-stage top-k whenever scores are tie-free (see ultralytics_pro_b200.head.detect_postprocess)."""
+    import torch
+
+    b, a, _ = preds.shape
+    k = min(max_det, a)
+    flat = preds[..., 4:].reshape(b, a * nc)
+    order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :k]
+    rows = torch.arange(b)[:, None]
+    return torch.cat([preds[rows, order // nc, :4], flat[rows, order][..., None], (order % nc)[..., None].to(preds.dtype)], -1)

@@ -97,7 +97,7 @@ int check_params(const ypb_nms_params* p, const ypb_nms_out* out) {
     return fail(YPB_ERR_INVALID_ARGUMENT, "nc=%d extra=%d max_det=%d max_nms=%d rows_cap=%d invalid", p->nc, p->extra,
                 p->max_det, p->max_nms, p->rows_cap);
   if (p->rule < YPB_NMS_GREEDY || p->rule > YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown rule %d", p->rule);
-  if (!(p->conf_thres >= 0.f) || !(p->iou_thres_eff >= 0.f) || p->iou_thres_eff > 1.f)
+  if ((!(p->conf_thres >= 0.f) && !p->conf_per_image && !p->boxes_xyxy) || !(p->iou_thres_eff >= 0.f) || p->iou_thres_eff > 1.f)
     return fail(YPB_ERR_INVALID_ARGUMENT, "conf/iou threshold outside [0,1] (nms.py:59-60)");
   if (!out->rows || !out->count) return fail(YPB_ERR_INVALID_ARGUMENT, "out.rows / out.count is NULL");
   if (out->num_peers < 0 || out->num_peers > YPB_MAX_PEERS) return fail(YPB_ERR_INVALID_ARGUMENT, "num_peers=%d outside [0,%d]", out->num_peers, YPB_MAX_PEERS);
@@ -213,7 +213,8 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     return fail(YPB_ERR_INVALID_ARGUMENT, "fused path carries extra=%d only (pass riders for more)", rotated ? 1 : 0);
   }
   if (p->rule == YPB_NMS_FAST_BOXIOU) return fail(YPB_ERR_UNSUPPORTED, "FAST_BOXIOU is only reachable through ypb_nms_boxes");
-  if (p->nms_box_divisor != 0.f || p->boxes_xyxy) return fail(YPB_ERR_UNSUPPORTED, "the exporter flavour (nms_box_divisor / boxes_xyxy) is served by ypb_nms_from_dense");
+  if (p->nms_box_divisor != 0.f || p->boxes_xyxy || p->conf_per_image)
+    return fail(YPB_ERR_UNSUPPORTED, "nms_box_divisor / boxes_xyxy / conf_per_image are served by ypb_nms_from_dense");
   ypb::Workspace w = ypb::carve_workspace(workspace, head->batch, g.anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);
   if (!workspace || w.bytes > workspace_bytes || !aligned(workspace, 256))
     return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
@@ -314,7 +315,7 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   ypb::FilterArgs f{};
   f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
   f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-  f.boxes_xyxy = p->boxes_xyxy;
+  f.boxes_xyxy = p->boxes_xyxy; f.conf_per_image = p->conf_per_image;
   e = ypb::launch_filter_from_dense(*pred, f, st);
   if (e != cudaSuccess) return cuda_fail(e, "filter_from_dense");
   ypb::SuppressArgs s = suppress_args(p, out, w, pred->batch, pred->anchors);

@@ -366,6 +366,7 @@ struct FilterArgs {
   uint8_t* tile_flags;
   int tile_cap;
   int boxes_xyxy;   // filter_from_dense: columns 0..3 are corners already (no nms.py:86 conversion)
+  const float* conf_per_image;  // filter_from_dense: per-image threshold replacing `conf`, or null
   int fuse_decode;  // 1: the class-scan kernel decodes the boxes of its own survivors; 0: separate decode_tiles kernel
   uint64_t* keys;
   float4* cand_box;

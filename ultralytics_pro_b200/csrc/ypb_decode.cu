@@ -485,7 +485,7 @@ filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_
   const int a = blockIdx.x * DEC_THREADS + threadIdx.x;
   const int b = blockIdx.y;
   const int nc = f.nc;
-  const float conf = f.conf;
+  const float conf = f.conf_per_image ? f.conf_per_image[b] : f.conf;
   const bool active = a < d.anchors;
   const T* p = static_cast<const T*>(d.ptr) + static_cast<long long>(b) * d.stride_b + static_cast<long long>(a) * d.stride_a;
   const T* pc = p + 4 * d.stride_c;

@@ -108,8 +108,8 @@ class NmsPlan:
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
               scale_padding: bool = True, peer_gather_group=None, nms_box=None, boxes_xyxy: bool = False,
-              pad_output: bool = False) -> NmsPlan:
-    rows_cap = anchors * nc if multi_label else anchors
+              pad_output: bool = False, conf_per_image: torch.Tensor | None = None, rows_cap: int | None = None) -> NmsPlan:
+    rows_cap = (anchors * nc if multi_label else anchors) if rows_cap is None else int(rows_cap)
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))
     max_det = max(1, min(int(max_det), max_nms))
@@ -139,6 +139,8 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     if nms_box is not None:  # exporter NMSModel flavour: suppression on multiplier * (box / divisor)
         p.nms_box_divisor, p.nms_box_multiplier = float(nms_box[0]), float(nms_box[1])
     p.boxes_xyxy, p.pad_output = int(bool(boxes_xyxy)), int(bool(pad_output))
+    if conf_per_image is not None:
+        p.conf_per_image = conf_per_image.data_ptr()
     o = _cabi.NmsOut()
     o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
     xforms = None
@@ -148,7 +150,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         o.scale_xforms, o.scale_padding = xforms.data_ptr(), int(bool(scale_padding))
     if peers is not None:
         peers.bind(o)
-    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask,), xforms, peers)
+    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image), xforms, peers)
 
 
 def set_transforms(plan: NmsPlan, img1_shape, orig_shapes, ratio_pads=None) -> None:

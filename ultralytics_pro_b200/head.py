@@ -104,6 +104,35 @@ def pose_kpts_decode(self, bs: int, kpts: torch.Tensor) -> torch.Tensor:
     return decode_keypoints(kpts.view(bs, self.nk, -1), hw, [float(s) for s in self.stride], self.kpt_shape)
 
 
+def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch.Tensor:
+    """``Detect.postprocess`` drop-in (head.py:193-214, the end2end / v10 top-k): preds (B, A, 4+nc) -> (B, K, 6) rows
+    ``box(4 as given), score, class`` of the K = min(max_det, A) best (anchor, class) pairs, best first.
+
+    The reference takes the K anchors with the largest class maximum and then the K best pairs among their K*nc scores;
+    for tie-free scores that is the global top-K over all pairs (an anchor outside the first set cannot own a pair that
+    beats K anchors' maxima).  Two passes of the filter + sort kernels, no suppression: pass 1 ranks the anchors by their
+    maximum and yields each image's K-th value T; pass 2 emits every pair with score >= T (at most K*nc) and ranks them.
+    Index arithmetic between the passes (picking T, nextafter) is torch plumbing on the device; nothing is read back."""
+    _cabi.require_cuda(preds, "detect_postprocess")
+    if preds.dim() != 3 or preds.shape[2] != 4 + nc:
+        raise ValueError(f"preds must be (B, A, {4 + nc}), got {tuple(preds.shape)}")
+    b, a, _ = preds.shape
+    k = min(int(max_det), a)
+    dev = preds.device
+    if b == 0 or k == 0:
+        return torch.zeros((b, k, 6), dtype=preds.dtype, device=dev)
+    dense = preds.transpose(1, 2)  # (B, 4+nc, A) view; the kernels take any strides
+    ninf = float("-inf")
+    first = engine.make_plan(dev, b, a, nc, 0, ninf, 1.0, k, a, 0.0, False, _cabi.RULE_GREEDY, boxes_xyxy=True)
+    engine.run_from_dense(dense, first)
+    kth = first.rows[:, k - 1, 4].contiguous()
+    thr = torch.nextafter(kth, torch.full_like(kth, ninf))  # score > thr  <=>  score >= K-th anchor maximum
+    second = engine.make_plan(dev, b, a, nc, 0, 0.0, 1.0, k, k * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
+                              conf_per_image=thr, rows_cap=k * nc)
+    engine.run_from_dense(dense, second)
+    return second.rows.to(preds.dtype)
+
+
 def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                           agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                           max_wh: int = 7680, reg_max: int = 16, angle_logits: torch.Tensor | None = None,

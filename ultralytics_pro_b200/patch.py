@@ -188,6 +188,13 @@ def install() -> list:
             _saved[f"ultralytics.nn.modules.head.{cname}._inference"] = (c, "_inference", c.__dict__["_inference"])
             c._inference = _wrap_inference(c.__dict__["_inference"], our_head.detect_inference)
             done.append(f"ultralytics.nn.modules.head.{cname}._inference")
+        for cname in _HEAD_CLASSES:  # head.py:193 end2end top-k (staticmethod)
+            c = getattr(ref_head, cname, None)
+            if c is None or "postprocess" not in c.__dict__:
+                continue
+            _saved[f"ultralytics.nn.modules.head.{cname}.postprocess"] = (c, "postprocess", c.__dict__["postprocess"])
+            c.postprocess = _wrap_static(c.postprocess, our_head.detect_postprocess)
+            done.append(f"ultralytics.nn.modules.head.{cname}.postprocess")
         for cname in _POSE_CLASSES:  # head.py:1254, :1322, :1390, :1459
             c = getattr(ref_head, cname, None)
             if c is None or "kpts_decode" not in c.__dict__:
