@@ -131,6 +131,28 @@ def main():
     out.append({"row": "8f-4 box_iou + match_predictions, B=64 x 300 detections x 40 labels x 10 IoU levels", "kernel": "match_predictions_kernel",
                 "ms": ms, "bound": "latency (one CTA per image)", "pairs": B * 300 * M, "cpu_oracle_ms": c, "cpu_sample": "numpy oracle, 1 image x 64"})
 
+    # ---- 6. exporter NMSModel flavour and the end2end top-k, on the decoded C2 batch ---------------------------------------
+    from ultralytics_pro_b200.export_nms import nms_model_postprocess
+    from ultralytics_pro_b200.head import detect_postprocess
+
+    dl = [lv.to(dev) for lv in make_head_batch(cfg, batch=B, seed=9)[0]]
+    y_xyxy = decode_head(dl, cfg.strides, cfg.nc, xyxy=True)
+    ms = gpu_ms(lambda: nms_model_postprocess(y_xyxy, (640, 640), cfg.nc, 0.25, 0.45, 300), reps=30)
+    y_cpu = y_xyxy[:4].cpu()
+    c = cpu_ms(lambda: ro.nms_model_oracle(y_cpu, (640, 640), cfg.nc, 0.25, 0.45, 300), 3.0) * (B / 4)
+    out.append({"row": "8f-3 exporter NMSModel post-processing, B=64 x 8400 anchors x 80 classes -> (64, 300, 6) padded, no host sync",
+                "kernels": "filter_from_dense_kernel + sort_suppress_kernel (normalised-offset mode)", "ms": ms,
+                "bound": "hbm (one pass over the 172 MB of scores) + latency", "achieved_gbs": B * 80 * A * 4 / ms / 1e6,
+                "cpu_oracle_ms": c, "cpu_sample": "torch CPU oracle (torchvision nms), 4 images x 16"})
+    preds = y_xyxy.permute(0, 2, 1)
+    ms = gpu_ms(lambda: detect_postprocess(preds, 300, cfg.nc), reps=20)
+    p_cpu = preds[:4].cpu()
+    c = cpu_ms(lambda: ro.detect_postprocess_oracle(p_cpu, 300, cfg.nc), 3.0) * (B / 4)
+    out.append({"row": "8f-4 Detect.postprocess end2end top-k, B=64 x 8400 anchors x 80 classes -> (64, 300, 6)",
+                "kernels": "2 x (filter_from_dense_kernel + sort_suppress_kernel)", "ms": ms,
+                "bound": "hbm (two passes over the 172 MB of scores) + the per-image radix sort of 8400 keys",
+                "achieved_gbs": 2 * B * 80 * A * 4 / ms / 1e6, "cpu_oracle_ms": c, "cpu_sample": "torch CPU oracle (one stable sort), 4 images x 16"})
+
     for o in out:
         print(json.dumps(o))
 
