@@ -155,6 +155,15 @@ int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32_t angle
     return fail(YPB_ERR_UNSUPPORTED, "out dtype %d != head dtype %d (Detect._inference keeps the dtype, head.py:169)", out_dtype, head->dtype);
   if (out_stride_c < g.anchors) return fail(YPB_ERR_INVALID_ARGUMENT, "out channel stride < anchors");
   if (head->batch == 0) return YPB_OK;
+  // 16-bit heads: 4 anchors (64-bit accesses) per thread instead of 8.  The 8-wide form needs 168-192 registers (3 CTAs
+  // per SM, 1.3 waves) and is latency-bound at half the bytes; YPB_DENSE16_VEC=8 restores it for comparison.
+  static const int dense16_vec = [] { const char* e = std::getenv("YPB_DENSE16_VEC"); return (e && e[0] == '8') ? 8 : 4; }();
+  if (dtype_size(head->dtype) == 2 && vec == 8 && dense16_vec == 4) {
+    vec = 4;
+    int gs = 0;
+    for (int l = 0; l < head->num_levels; ++l) { g.group_start[l] = gs; gs += head->level_h[l] * head->level_w[l] / vec; }
+    for (int l = head->num_levels; l <= YPB_MAX_LEVELS; ++l) g.group_start[l] = gs;
+  }
   cudaError_t e = ypb::launch_decode_dense(g, head->dtype, angle, angle_is_logit, append_angle, xyxy, out, out_dtype,
                                            out_stride_b, out_stride_c, vec, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "ypb_decode_dense");

@@ -596,9 +596,11 @@ cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* ang
     if (vec == 1) YPB_DD(YPB_F32, 1);
   } else if (in_dtype == YPB_BF16) {
     if (vec == 8) YPB_DD(YPB_BF16, 8);
+    if (vec == 4) YPB_DD(YPB_BF16, 4);
     if (vec == 1) YPB_DD(YPB_BF16, 1);
   } else if (in_dtype == YPB_F16) {
     if (vec == 8) YPB_DD(YPB_F16, 8);
+    if (vec == 4) YPB_DD(YPB_F16, 4);
     if (vec == 1) YPB_DD(YPB_F16, 1);
   }
 #undef YPB_DD
