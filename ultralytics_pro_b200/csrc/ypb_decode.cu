@@ -18,6 +18,9 @@ namespace ypb {
 #ifndef YPB_SCAN_DEPTH
 #define YPB_SCAN_DEPTH 8
 #endif
+#ifndef YPB_SCAN_DEPTH16
+#define YPB_SCAN_DEPTH16 16
+#endif
 constexpr int DEC_THREADS = YPB_DEC_THREADS;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -286,7 +289,7 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
             pidx[j] = (cc & gt) | (pidx[j] & ~gt);
           }
         };
-        stream_rows<TI, VEC>(csrc, cs, nc, visit);
+        stream_rows<TI, VEC, YPB_SCAN_DEPTH16>(csrc, cs, nc, visit);  // 16-bit rows: half the bytes per load, twice the loads in flight
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           m[2 * j] = Packed2<DT_IN>::lo(pm[j]);   m[2 * j + 1] = Packed2<DT_IN>::hi(pm[j]);
