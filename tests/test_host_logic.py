@@ -189,3 +189,45 @@ def test_patch_points_exist_in_reference_when_mounted():
     finally:
         patch.uninstall()
     assert ref.nms.non_max_suppression.__name__ == "non_max_suppression" and not hasattr(ref.nms.non_max_suppression, "__wrapped__")
+
+
+def test_new_entry_points_validate_arguments_before_any_launch():
+    """The 8f / multi-GPU entry points reject bad arguments on the host (no device needed) with the documented codes."""
+    import ctypes as C
+
+    from ultralytics_pro_b200 import _cabi
+
+    lib = _cabi.load()
+    err = lambda: lib.ypb_last_error_string().decode()  # noqa: E731
+    xf = _cabi.ScaleXform()
+    assert lib.ypb_scale_rows(None, 0, 4, 1, 0, None, None, C.byref(xf), _cabi.BOXES_XYXY, 0, 0, None, 0, 0, 0, 0, None) == 0  # empty: OK
+    assert lib.ypb_scale_rows(16, 0, 4, 1, 3, None, None, C.byref(xf), 17, 0, 0, None, 0, 0, 0, 0, None) == -1 and "box mode" in err()
+    assert lib.ypb_scale_rows(16, 0, 4, 1, 3, None, None, None, _cabi.BOXES_XYXY, 0, 0, None, 0, 0, 0, 0, None) == -1 and "transform" in err()
+    assert lib.ypb_scale_rows(16, 0, 5, 1, 3, None, None, C.byref(xf), _cabi.BOXES_XYWHR, 0, 2, None, 0, 0, 0, 0, None) == -1 and "angle_col" in err()
+    g = _cabi.HeadDesc()
+    g.num_levels, g.batch, g.dtype = 1, 1, _cabi.YPB_F32
+    g.level_h[0], g.level_w[0], g.level_stride[0] = 4, 4, 8.0
+    assert lib.ypb_kpts_decode(C.byref(g), None, 0, 16, 7, 3, None, None) == -1 and "ndim" in err()   # 7 channels, ndim 3
+    assert lib.ypb_kpts_decode(C.byref(g), None, 0, 16, 6, 3, None, None) == -1 and "NULL" in err()
+    pd = _cabi.ProtosDesc()
+    pd.dtype, pd.channels, pd.mh, pd.mw, pd.stride_c = _cabi.YPB_F32, 32, 8, 8, 64
+    args = [None, 0, 32, None, 0, 4, None, 1, 0, 16, 16, 0, 0, 8, 8, _cabi.MASK_CROP_PROTO, 1.0, 1.0, None, None]
+    assert lib.ypb_process_mask(C.byref(pd), *args) == 0                                            # no detections: OK
+    bad = list(args); bad[13] = 9                                                                  # window taller than the grid
+    assert lib.ypb_process_mask(C.byref(pd), *bad) == -1 and "window" in err()
+    bad = list(args); bad[15] = 7
+    assert lib.ypb_process_mask(C.byref(pd), *bad) == -1 and "crop mode" in err()
+    thr = (C.c_float * 2)(0.5, 0.75)
+    assert lib.ypb_match_predictions(None, 0, 6, 5, 1, 0, None, None, None, 0, 0, None, 0, None, thr, 2, None, None, 0, None) == 0
+    assert lib.ypb_match_predictions(None, 0, 6, 5, 1, 4, None, None, None, 0, 0, None, 0, None, thr, 0, None, None, 0, None) == -1
+    assert lib.ypb_peer_wait(None, 2, None, 0, None) == -1
+    # ABI structs the header documents
+    assert C.sizeof(_cabi.ScaleXform) == 32 and _cabi.MAX_PEERS == 8
+    out = _cabi.NmsOut()
+    out.num_peers = 9
+    p = _cabi.NmsParams()
+    p.nc, p.max_det, p.max_nms, p.rows_cap, p.conf_thres, p.iou_thres_eff = 1, 1, 1, 1, 0.25, 0.5
+    out.rows = out.count = 1  # non-NULL dummies: validation stops at num_peers before any use
+    d = _cabi.DenseDesc()
+    d.dtype, d.batch, d.channels, d.anchors = _cabi.YPB_F32, 1, 5, 4
+    assert lib.ypb_nms_from_dense(C.byref(d), C.byref(p), C.byref(out), None, 0, None) == -1 and "num_peers" in err()
