@@ -231,3 +231,27 @@ def test_new_entry_points_validate_arguments_before_any_launch():
     d = _cabi.DenseDesc()
     d.dtype, d.batch, d.channels, d.anchors = _cabi.YPB_F32, 1, 5, 4
     assert lib.ypb_nms_from_dense(C.byref(d), C.byref(p), C.byref(out), None, 0, None) == -1 and "num_peers" in err()
+
+
+def test_c_program_links_against_the_library(tmp_path):
+    """A plain C99 translation unit includes the header, links the shared library and exercises the host-only entry points."""
+    import shutil
+    import subprocess
+
+    from ultralytics_pro_b200 import build
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    lib = build.build_library()
+    exe = tmp_path / "c_abi_smoke"
+    src = os.path.join(ROOT, "tests", "c_abi_smoke.c")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", str(exe),
+           "-L", os.path.dirname(lib), "-lyolopost_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    subprocess.run(cmd, check=True, capture_output=True)
+    env = dict(os.environ)
+    cudart = "/usr/local/cuda/lib64"
+    env["LD_LIBRARY_PATH"] = cudart + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c abi ok" in out.stdout
