@@ -255,3 +255,36 @@ def test_c_program_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "c abi ok" in out.stdout
+
+
+def test_host_scalars_of_the_result_ops_match_the_oracle():
+    """letterbox gain / pad scalars (ops.py:120-127, :580-587) and the scale_masks window (ops.py:544-559): the host side of
+    the drop-ins computes them in Python - they must equal the oracle's (which is pinned to the live reference)."""
+    import struct
+
+    from oracle import result_ops_oracle as ro
+    from ultralytics_pro_b200 import ops
+
+    f32 = lambda v: struct.unpack("f", struct.pack("f", v))[0]  # noqa: E731
+    cases = [((640, 640), (480, 640, 3), None), ((384, 640), (1080, 1920), None), ((640, 480), (1333, 999), None),
+             ((1024, 1024), (3000, 4000, 3), None), ((640, 640), (500, 375), ((1.28, 1.28), (80.5, 0.25)))]
+    for img1, img0, rp in cases:
+        gain, pad, cpad = ro.letterbox_scalars(img1, img0, rp)
+        x = ops.letterbox_transform(img1, img0, rp)
+        assert (x.gain, x.pad_x, x.pad_y, x.cpad_x, x.cpad_y) == (f32(gain), f32(pad[0]), f32(pad[1]), f32(cpad[0]), f32(cpad[1]))
+        assert (x.img_w, x.img_h) == (float(img0[1]), float(img0[0]))
+    for mh, mw, shape in [(160, 160, (480, 640)), (40, 40, (120, 213)), (40, 40, (333, 250)), (96, 160, (720, 1280))]:
+        top, left, bottom, right = ro.scale_masks_window(mh, mw, shape)
+        assert ops._scale_masks_window(mh, mw, shape) == (top, left, bottom - top, right - left)
+
+
+def test_new_drop_ins_refuse_cpu_tensors():
+    from ultralytics_pro_b200 import export_nms, head, ops, val
+
+    z = torch.zeros
+    for call in (lambda: ops.clip_boxes(z(2, 4), (10, 10)), lambda: ops.scale_coords((8, 8), z(2, 3), (4, 4)),
+                 lambda: ops.regularize_rboxes(z(2, 5)), lambda: ops.process_mask(z(4, 8, 8), z(1, 4), z(1, 4), (32, 32)),
+                 lambda: head.decode_keypoints(z(1, 6, 16), [(4, 4)], [8], (2, 3)), lambda: head.detect_postprocess(z(1, 16, 9), 5, 5),
+                 lambda: val.match_iou_matrix([0.5], z(2), z(2), z(2, 2)), lambda: export_nms.nms_model_postprocess(z(1, 9, 16), (32, 32), 5, 0.25, 0.5, 5)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
