@@ -439,6 +439,13 @@ def run_ours(args):
              "frac": dense_bytes / (t_dense * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": dense_bytes}
     del y
 
+    # ---- the drop-in boundary: the reference's OWN call sequence (Detect._inference -> non_max_suppression,
+    #      predictor.py:335-336 + detect/predict.py:54) through the wrappers patch.install() binds, on a stub module carrying
+    #      Detect's attributes (head.py:70-93).  two_call = dense decode kernel + NMS-from-dense kernels; fused = the lazily
+    #      decoded tensor hands the level tensors to the fused head->NMS kernels.  Wall clock per call INCLUDING the count
+    #      read-back the list-of-tensors return type forces (one stream synchronisation per call, like the reference).
+    dropin = _bench_dropin(dev, cfg, sets, NSETS, min(K, 200))
+
     # ---- end to end through the public API with HOST buffers: H2D of the head, decode+NMS, D2H of rows+counts ---------
     KE = min(K, 30)
     host_sets = [[lv.cpu().pin_memory() for lv in s] for s in sets[:2]]
@@ -516,6 +523,8 @@ def run_ours(args):
                             "synchronised every step"},
             "roofline": roofline,
             "decode_dense": dense,
+            "dropin_two_call": dropin["two_call"],
+            "dropin_fused": dropin["fused"],
             "latency_b1_ms_p50": lat[len(lat) // 2],
             "latency_b1_ms_p90": lat[int(len(lat) * 0.9)],
             "latency_b1_ms_p50_cached_plan": lat_pp[len(lat_pp) // 2],
@@ -532,6 +541,62 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         os._exit(0)
     return 0
+
+
+class _StubDetect:
+    """Attribute surface of the reference's ``Detect`` (head.py:70-93) without the convolutions; the methods bound below
+    are the wrappers ``patch.install()`` puts on the reference's classes."""
+
+    dynamic = export = end2end = xyxy = training = False
+    format = None
+    shape = None
+    max_det = 300
+
+    def __init__(self, cfg, dev):
+        self.nc, self.nl, self.reg_max, self.no = cfg.nc, len(cfg.strides), cfg.reg_max, cfg.no
+        self.stride = torch.tensor([float(s) for s in cfg.strides], device=dev)
+        self.anchors = self.strides = torch.empty(0)
+
+
+def _bench_dropin(dev, cfg, sets, nsets, reps):
+    import types
+
+    from ultralytics_pro_b200 import head, lazy, nms, patch
+
+    def boom(*a, **k):
+        raise RuntimeError("reference function called on the GPU path")
+
+    mod = _StubDetect(cfg, dev)
+    mod._inference = types.MethodType(patch._wrap_inference(boom, head.detect_inference), mod)
+    nms_fn = patch._wrap_nms(boom, nms.non_max_suppression)
+    out = {}
+    B = sets[0][0].shape[0]
+    for name, lazy_on in (("two_call", False), ("fused", True)):
+        lazy.ENABLED = lazy_on
+
+        def call(i):
+            with torch.inference_mode():
+                y = mod._inference(sets[i % nsets])
+                return nms_fn((y, sets[i % nsets]), cfg.conf, cfg.iou, max_det=cfg.max_det)
+
+        for i in range(5):
+            res = call(i)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for i in range(reps):
+            res = call(i)
+        b.record()
+        torch.cuda.synchronize(dev)
+        wall = (time.perf_counter() - t0) / reps
+        out[name] = {"imgs_per_s": B / wall, "ms_per_call": wall * 1e3, "ms_per_call_cuda_events": a.elapsed_time(b) / reps,
+                     "calls": reps, "kept_last_call": int(sum(r.shape[0] for r in res)),
+                     "path": ("LazyDecoded -> ypb_nms_from_head (scan_classes + decode_tiles + sort_suppress)" if lazy_on
+                              else "ypb_decode_dense + ypb_nms_from_dense (filter_from_dense + sort_suppress)"),
+                     "includes": "python + ctypes + kernels + the count D2H and stream sync of every call"}
+    lazy.ENABLED = False
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 5
+#define YPB_ABI_VERSION 6
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -180,6 +180,22 @@ YPB_API int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32
                      int32_t xyxy, void* out, int32_t out_dtype, int64_t out_stride_b, int64_t out_stride_c,
                      void* stream);
 
+/* The two pieces of the decode a head may call on its own (YOLOEDetect.forward_lrpc, head.py:1777-1813, does):
+ *   DFL.forward (nn/modules/block.py:250-253): x (B, 4*reg_max, A) -> out (B, 4, A) = sum_k k * softmax_k, same dtype;
+ *     channel index = side*reg_max + bin; anchors contiguous (stride 1), strides in elements.
+ *   Detect.decode_bboxes (head.py:184-191) == dist2bbox(dim=1) (utils/tal.py:367-376): dist (B, 4, A) l,t,r,b and
+ *     anchor_points (1 or B, 2, A; any strides - the module caches a transposed (A, 2) tensor,
+ *     head.py:164; anchor_stride_b = 0 broadcasts) -> out (B, 4, A) cx,cy,w,h (xywh=1) or x1,y1,x2,y2;
+ *     with angle != NULL ((B, 1, A), already activated) it is OBB.decode_bboxes (head.py:1040-1042) == dist2rbox(dim=1)
+ *     (utils/tal.py:385-403) and xywh is ignored.  Every step is rounded to `dtype` like the reference's tensor ops. */
+YPB_API int ypb_dfl_expectation(const void* x, int32_t dtype, int32_t batch, int32_t reg_max, int32_t anchors,
+                                int64_t stride_b, int64_t stride_c, void* out, int64_t out_stride_b, int64_t out_stride_c,
+                                void* stream);
+YPB_API int ypb_dist2bbox(const void* dist, int64_t dist_stride_b, int64_t dist_stride_c, const void* anchor_points,
+                          int64_t anchor_stride_b, int64_t anchor_stride_c, int64_t anchor_stride_a, const void* angle, int64_t angle_stride_b,
+                          int32_t dtype, int32_t batch, int32_t anchors, int32_t xywh, void* out, int64_t out_stride_b,
+                          int64_t out_stride_c, void* stream);
+
 /* Fused decode -> confidence filter -> sort/top-k -> suppression -> gather, reading the head once and never writing
  * the dense tensor.  `value_dtype` is the dtype the dense tensor WOULD have had (scores and boxes are rounded to it
  * so results are bit-identical to ypb_decode_dense followed by ypb_nms_from_dense). */
@@ -274,6 +290,18 @@ YPB_API size_t ypb_nms_boxes_workspace_bytes(int32_t n);
 YPB_API int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t box_dim, int32_t rule,
                   float iou_thres_eff, int64_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* Packs the kept rows of a batch back to back in image order (the list-of-tensors return type of nms.py:159-161 is then
+ * ONE split on the host): rows (B, max_det, cols) fp32 / idx (B, max_det) int64 / count (B) as written by the NMS calls ->
+ * out_rows (>= sum count, cols), out_idx (>= sum count), out_offsets (B+1) exclusive prefix of count; any output may be NULL. */
+YPB_API int ypb_compact_results(const float* rows, const int64_t* idx, const int32_t* count, int32_t batch, int32_t max_det,
+                                int32_t cols, float* out_rows, int64_t* out_idx, int32_t* out_offsets, void* stream);
+
+/* utils/metrics.py:54-75 box_iou (box_dim 4: x1,y1,x2,y2; eps 1e-7 in the denominator) and metrics.py:251-284
+ * batch_probiou (box_dim 5: x,y,w,h,r) as free functions: boxes1 (n, box_dim), boxes2 (m, box_dim) fp32 row-major ->
+ * out (n, m) fp32.  The suppression kernels evaluate the same device functions pair by pair without this matrix. */
+YPB_API int ypb_pairwise_iou(const float* boxes1, int32_t n, const float* boxes2, int32_t m, int32_t box_dim, float* out,
+                             void* stream);
 
 /* ---- result-side steps that follow NMS in the reference's predictors / validators -------- */
 

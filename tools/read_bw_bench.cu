@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
@@ -130,8 +131,9 @@ __global__ void __launch_bounds__(256) rows_bulk_kernel(const float* __restrict_
   if (acc == 0x12345678) *sink = acc;
 }
 
-int main() {
-  const int B = 64, C = 144, A = 6400 + 1600 + 400, NC = 80;  // level tensors concatenated per image for simplicity: rows of A
+int main(int argc, char** argv) {
+  const int B = 64, C = 144, NC = 80;
+  const int A = argc > 1 ? atoi(argv[1]) : 6400 + 1600 + 400;  // 4200 emulates the bf16 rows (8400 x 2 B)  // level tensors concatenated per image for simplicity: rows of A
   const long long img_stride = (long long)C * A;
   const size_t bytes = (size_t)B * C * A * 4;
   const int NBUF = 3;
@@ -182,6 +184,7 @@ int main() {
       char nm[96]; snprintf(nm, sizeof nm, "rows bulk TW=%d RT=%d ST=%d grid=%d", TW, RT, ST, GRID);                   \
       TIME(nm, rows_bytes, (rows_bulk_kernel<TW, RT, ST><<<GRID, 256, sm>>>(P + 64LL * A, A, NC, img_stride, B, sink))); \
     } while (0)
+    if (A == 8400) {
     BULK(240, 16, 4, 148);
     BULK(240, 16, 8, 148);
     BULK(240, 16, 4, 296);
@@ -192,6 +195,27 @@ int main() {
     BULK(1200, 8, 4, 148);
     BULK(240, 80, 2, 148);
     BULK(400, 40, 3, 148);
+    BULK(80, 80, 4, 148);
+    BULK(80, 80, 6, 148);
+    BULK(80, 80, 4, 296);
+    BULK(80, 80, 3, 444);
+    BULK(160, 80, 3, 148);
+    BULK(160, 80, 2, 296);
+    } else if (A == 4200) {
+    BULK(168, 16, 4, 148);
+    BULK(280, 16, 4, 148);
+    BULK(280, 16, 6, 148);
+    BULK(280, 16, 4, 296);
+    BULK(600, 8, 4, 148);
+    BULK(168, 80, 2, 148);
+    BULK(168, 80, 3, 148);
+    BULK(280, 40, 3, 148);
+    BULK(40, 80, 6, 148);
+    BULK(40, 80, 8, 296);
+    BULK(40, 80, 4, 444);
+    BULK(120, 80, 4, 148);
+    BULK(120, 80, 3, 296);
+    }
   }
   printf("done\n");
   return 0;

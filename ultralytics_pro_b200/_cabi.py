@@ -6,6 +6,7 @@ raises.  PyTorch is used only for device memory (caching allocator) and the curr
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import struct
 
@@ -17,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -39,6 +40,10 @@ EXPORTS = (
     "ypb_process_mask",
     "ypb_match_predictions",
     "ypb_peer_wait",
+    "ypb_dfl_expectation",
+    "ypb_dist2bbox",
+    "ypb_pairwise_iou",
+    "ypb_compact_results",
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
@@ -209,6 +214,17 @@ def load():
                                           C.c_size_t, C.c_void_p]
     lib.ypb_peer_wait.restype = C.c_int
     lib.ypb_peer_wait.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ypb_dfl_expectation.restype = C.c_int
+    lib.ypb_dfl_expectation.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.ypb_dist2bbox.restype = C.c_int
+    lib.ypb_dist2bbox.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.ypb_pairwise_iou.restype = C.c_int
+    lib.ypb_pairwise_iou.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ypb_compact_results.restype = C.c_int
+    lib.ypb_compact_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib
@@ -260,6 +276,7 @@ def largest_f32_not_above(v: float) -> float:
     return struct.unpack("f", struct.pack("I", bits))[0]
 
 
+@functools.lru_cache(maxsize=256)
 def round_to_dtype(v: float, dt: torch.dtype) -> float:
     """Value of the Python scalar after torch casts it to `dt` for a tensor-scalar comparison (nms.py:76,115,121)."""
     return float(torch.tensor(v, dtype=torch.float64).to(dt).to(torch.float64))

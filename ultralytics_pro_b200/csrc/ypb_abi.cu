@@ -170,6 +170,40 @@ int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32_t angle
   return YPB_OK;
 }
 
+int ypb_dfl_expectation(const void* x, int32_t dtype, int32_t batch, int32_t reg_max, int32_t anchors, int64_t stride_b,
+                        int64_t stride_c, void* out, int64_t out_stride_b, int64_t out_stride_c, void* stream) {
+  if (!dtype_ok(dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  if (batch < 0 || anchors < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d anchors=%d invalid", batch, anchors);
+  if (reg_max != 16) return fail(YPB_ERR_UNSUPPORTED, "reg_max=%d: only 16 is built (block.py:232)", reg_max);
+  if (batch == 0 || anchors == 0) return YPB_OK;
+  if (!x || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "x / out is NULL");
+  if (batch > 65535) return fail(YPB_ERR_UNSUPPORTED, "batch %d > 65535", batch);
+  cudaError_t e = ypb::launch_dfl(x, dtype, batch, anchors, stride_b, stride_c, out, out_stride_b, out_stride_c,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_dfl_expectation");
+  return YPB_OK;
+}
+
+int ypb_dist2bbox(const void* dist, int64_t dist_stride_b, int64_t dist_stride_c, const void* anchor_points,
+                  int64_t anchor_stride_b, int64_t anchor_stride_c, int64_t anchor_stride_a, const void* angle, int64_t angle_stride_b, int32_t dtype,
+                  int32_t batch, int32_t anchors, int32_t xywh, void* out, int64_t out_stride_b, int64_t out_stride_c,
+                  void* stream) {
+  if (!dtype_ok(dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  if (batch < 0 || anchors < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d anchors=%d invalid", batch, anchors);
+  if (batch == 0 || anchors == 0) return YPB_OK;
+  if (!dist || !anchor_points || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "dist / anchor_points / out is NULL");
+  if (batch > 65535) return fail(YPB_ERR_UNSUPPORTED, "batch %d > 65535", batch);
+  ypb::Dist2BoxArgs d{};
+  d.dist = dist; d.dsb = dist_stride_b; d.dsc = dist_stride_c;
+  d.anchor_points = anchor_points; d.asb = anchor_stride_b; d.asc = anchor_stride_c; d.asa = anchor_stride_a;
+  d.angle = angle; d.angle_sb = angle_stride_b;
+  d.batch = batch; d.anchors = anchors; d.xywh = xywh;
+  d.out = out; d.osb = out_stride_b; d.osc = out_stride_c;
+  cudaError_t e = ypb::launch_dist2bbox(d, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_dist2bbox");
+  return YPB_OK;
+}
+
 int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
                       const ypb_nms_params* p, const ypb_nms_out* out, void* workspace, size_t workspace_bytes,
                       void* stream) {
@@ -364,6 +398,28 @@ int ypb_nms_boxes(const float* boxes, const float* scores, int32_t n, int32_t bo
   s.out_rows = nullptr; s.out_idx = reinterpret_cast<long long*>(keep); s.out_count = keep_count; s.idx_as_row = 1;
   e = ypb::launch_sort_suppress(s, st);
   if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  return YPB_OK;
+}
+
+int ypb_compact_results(const float* rows, const int64_t* idx, const int32_t* count, int32_t batch, int32_t max_det,
+                        int32_t cols, float* out_rows, int64_t* out_idx, int32_t* out_offsets, void* stream) {
+  if (batch < 0 || max_det < 1 || cols < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "batch=%d max_det=%d cols=%d invalid", batch, max_det, cols);
+  if (batch == 0) return YPB_OK;
+  if (!count || (out_rows && !rows) || (out_idx && !idx)) return fail(YPB_ERR_INVALID_ARGUMENT, "count / rows / idx is NULL");
+  cudaError_t e = ypb::launch_compact_results(rows, reinterpret_cast<const long long*>(idx), count, batch, max_det, cols, out_rows,
+                                              reinterpret_cast<long long*>(out_idx), out_offsets, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_compact_results");
+  return YPB_OK;
+}
+
+int ypb_pairwise_iou(const float* boxes1, int32_t n, const float* boxes2, int32_t m, int32_t box_dim, float* out,
+                     void* stream) {
+  if (n < 0 || m < 0 || (box_dim != 4 && box_dim != 5)) return fail(YPB_ERR_INVALID_ARGUMENT, "n=%d m=%d box_dim=%d invalid", n, m, box_dim);
+  if (n == 0 || m == 0) return YPB_OK;
+  if (!boxes1 || !boxes2 || !out) return fail(YPB_ERR_INVALID_ARGUMENT, "boxes1 / boxes2 / out is NULL");
+  if (static_cast<long long>(n) * m > (1LL << 38)) return fail(YPB_ERR_UNSUPPORTED, "%d x %d pairs: too large for one launch", n, m);
+  cudaError_t e = ypb::launch_pairwise_iou(boxes1, n, boxes2, m, box_dim, out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_pairwise_iou");
   return YPB_OK;
 }
 

@@ -481,6 +481,21 @@ struct MatchArgs {  // ypb_match_predictions
 };
 cudaError_t launch_match_predictions(const MatchArgs& a, int max_labels, cudaStream_t st);
 
+struct Dist2BoxArgs {  // ypb_dist2bbox
+  const void* dist;            // (B, 4, A) l,t,r,b
+  long long dsb, dsc;
+  const void* anchor_points;   // (1|B, 2, A)
+  long long asb, asc, asa;
+  const void* angle;           // (B, 1, A) or null
+  long long angle_sb;
+  int batch, anchors, xywh;
+  void* out;                   // (B, 4, A)
+  long long osb, osc;
+};
+cudaError_t launch_dfl(const void* x, int dtype, int batch, int anchors, long long sb, long long sc, void* out, long long osb,
+                       long long osc, cudaStream_t st);
+cudaError_t launch_dist2bbox(const Dist2BoxArgs& d, int dtype, cudaStream_t st);
+
 cudaError_t launch_decode_dense(const HeadGeom& g, int in_dtype, const void* angle, int angle_is_logit,
                                 int append_angle, int xyxy, void* out, int out_dtype, long long osb, long long osc,
                                 int vec, cudaStream_t st);
@@ -491,6 +506,9 @@ cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& 
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,
                               float4* cand_box, float* cand_ang, int32_t* row_count, cudaStream_t st);
+cudaError_t launch_compact_results(const float* rows, const long long* idx, const int32_t* count, int batch, int max_det,
+                                   int cols, float* out_rows, long long* out_idx, int32_t* out_offsets, cudaStream_t st);
+cudaError_t launch_pairwise_iou(const float* a, int n, const float* b, int m, int box_dim, float* out, cudaStream_t st);
 cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, cudaStream_t st);
 cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st);
 

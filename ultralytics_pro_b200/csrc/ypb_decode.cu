@@ -555,6 +555,89 @@ filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// stand-alone pieces of the decode, for callers that compose it themselves (YOLOEDetect.forward_lrpc, head.py:1777-1813,
+// calls self.dfl and self.decode_bboxes directly):
+//   dfl_kernel        DFL.forward, block.py:250-253: (B, 4*16, A) -> (B, 4, A), softmax expectation per side
+//   dist2bbox_kernel  Detect.decode_bboxes == tal.py:367-376 dist2bbox(dim=1) and OBB.decode_bboxes == tal.py:385-403
+//                     dist2rbox(dim=1): every torch op of the reference is one separately rounded operation in the
+//                     tensor dtype T, so the axis-aligned result is bit-identical to the reference (IEEE add/sub/mul).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256)
+dfl_kernel(const void* __restrict__ x_v, long long sb, long long sc, int anchors, void* __restrict__ out_v, long long osb,
+           long long osc) {
+  using T = typename DType<DT>::type;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= anchors) return;
+  const int side = blockIdx.y, b = blockIdx.z;
+  const T* x = static_cast<const T*>(x_v) + static_cast<long long>(b) * sb + static_cast<long long>(side * 16) * sc + a;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = DType<DT>::to_f(x[static_cast<long long>(k) * sc]);
+  static_cast<T*>(out_v)[static_cast<long long>(b) * osb + static_cast<long long>(side) * osc + a] = DType<DT>::from_f(dfl_expect<16>(v));
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+dist2bbox_kernel(const Dist2BoxArgs d) {
+  using T = typename DType<DT>::type;
+  using D = DType<DT>;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= d.anchors) return;
+  const int b = blockIdx.y;
+  const T* dist = static_cast<const T*>(d.dist) + static_cast<long long>(b) * d.dsb + a;
+  const T* ap = static_cast<const T*>(d.anchor_points) + static_cast<long long>(b) * d.asb + static_cast<long long>(a) * d.asa;
+  T* out = static_cast<T*>(d.out) + static_cast<long long>(b) * d.osb + a;
+  const float l = D::to_f(dist[0]), t = D::to_f(dist[d.dsc]), r = D::to_f(dist[2 * d.dsc]), bt = D::to_f(dist[3 * d.dsc]);
+  const float ax = D::to_f(ap[0]), ay = D::to_f(ap[d.asc]);
+  float o0, o1, o2, o3;
+  if (d.angle) {  // tal.py:397-403
+    const float th = D::to_f(static_cast<const T*>(d.angle)[static_cast<long long>(b) * d.angle_sb + a]);
+    const float co = D::rnd(cosf(th)), si = D::rnd(sinf(th));
+    const float xf = D::rnd(__fmul_rn(D::rnd(__fsub_rn(r, l)), 0.5f)), yf = D::rnd(__fmul_rn(D::rnd(__fsub_rn(bt, t)), 0.5f));
+    const float x = D::rnd(__fsub_rn(D::rnd(__fmul_rn(xf, co)), D::rnd(__fmul_rn(yf, si))));
+    const float y = D::rnd(__fadd_rn(D::rnd(__fmul_rn(xf, si)), D::rnd(__fmul_rn(yf, co))));
+    o0 = D::rnd(__fadd_rn(x, ax)); o1 = D::rnd(__fadd_rn(y, ay));
+    o2 = D::rnd(__fadd_rn(l, r)); o3 = D::rnd(__fadd_rn(t, bt));
+  } else {        // tal.py:369-376
+    const float x1 = D::rnd(__fsub_rn(ax, l)), y1 = D::rnd(__fsub_rn(ay, t));
+    const float x2 = D::rnd(__fadd_rn(ax, r)), y2 = D::rnd(__fadd_rn(ay, bt));
+    if (d.xywh) {
+      o0 = D::rnd(__fmul_rn(D::rnd(__fadd_rn(x1, x2)), 0.5f)); o1 = D::rnd(__fmul_rn(D::rnd(__fadd_rn(y1, y2)), 0.5f));
+      o2 = D::rnd(__fsub_rn(x2, x1)); o3 = D::rnd(__fsub_rn(y2, y1));
+    } else {
+      o0 = x1; o1 = y1; o2 = x2; o3 = y2;
+    }
+  }
+  out[0] = D::from_f(o0); out[d.osc] = D::from_f(o1); out[2 * d.osc] = D::from_f(o2); out[3 * d.osc] = D::from_f(o3);
+}
+
+cudaError_t launch_dfl(const void* x, int dtype, int batch, int anchors, long long sb, long long sc, void* out, long long osb,
+                       long long osc, cudaStream_t st) {
+  if (batch <= 0 || anchors <= 0) return cudaSuccess;
+  dim3 grid((anchors + 255) / 256, 4, batch);
+  switch (dtype) {
+    case YPB_F32: dfl_kernel<YPB_F32><<<grid, 256, 0, st>>>(x, sb, sc, anchors, out, osb, osc); break;
+    case YPB_F16: dfl_kernel<YPB_F16><<<grid, 256, 0, st>>>(x, sb, sc, anchors, out, osb, osc); break;
+    case YPB_BF16: dfl_kernel<YPB_BF16><<<grid, 256, 0, st>>>(x, sb, sc, anchors, out, osb, osc); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist2bbox(const Dist2BoxArgs& d, int dtype, cudaStream_t st) {
+  if (d.batch <= 0 || d.anchors <= 0) return cudaSuccess;
+  dim3 grid((d.anchors + 255) / 256, d.batch);
+  switch (dtype) {
+    case YPB_F32: dist2bbox_kernel<YPB_F32><<<grid, 256, 0, st>>>(d); break;
+    case YPB_F16: dist2bbox_kernel<YPB_F16><<<grid, 256, 0, st>>>(d); break;
+    case YPB_BF16: dist2bbox_kernel<YPB_BF16><<<grid, 256, 0, st>>>(d); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // exhaustive monotonicity check of round_T(sigmoid_f(x)) over every finite fp32 x
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT>

@@ -126,13 +126,16 @@ __device__ __forceinline__ bool greedy_suppresses(const float4& a, float aa, con
   return sure != 0u;
 }
 
-// metrics.py:54-75 with eps in the denominator, rule ">= thr" (nms.py:223).
-__device__ __forceinline__ bool boxiou_suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+// metrics.py:54-75 with eps in the denominator.
+__device__ __forceinline__ float boxiou_value(const float4& a, float aa, const float4& b, float ab) {
   float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
   float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
   float inter = __fmul_rn(w, h);
-  float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-7f));
-  return iou >= thr;
+  return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-7f));
+}
+// rule ">= thr" (nms.py:223)
+__device__ __forceinline__ bool boxiou_suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+  return boxiou_value(a, aa, b, ab) >= thr;
 }
 
 struct ObbRec { float x, y, a, b, c, det; };
@@ -151,8 +154,8 @@ __device__ __forceinline__ ObbRec obb_record(float x, float y, float w, float h,
   return o;
 }
 
-// metrics.py:251-284, p = higher-ranked row (obb1), q = lower-ranked (obb2); rule ">= thr" (nms.py:223).
-__device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec& q, float thr) {
+// metrics.py:251-284, p = obb1, q = obb2.
+__device__ __forceinline__ float probiou_value(const ObbRec& p, const ObbRec& q) {
   const float eps = 1e-7f;
   float sa = __fadd_rn(p.a, q.a), sb = __fadd_rn(p.b, q.b), sc = __fadd_rn(p.c, q.c);
   float dy = __fsub_rn(p.y, q.y), dx = __fsub_rn(p.x, q.x);
@@ -165,7 +168,11 @@ __device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec
   float bd = __fadd_rn(__fadd_rn(t1, t2), t3);
   bd = bd != bd ? bd : fminf(fmaxf(bd, eps), 100.f);
   float hd = sqrtf(__fadd_rn(__fsub_rn(1.0f, expf(-bd)), eps));
-  return __fsub_rn(1.0f, hd) >= thr;
+  return __fsub_rn(1.0f, hd);
+}
+// p = higher-ranked row, q = lower-ranked; rule ">= thr" (nms.py:223).
+__device__ __forceinline__ bool probiou_suppresses(const ObbRec& p, const ObbRec& q, float thr) {
+  return probiou_value(p, q) >= thr;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1011,6 +1018,76 @@ __global__ void boxes_prep_kernel(const float* __restrict__ boxes, const float* 
   const float* p = boxes + static_cast<long long>(i) * box_dim;
   cand_box[i] = make_float4(p[0], p[1], p[2], p[3]);
   if (box_dim == 5) cand_ang[i] = p[4];
+}
+
+// nms.py:159-161 returns one tensor per image.  The suppression kernel writes fixed-stride (B, max_det, cols) rows; this
+// kernel packs the kept rows of all images back to back (image order) so the host can cut the per-image views with ONE
+// split instead of B slicing calls: CTA b sums count[0..b) and copies its image's rows / anchor indices.
+__global__ void __launch_bounds__(256)
+compact_results_kernel(const float* __restrict__ rows, const long long* __restrict__ idx, const int32_t* __restrict__ count,
+                       int batch, int max_det, int cols, float* __restrict__ out_rows, long long* __restrict__ out_idx,
+                       int32_t* __restrict__ out_offsets) {
+  __shared__ int warp_part[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int part = 0;
+  for (int i = tid; i < b; i += 256) part += min(count[i], max_det);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) warp_part[tid >> 5] = part;
+  __syncthreads();
+  int prefix = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) prefix += warp_part[w];
+  const int n = min(count[b], max_det);
+  if (out_offsets && tid == 0) {
+    out_offsets[b] = prefix;
+    if (b == batch - 1) out_offsets[batch] = prefix + n;
+  }
+  if (out_rows) {
+    const float* src = rows + static_cast<long long>(b) * max_det * cols;
+    float* dst = out_rows + static_cast<long long>(prefix) * cols;
+    const int nfl = n * cols;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+      for (int i = tid; i < (nfl >> 2); i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+      for (int i = (nfl & ~3) + tid; i < nfl; i += 256) dst[i] = src[i];
+    } else {
+      for (int i = tid; i < nfl; i += 256) dst[i] = src[i];
+    }
+  }
+  if (out_idx && idx) {
+    const long long* src = idx + static_cast<long long>(b) * max_det;
+    for (int i = tid; i < n; i += 256) out_idx[prefix + i] = src[i];
+  }
+}
+
+cudaError_t launch_compact_results(const float* rows, const long long* idx, const int32_t* count, int batch, int max_det,
+                                   int cols, float* out_rows, long long* out_idx, int32_t* out_offsets, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  compact_results_kernel<<<batch, 256, 0, st>>>(rows, idx, count, batch, max_det, cols, out_rows, out_idx, out_offsets);
+  return cudaGetLastError();
+}
+
+// metrics.py:54-75 box_iou / metrics.py:251-284 batch_probiou as free functions: out[i * m + j] = iou(a_i, b_j).
+__global__ void __launch_bounds__(256)
+pairwise_iou_kernel(const float* __restrict__ a, int n, const float* __restrict__ b, int m, int box_dim, float* __restrict__ out) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(n) * m) return;
+  const int i = static_cast<int>(t / m), j = static_cast<int>(t - static_cast<long long>(i) * m);
+  const float* p = a + static_cast<long long>(i) * box_dim;
+  const float* q = b + static_cast<long long>(j) * box_dim;
+  if (box_dim == 5) {
+    out[t] = probiou_value(obb_record(p[0], p[1], p[2], p[3], p[4]), obb_record(q[0], q[1], q[2], q[3], q[4]));
+  } else {
+    const float4 ba = make_float4(p[0], p[1], p[2], p[3]), bb = make_float4(q[0], q[1], q[2], q[3]);
+    out[t] = boxiou_value(ba, box_area(ba), bb, box_area(bb));
+  }
+}
+
+cudaError_t launch_pairwise_iou(const float* a, int n, const float* b, int m, int box_dim, float* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * m;
+  if (total <= 0) return cudaSuccess;
+  pairwise_iou_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(a, n, b, m, box_dim, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {

@@ -103,12 +103,41 @@ class NmsPlan:
     keep_alive: tuple = ()
     xforms: torch.Tensor = None  # (B, 8) ypb_scale_xform array when the gather rescales to the original images
     peers: object = None         # dist.PeerGather when the kernel also stores the results into every peer's buffer
+    scratch_bytes: int = 0
+
+
+_PLAN_CACHE_MAX = 32
+
+
+def _plan_cache():
+    cache = getattr(_tls, "plans", None)
+    if cache is None:
+        from collections import OrderedDict
+
+        cache = _tls.plans = OrderedDict()
+    return cache
 
 
 def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: float, iou_eff: float, max_det: int,
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
               scale_padding: bool = True, peer_gather_group=None, nms_box=None, boxes_xyxy: bool = False,
-              pad_output: bool = False, conf_per_image: torch.Tensor | None = None, rows_cap: int | None = None) -> NmsPlan:
+              pad_output: bool = False, conf_per_image: torch.Tensor | None = None, rows_cap: int | None = None,
+              cached: bool = False) -> NmsPlan:
+    """cached=True: the plan (parameter structs, fixed-stride result buffers) is kept per (thread, stream, geometry,
+    parameters) and REUSED by the next call with the same key - only for callers that copy the results out before
+    returning (``split_results`` packs them into fresh tensors); everything is stream-ordered, so reuse is safe."""
+    key = None
+    if cached and peer_gather_group is None and conf_per_image is None:
+        ckey = None if classes is None else tuple(int(c) for c in (classes.tolist() if isinstance(classes, torch.Tensor) else classes))
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, batch, anchors, nc, extra, conf_t, iou_eff, int(max_det),
+               int(max_nms), float(max_wh), bool(multi_label), rule, ckey, bool(with_scale), bool(scale_padding),
+               None if nms_box is None else tuple(nms_box), bool(boxes_xyxy), bool(pad_output), rows_cap)
+        cache = _plan_cache()
+        hit = cache.get(key)
+        if hit is not None:
+            cache.move_to_end(key)
+            hit.scratch = _scratch(device, hit.scratch_bytes)  # the pool buffer may have been regrown since
+            return hit
     rows_cap = (anchors * nc if multi_label else anchors) if rows_cap is None else int(rows_cap)
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))
@@ -150,7 +179,14 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         o.scale_xforms, o.scale_padding = xforms.data_ptr(), int(bool(scale_padding))
     if peers is not None:
         peers.bind(o)
-    return NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image), xforms, peers)
+    plan = NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image), xforms, peers)
+    plan.scratch_bytes = nbytes
+    if key is not None:
+        cache = _plan_cache()
+        cache[key] = plan
+        while len(cache) > _PLAN_CACHE_MAX:
+            cache.popitem(last=False)
+    return plan
 
 
 def set_transforms(plan: NmsPlan, img1_shape, orig_shapes, ratio_pads=None) -> None:
@@ -172,12 +208,36 @@ def fetch_counts(count: torch.Tensor) -> list:
     return host.tolist()
 
 
-def split_results(plan: NmsPlan, return_idxs: bool):
-    counts = fetch_counts(plan.count)
-    out = [plan.rows[b, :n] for b, n in enumerate(counts)]
+def compact_results(plan: NmsPlan, with_idx: bool, out_rows: torch.Tensor | None = None, out_idx: torch.Tensor | None = None):
+    """Pack the kept rows (and anchor indices) of the plan's fixed-stride buffers back to back into fresh (or given) tensors:
+    one launch, no host synchronisation."""
+    b, md, cols = plan.rows.shape
+    dev = plan.rows.device
+    if out_rows is None:
+        out_rows = torch.empty((b * md, cols), dtype=torch.float32, device=dev)
+    if with_idx and out_idx is None:
+        out_idx = torch.empty((b * md,), dtype=torch.int64, device=dev)
+    rc = _cabi.load().ypb_compact_results(plan.rows.data_ptr(), plan.idx.data_ptr() if with_idx else None, plan.count.data_ptr(),
+                                          b, md, cols, out_rows.data_ptr(), out_idx.data_ptr() if with_idx else None, None,
+                                          _cabi.stream_ptr(dev))
+    _cabi.check(rc, "ypb_compact_results")
+    return out_rows, out_idx
+
+
+def cut_results(out_rows: torch.Tensor, out_idx, counts: list, return_idxs: bool):
+    """list[Tensor(n_i, cols)] (nms.py:159-161) from the packed rows: ONE split, not B slicing calls."""
+    total = sum(counts)
+    out = list(torch.split(out_rows[:total], counts)) if counts else []
     if return_idxs:
-        return out, [plan.idx[b, :n] for b, n in enumerate(counts)]
+        return out, (list(torch.split(out_idx[:total], counts)) if counts else [])
     return out
+
+
+def split_results(plan: NmsPlan, return_idxs: bool):
+    if plan.rows.shape[0] == 0:
+        return ([], []) if return_idxs else []
+    out_rows, out_idx = compact_results(plan, return_idxs)
+    return cut_results(out_rows, out_idx, fetch_counts(plan.count), return_idxs)
 
 
 def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:

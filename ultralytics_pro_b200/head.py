@@ -1,6 +1,9 @@
 """Drop-ins for the Detect-family decode (``ultralytics/nn/modules/head.py``) and the fused post-process call.
 
   detect_inference(self, x)      bound as ``Detect._inference`` (head.py:151-169; identical copies :340,:535,:724)
+  detect_decode_bboxes / obb_decode_bboxes / dfl_forward
+                                 bound as ``Detect.decode_bboxes`` (head.py:184-191), ``OBB.decode_bboxes`` (:1040-1042) and
+                                 ``DFL.forward`` (block.py:250-253) - the pieces ``YOLOEDetect.forward_lrpc`` (:1777-1813) calls
   decode_head(...)               the same decode as a free function on raw level tensors
   postprocess_from_head(...)     decode + non_max_suppression in one pass over the head (never writes the dense
                                  tensor) - the `postprocess` envelope of predictor.py:335 / validator.py:221
@@ -58,17 +61,106 @@ def decode_head(levels, strides, nc: int, reg_max: int = 16, angle: torch.Tensor
     return out
 
 
+def host_strides(self) -> tuple:
+    """``self.stride`` (head.py:79; a device tensor once ``BaseModel._apply`` moved the model) as host floats, read back
+    ONCE per stride tensor: ``float(s) for s in self.stride`` would be one device->host sync per level on every forward -
+    the reference's ``_inference`` has none on a cache hit (``make_anchors`` reads the strides only when the shape changes)."""
+    st = self.stride
+    key = (id(st), st.data_ptr() if isinstance(st, torch.Tensor) else None, getattr(st, "device", None))
+    cached = self.__dict__.get("_ypb_stride_cache")
+    if cached is None or cached[0] != key:
+        vals = tuple(float(v) for v in (st.tolist() if isinstance(st, torch.Tensor) else st))
+        cached = (key, vals, st)  # holding `st` keeps id() unique
+        self.__dict__["_ypb_stride_cache"] = cached
+    return cached[1]
+
+
+def _is_obb(self) -> bool:
+    return hasattr(self, "ne") and hasattr(self, "cv4") and getattr(self, "angle", None) is not None
+
+
+def _has_riders(self) -> bool:
+    """Segment / Pose / OBB heads concatenate their own channels to ``_inference``'s result right away (head.py:837,
+    :1038, :1252), so a lazily materialised tensor would only add overhead there."""
+    return any(hasattr(self, a) for a in ("nm", "ne", "kpt_shape", "nk"))
+
+
 def detect_inference(self, x: list) -> torch.Tensor:
     """``Detect._inference`` drop-in (head.py:151-169).  Reads the same module attributes, keeps caching
-    ``self.anchors/self.strides/self.shape`` and returns the dense (B, 4+nc, A) tensor in the input dtype."""
+    ``self.anchors/self.strides/self.shape`` and returns the dense (B, 4+nc, A) tensor in the input dtype.
+
+    With ``lazy.ENABLED`` (set by ``patch.install(lazy_decode=True)``) a plain Detect head returns a ``LazyDecoded``
+    tensor instead: same shape/dtype/device, materialised by the dense kernel on first use by ANY torch op - unless the
+    first consumer is the patched ``non_max_suppression``, which then runs the fused head->NMS kernels on the level
+    tensors and the dense tensor is never written (SURVEY.md section 7 "Drop-in surface")."""
     shape = x[0].shape  # BCHW
     self._ypb_level_hw = [(int(lv.shape[2]), int(lv.shape[3])) for lv in x]  # read by pose_kpts_decode
+    strides = host_strides(self)
     if self.dynamic or self.shape != shape:
-        self.anchors, self.strides = _anchor_cache(x, self.stride, x[0].dtype, x[0].device)
+        self.anchors, self.strides = _anchor_cache(x, strides, x[0].dtype, x[0].device)
         self.shape = shape
-    angle = getattr(self, "angle", None) if hasattr(self, "ne") and hasattr(self, "cv4") else None  # OBB family
-    return decode_head(x, [float(s) for s in self.stride], self.nc, self.reg_max, angle=angle, angle_is_logit=False,
-                       append_angle=False, xyxy=bool(self.end2end or self.xyxy))
+    angle = self.angle if _is_obb(self) else None  # OBB family (head.py:1032)
+    xyxy = bool(self.end2end or self.xyxy)
+    from . import lazy
+
+    if lazy.ENABLED and angle is None and not self.end2end and not _has_riders(self) and not torch.is_grad_enabled():
+        return lazy.LazyDecoded.from_head(list(x), strides, self.nc, self.reg_max, xyxy)
+    return decode_head(x, strides, self.nc, self.reg_max, angle=angle, angle_is_logit=False, append_angle=False, xyxy=xyxy)
+
+
+def dfl_forward(self, x: torch.Tensor) -> torch.Tensor:
+    """``DFL.forward`` drop-in (block.py:250-253): (B, 4*c1, A) -> (B, 4, A), softmax expectation over the c1 bins of
+    every side (the frozen ``arange(c1)`` 1x1 conv of block.py:245-247 folded into the kernel)."""
+    _cabi.require_cuda(x, "DFL.forward")
+    b, ch, a = x.shape
+    if x.stride(2) != 1 and a > 1:
+        x = x.contiguous()
+    out = torch.empty((b, 4, a), dtype=x.dtype, device=x.device)
+    rc = _cabi.load().ypb_dfl_expectation(x.data_ptr(), _cabi.dtype_code(x.dtype), b, ch // 4, a, x.stride(0), x.stride(1),
+                                          out.data_ptr(), out.stride(0), out.stride(1), _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "ypb_dfl_expectation")
+    return out
+
+
+def dist2bbox(distance: torch.Tensor, anchor_points: torch.Tensor, xywh: bool = True, angle: torch.Tensor | None = None):
+    """``dist2bbox(distance, anchor_points, xywh, dim=1)`` (tal.py:367-376) or, with ``angle``, ``dist2rbox(distance,
+    angle, anchor_points, dim=1)`` (tal.py:385-403): distance (B, 4, A), anchor_points (2, A) / (1|B, 2, A) of any
+    strides, angle (B, 1, A) -> (B, 4, A) in the input dtype."""
+    _cabi.require_cuda(distance, "decode_bboxes")
+    if distance.dim() != 3 or distance.shape[1] != 4:
+        raise ValueError(f"distance must be (B, 4, A), got {tuple(distance.shape)}")
+    b, _, a = distance.shape
+    dt = distance.dtype
+    if distance.stride(2) != 1 and a > 1:
+        distance = distance.contiguous()
+    ap = anchor_points if anchor_points.dim() == 3 else anchor_points.unsqueeze(0)
+    if ap.shape[-2:] != (2, a) or ap.shape[0] not in (1, b):
+        raise ValueError(f"anchor_points {tuple(anchor_points.shape)} does not broadcast against (B={b}, 2, A={a})")
+    if ap.dtype != dt or ap.device != distance.device:
+        ap = ap.to(device=distance.device, dtype=dt)
+    ang_ptr, ang_sb = None, 0
+    if angle is not None:
+        angle = angle.to(dt).reshape(b, a)
+        if not angle.is_contiguous():
+            angle = angle.contiguous()
+        ang_ptr, ang_sb = angle.data_ptr(), angle.stride(0)
+    out = torch.empty((b, 4, a), dtype=dt, device=distance.device)
+    rc = _cabi.load().ypb_dist2bbox(distance.data_ptr(), distance.stride(0), distance.stride(1), ap.data_ptr(),
+                                    ap.stride(0) if ap.shape[0] == b and b > 1 else 0, ap.stride(1), ap.stride(2), ang_ptr,
+                                    ang_sb, _cabi.dtype_code(dt), b, a, int(bool(xywh)), out.data_ptr(), out.stride(0),
+                                    out.stride(1), _cabi.stream_ptr(distance.device))
+    _cabi.check(rc, "ypb_dist2bbox")
+    return out
+
+
+def detect_decode_bboxes(self, bboxes: torch.Tensor, anchors: torch.Tensor, xywh: bool = True) -> torch.Tensor:
+    """``Detect.decode_bboxes`` drop-in (head.py:184-191)."""
+    return dist2bbox(bboxes, anchors, xywh=xywh and not self.end2end and not self.xyxy)
+
+
+def obb_decode_bboxes(self, bboxes: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:
+    """``OBB.decode_bboxes`` drop-in (head.py:1040-1042): rotated decode with the angle ``OBB.forward`` stored."""
+    return dist2bbox(bboxes, anchors, angle=self.angle)
 
 
 def decode_keypoints(kpts: torch.Tensor, level_hw, strides, kpt_shape) -> torch.Tensor:
@@ -93,15 +185,22 @@ def pose_kpts_decode(self, bs: int, kpts: torch.Tensor) -> torch.Tensor:
     """``Pose.kpts_decode`` drop-in (head.py:1254; identical copies :1322, :1390, :1459).  The level grid sizes come from
     the level list seen by ``detect_inference`` (``Pose.forward`` runs ``Detect.forward`` first, head.py:1249-1252)."""
     hw = getattr(self, "_ypb_level_hw", None)
+    strides = host_strides(self)
     if hw is None or sum(h * w for h, w in hw) != kpts.shape[-1]:
-        # _inference ran through the reference (not patched): recover the grids from the cached stride row (head.py:163-165)
-        srow = self.strides.view(-1)
-        hw = []
-        for s in self.stride:
-            sel = srow == float(s)
-            w = int(self.anchors[0, sel].max().item() + 0.5)
-            hw.append((int(sel.sum()) // w, w))
-    return decode_keypoints(kpts.view(bs, self.nk, -1), hw, [float(s) for s in self.stride], self.kpt_shape)
+        # _inference ran through the reference (not patched): recover the grids from the cached anchor rows
+        # (head.py:163-165), once per cached shape - this reads back from the device
+        cached = self.__dict__.get("_ypb_hw_from_anchors")
+        if cached is None or cached[0] != (tuple(self.shape), kpts.shape[-1]):
+            srow = self.strides.view(-1)
+            hw = []
+            for s in strides:
+                sel = srow == s
+                w = int(self.anchors[0, sel].max().item() + 0.5)
+                hw.append((int(sel.sum()) // w, w))
+            cached = ((tuple(self.shape), kpts.shape[-1]), hw)
+            self.__dict__["_ypb_hw_from_anchors"] = cached
+        hw = cached[1]
+    return decode_keypoints(kpts.view(bs, self.nk, -1), hw, strides, self.kpt_shape)
 
 
 def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch.Tensor:
@@ -175,7 +274,7 @@ def postprocess_from_head(levels, strides, nc: int, conf_thres: float = 0.25, io
     extra = riders.channels if riders is not None else (1 if rotated else 0)
     plan = engine.make_plan(lv0.device, b, anchors, nc, extra, conf_t, iou_eff, max_det, max_nms,
                             0.0 if agnostic else float(max_wh), multi_label, rule, classes,
-                            with_scale=orig_shapes is not None)
+                            with_scale=orig_shapes is not None, cached=sync)
     if orig_shapes is not None and b:
         if img_shape is None:
             img_shape = (lv0.shape[2] * int(strides[0]), lv0.shape[3] * int(strides[0]))

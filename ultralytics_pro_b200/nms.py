@@ -88,6 +88,20 @@ def non_max_suppression(
     if isinstance(prediction, (list, tuple)):  # (inference_out, loss_out), nms.py:61
         prediction = prediction[0]
     _cabi.require_cuda(prediction, "non_max_suppression")
+    from . import lazy
+
+    if isinstance(prediction, lazy.LazyDecoded):
+        # the tensor came from our Detect._inference drop-in and nobody has needed its values yet: run the fused
+        # head -> NMS kernels on the recorded level tensors (bit-identical to decode + NMS); the dense tensor is never written
+        rec = prediction.head_record()
+        if (rec is not None and not rotated and not end2end and not rec.xyxy and nc in (0, rec.nc)
+                and not (labels and any(len(l) for l in labels)) and not MUTATE_INPUT_LIKE_REFERENCE):
+            from .head import postprocess_from_head
+
+            lazy.STATS["fused"] += 1
+            return postprocess_from_head(rec.levels, rec.strides, rec.nc, conf_thres, iou_thres, classes, agnostic,
+                                         multi_label, max_det, max_nms, max_wh, rec.reg_max, return_idxs=return_idxs)
+        prediction = prediction.materialize()
     if prediction.shape[-1] == 6 or end2end:
         return _end2end_select(prediction, conf_thres, max_det, classes)
 
@@ -113,7 +127,7 @@ def non_max_suppression(
     else:
         rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(iou_thres)
     plan = engine.make_plan(prediction.device, bs, na, nc, extra, conf_t, iou_eff, max_det, max_nms,
-                            0.0 if agnostic else float(max_wh), multi_label, rule, classes)
+                            0.0 if agnostic else float(max_wh), multi_label, rule, classes, cached=True)
     engine.run_from_dense(prediction, plan)
     if MUTATE_INPUT_LIKE_REFERENCE and not rotated:
         xy, wh = prediction[:, :2].clone(), prediction[:, 2:4] / 2
@@ -121,14 +135,32 @@ def non_max_suppression(
     return engine.split_results(plan, return_idxs)
 
 
+def _pairwise(box1: torch.Tensor, box2: torch.Tensor, dim: int, what: str) -> torch.Tensor:
+    _cabi.require_cuda(box1, what)
+    if box1.dim() != 2 or box2.dim() != 2 or box1.shape[1] != dim or box2.shape[1] != dim:
+        raise ValueError(f"{what}: expected (N, {dim}) and (M, {dim}), got {tuple(box1.shape)} and {tuple(box2.shape)}")
+    a = box1.to(torch.float32).contiguous()
+    b = box2.to(device=box1.device, dtype=torch.float32).contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=box1.device)
+    rc = _cabi.load().ypb_pairwise_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], dim, out.data_ptr(),
+                                       _cabi.stream_ptr(box1.device))
+    _cabi.check(rc, "ypb_pairwise_iou")
+    return out
+
+
 def box_iou(box1, box2, eps: float = 1e-7):
-    """Marker for ``TorchNMS.fast_nms(iou_func=box_iou)`` (metrics.py:54); the pairwise matrix is never materialised."""
-    raise NotImplementedError("box_iou is evaluated inside the suppression kernel; pass it as iou_func to TorchNMS.fast_nms")
+    """``metrics.box_iou`` (metrics.py:54-75): (N, 4), (M, 4) xyxy -> (N, M) fp32.  As ``iou_func`` of ``TorchNMS.fast_nms`` it is
+    recognised by name and evaluated pair by pair inside the suppression kernel (the matrix is never materialised)."""
+    if eps != 1e-7:
+        raise NotImplementedError("box_iou: the kernel is built with the reference's default eps=1e-7")
+    return _pairwise(box1, box2, 4, "box_iou")
 
 
 def batch_probiou(obb1, obb2, eps: float = 1e-7):
-    """Marker for ``TorchNMS.fast_nms(iou_func=batch_probiou)`` (metrics.py:251)."""
-    raise NotImplementedError("batch_probiou is evaluated inside the suppression kernel; pass it as iou_func to TorchNMS.fast_nms")
+    """``metrics.batch_probiou`` (metrics.py:251-284): (N, 5), (M, 5) xywhr -> (N, M) fp32; same remark as ``box_iou``."""
+    if eps != 1e-7:
+        raise NotImplementedError("batch_probiou: the kernel is built with the reference's default eps=1e-7")
+    return _pairwise(obb1, obb2, 5, "batch_probiou")
 
 
 def _nms_boxes(boxes: torch.Tensor, scores: torch.Tensor, rule: int, thr: float) -> torch.Tensor:

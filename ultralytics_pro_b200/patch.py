@@ -12,7 +12,13 @@ What is rebound (reference paths relative to ultralytics/):
   utils/nms.py:169         TorchNMS.nms / fast_nms / batched_nms - patched as static methods ON the class object, because
                                                    models/yolo/obb/val.py:14 and engine/exporter.py:122 hold the class by name
   nn/modules/head.py:151   Detect._inference (and the byte-identical copies MAFDetect :340, IDetect :535, DDetect :724);
-                                                   Segment/Pose/OBB/World/YOLOE/v10 inherit it
+                                                   Segment/Pose/OBB/World/YOLOE/v10 inherit it.  With lazy_decode (default) a
+                                                   plain Detect head returns a lazily decoded tensor (lazy.LazyDecoded) and the
+                                                   patched non_max_suppression runs the FUSED head->NMS kernels on it - the
+                                                   reference's own call sites (predictor.py:335-336, detect/predict.py:54,
+                                                   detect/val.py:115) reach the fused path without any change
+  nn/modules/head.py:184   Detect.decode_bboxes (same four classes), head.py:1040 OBB.decode_bboxes (OBB, MAFOBB, IOBB, DOBB)
+  nn/modules/block.py:250  DFL.forward - with decode_bboxes the whole of YOLOEDetect.forward_lrpc's decode (head.py:1777-1813)
   utils/ops.py:102,152,562,598,621  scale_boxes / clip_boxes / scale_coords / clip_coords / regularize_rboxes - on the module
                                                    object (every caller goes through `ops.<name>`: detect/predict.py:120,
                                                    obb/predict.py:59-60, pose/predict.py:75, detect/val.py:422, engine/results.py:341)
@@ -28,6 +34,7 @@ _saved: dict = {}
 
 _HEAD_CLASSES = ("Detect", "MAFDetect", "IDetect", "DDetect")
 _POSE_CLASSES = ("Pose", "MAFPose", "IPose", "DPose")
+_OBB_CLASSES = ("OBB", "MAFOBB", "IOBB", "DOBB")
 
 
 def _wrap_nms(ref_fn, ours):
@@ -42,14 +49,46 @@ def _wrap_nms(ref_fn, ours):
     return non_max_suppression
 
 
+def _kernel_ok(self) -> bool:
+    """Configurations the kernels are built for; anything else runs the saved reference function."""
+    import torch
+
+    return getattr(self, "reg_max", 16) == 16 and not getattr(self, "export", False) and not torch.is_grad_enabled()
+
+
 def _wrap_inference(ref_fn, ours):
     def _inference(self, x):
-        if x[0].is_cuda and not getattr(self, "export", False):
+        if x[0].is_cuda and _kernel_ok(self) and not x[0].requires_grad:
             return ours(self, x)
         return ref_fn(self, x)
 
     _inference.__wrapped__ = ref_fn
     return _inference
+
+
+def _wrap_decode_bboxes(ref_fn, ours):
+    def decode_bboxes(self, bboxes, anchors, *args, **kwargs):
+        # the tflite/edgetpu export branch of _inference passes pre-normalised tensors and is never taken here (export)
+        if getattr(bboxes, "is_cuda", False) and bboxes.dim() == 3 and bboxes.shape[1] == 4 and _kernel_ok(self) \
+                and not bboxes.requires_grad:
+            return ours(self, bboxes, anchors, *args, **kwargs)
+        return ref_fn(self, bboxes, anchors, *args, **kwargs)
+
+    decode_bboxes.__wrapped__ = ref_fn
+    return decode_bboxes
+
+
+def _wrap_dfl(ref_fn, ours):
+    def forward(self, x):
+        import torch
+
+        if getattr(x, "is_cuda", False) and x.dim() == 3 and self.c1 == 16 and x.shape[1] == 64 and not torch.is_grad_enabled() \
+                and not x.requires_grad:
+            return ours(self, x)
+        return ref_fn(self, x)
+
+    forward.__wrapped__ = ref_fn
+    return forward
 
 
 def _wrap_kpts(ref_fn, ours):
@@ -124,11 +163,17 @@ def _wrap_process_batch(ref_fn, ours):
     return _process_batch
 
 
-def install() -> list:
-    """Patch the already-importable `ultralytics` package in place; returns the list of rebound symbols."""
+def install(lazy_decode: bool = True) -> list:
+    """Patch the already-importable `ultralytics` package in place; returns the list of rebound symbols.
+
+    lazy_decode: ``Detect._inference`` of a plain Detect head returns ``lazy.LazyDecoded`` so that the reference's
+    ``_inference`` -> ``non_max_suppression`` call sites take the fused kernels (see ``lazy.py``); False keeps the two
+    independent kernels (dense decode, NMS from the dense tensor)."""
     from . import head as our_head
+    from . import lazy
     from . import nms as our_nms
 
+    lazy.ENABLED = bool(lazy_decode)
     if _saved:
         return sorted(_saved)
     done = []
@@ -188,6 +233,25 @@ def install() -> list:
             _saved[f"ultralytics.nn.modules.head.{cname}._inference"] = (c, "_inference", c.__dict__["_inference"])
             c._inference = _wrap_inference(c.__dict__["_inference"], our_head.detect_inference)
             done.append(f"ultralytics.nn.modules.head.{cname}._inference")
+        for cname in _HEAD_CLASSES:  # head.py:184-191 (copies :374, :569, :757)
+            c = getattr(ref_head, cname, None)
+            if c is None or "decode_bboxes" not in c.__dict__:
+                continue
+            _saved[f"ultralytics.nn.modules.head.{cname}.decode_bboxes"] = (c, "decode_bboxes", c.__dict__["decode_bboxes"])
+            c.decode_bboxes = _wrap_decode_bboxes(c.__dict__["decode_bboxes"], our_head.detect_decode_bboxes)
+            done.append(f"ultralytics.nn.modules.head.{cname}.decode_bboxes")
+        for cname in _OBB_CLASSES:  # head.py:1040, :1094, :1148, :1203
+            c = getattr(ref_head, cname, None)
+            if c is None or "decode_bboxes" not in c.__dict__:
+                continue
+            _saved[f"ultralytics.nn.modules.head.{cname}.decode_bboxes"] = (c, "decode_bboxes", c.__dict__["decode_bboxes"])
+            c.decode_bboxes = _wrap_decode_bboxes(c.__dict__["decode_bboxes"], our_head.obb_decode_bboxes)
+            done.append(f"ultralytics.nn.modules.head.{cname}.decode_bboxes")
+        dfl = getattr(ref_head, "DFL", None)  # head.py imports DFL from .block by name; patching the class covers both
+        if dfl is not None and "forward" in dfl.__dict__:
+            _saved["ultralytics.nn.modules.block.DFL.forward"] = (dfl, "forward", dfl.__dict__["forward"])
+            dfl.forward = _wrap_dfl(dfl.__dict__["forward"], our_head.dfl_forward)
+            done.append("ultralytics.nn.modules.block.DFL.forward")
         for cname in _HEAD_CLASSES:  # head.py:193 end2end top-k (staticmethod)
             c = getattr(ref_head, cname, None)
             if c is None or "postprocess" not in c.__dict__:
@@ -206,6 +270,9 @@ def install() -> list:
 
 
 def uninstall() -> None:
+    from . import lazy
+
     for _, (obj, name, orig) in list(_saved.items()):
         setattr(obj, name, orig)
     _saved.clear()
+    lazy.ENABLED = False

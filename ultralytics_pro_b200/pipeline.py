@@ -19,7 +19,7 @@ class HeadPostProcessor:
     def __init__(self, nc: int, strides, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                  agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                  max_wh: int = 7680, reg_max: int = 16, rotated: bool = False, scale_to_original: bool = False,
-                 peer_gather_group=None):
+                 peer_gather_group=None, use_graph: bool = False):
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
         self.nc, self.strides, self.reg_max = nc, tuple(float(s) for s in strides), reg_max
@@ -32,6 +32,11 @@ class HeadPostProcessor:
         # multi-GPU: True / a process group = one-sided gather of every rank's results over NVLink peer memory
         # (dist.PeerGather); plans are then created collectively, in the same order on every rank
         self.peer_gather_group = peer_gather_group
+        # use_graph: __call__ replays ONE CUDA graph per distinct set of input tensors (kernels + result packing + the count
+        # copy to pinned memory): a serving loop with static input buffers pays one graph launch and one stream
+        # synchronisation per batch.  The returned views are then valid until the next call on the same inputs.
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
         self._plans = {}
         self.last = None
 
@@ -113,7 +118,36 @@ class HeadPostProcessor:
         return pl.peers.gathered(pl.rows.shape[0], pl.rows.shape[1], pl.rows.shape[2])
 
     def __call__(self, levels, angle_logits=None, return_idxs: bool = False):
+        if self.use_graph:
+            return self._call_graphed(levels, angle_logits, return_idxs)
         return engine.split_results(self.enqueue(levels, angle_logits), return_idxs)
+
+    def _call_graphed(self, levels, angle_logits, return_idxs: bool):
+        dev = levels[0].device
+        key = (tuple((lv.data_ptr(), tuple(lv.shape), lv.stride()) for lv in levels), levels[0].dtype,
+               angle_logits.data_ptr() if angle_logits is not None else 0)
+        ent = self._graphs.get(key)
+        if ent is None:
+            plan = self.enqueue(levels, angle_logits)  # warm-up: plan, scratch and result buffers exist after this
+            out_rows, out_idx = engine.compact_results(plan, True)
+            host = torch.empty((plan.count.numel(),), dtype=torch.int32).pin_memory()
+            host.copy_(plan.count, non_blocking=True)
+            cur = torch.cuda.current_stream(dev)
+            cur.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            cap = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(dev)
+            with torch.cuda.graph(graph, stream=cap):
+                self.enqueue(levels, angle_logits)
+                engine.compact_results(plan, True, out_rows, out_idx)
+                host.copy_(plan.count, non_blocking=True)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = (graph, plan, out_rows, out_idx, host, list(levels), angle_logits)
+        graph, plan, out_rows, out_idx, host = ent[:5]
+        graph.replay()
+        torch.cuda.current_stream(dev).synchronize()
+        self.last = plan
+        return engine.cut_results(out_rows, out_idx, host.tolist(), return_idxs)
 
     def results(self, return_idxs: bool = False):
         if self.last is None:

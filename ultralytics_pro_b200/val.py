@@ -17,11 +17,27 @@ import torch
 from . import _cabi, engine
 
 
+_thr_cache: dict = {}
+
+
 def _thresholds(iouv):
+    """Host copy of the validator's IoU levels (``self.iouv``, a device tensor: validator.py:148) - read back once per
+    tensor, not on every call."""
+    key = None
+    if isinstance(iouv, torch.Tensor):
+        key = (id(iouv), iouv.data_ptr(), iouv.numel())
+        hit = _thr_cache.get(key)
+        if hit is not None and hit[0] is iouv:
+            return hit[1], hit[2]
     vals = [float(v) for v in (iouv.cpu().tolist() if isinstance(iouv, torch.Tensor) else iouv)]
     if not 1 <= len(vals) <= 16:
         raise ValueError(f"{len(vals)} IoU levels: the kernel takes 1..16")
-    return (C.c_float * len(vals))(*vals), len(vals)
+    arr = (C.c_float * len(vals))(*vals)
+    if key is not None:
+        if len(_thr_cache) > 64:
+            _thr_cache.clear()
+        _thr_cache[key] = (iouv, arr, len(vals))
+    return arr, len(vals)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
