@@ -301,11 +301,12 @@ def test_bound_kpts_decode_both_grid_sources(cuda_device):
     m = _detect(cfg, cuda_device)
     m.kpt_shape, m.nk = (17, 3), 51
     _bind(m, "kpts_decode", patch._wrap_kpts(_boom, head.pose_kpts_decode))
+    kd = kp.to(cuda_device)
     with torch.inference_mode():
         m._inference(dl)  # Pose.forward runs Detect.forward first (head.py:1249)
-        got = m.kpts_decode(2, kp.to(cuda_device))
+        got = m.kpts_decode(2, kd)
         with no_host_sync():
-            got = m.kpts_decode(2, kp.to(cuda_device).clone())
+            got = m.kpts_decode(2, kd.clone())
     g4, w4 = got.cpu().view(2, 17, 3, -1), want.view(2, 17, 3, -1)
     assert torch.equal(g4[:, :, :2], w4[:, :, :2]) and float((g4[:, :, 2] - w4[:, :, 2]).abs().max()) < 1e-6
     # a module whose _inference ran through the reference: grids recovered from the cached anchor rows, once
@@ -314,9 +315,9 @@ def test_bound_kpts_decode_both_grid_sources(cuda_device):
     anc, srow = anchor_table(cfg.level_hw, cfg.strides)
     m2.anchors, m2.strides, m2.shape = anc.to(cuda_device), srow.to(cuda_device), dl[0].shape
     _bind(m2, "kpts_decode", patch._wrap_kpts(_boom, head.pose_kpts_decode))
-    got2 = m2.kpts_decode(2, kp.to(cuda_device))
+    got2 = m2.kpts_decode(2, kd)
     with no_host_sync():
-        got3 = m2.kpts_decode(2, kp.to(cuda_device).clone())
+        got3 = m2.kpts_decode(2, kd.clone())
     assert torch.equal(got2, got) and torch.equal(got3, got)
 
 
@@ -338,10 +339,10 @@ def test_bound_validator_methods(cuda_device):
     me = types.SimpleNamespace(iouv=iouv.to(dev), niou=10)  # validator.py:148 keeps iouv on the device
     _bind(me, "match_predictions", patch._wrap_match(_boom, val.match_predictions))
     _bind(me, "_process_batch", patch._wrap_process_batch(_boom, val.process_batch))
-    iou_d = torch.from_numpy(iou).to(dev)
-    got = me.match_predictions(pcls.to(dev), gcls.to(dev), iou_d)
+    iou_d, pcls_d, gcls_d = torch.from_numpy(iou).to(dev), pcls.to(dev), gcls.to(dev)
+    got = me.match_predictions(pcls_d, gcls_d, iou_d)
     with no_host_sync():  # the IoU levels were read back once, on the first call
-        got = me.match_predictions(pcls.to(dev), gcls.to(dev), iou_d)
+        got = me.match_predictions(pcls_d, gcls_d, iou_d)
     assert got.dtype == torch.bool and np.array_equal(got.cpu().numpy(), want)
     tp = me._process_batch({"bboxes": boxes.to(dev), "cls": pcls.to(dev)}, {"bboxes": gt.to(dev), "cls": gcls.to(dev)})["tp"]
     assert np.array_equal(tp, want)

@@ -105,6 +105,15 @@ CASES = [
     ("c4_p6_1280_b16", 2, {"agnostic": True}),
     ("c3_val_stress_b32", 2, {}),
     ("c3_val_stress_b32", 1, {"max_nms": 5000}),
+    # the benchmarked sizes (bench.py: C2 at B=64; config sweep: C4 at B=16, C3 at B=8 of 32): the batch-dependent machinery -
+    # GPU-wide octet list, one suppression CTA per image on 64 SMs at once, the prefix select of the 29 k-row images
+    ("c2_v8x_640_b64", 64, {}),
+    ("c4_p6_1280_b16", 16, {}),
+    ("c3_val_stress_b32", 8, {}),
+    # the prefix (radix select of the best rows) is not enough: max_det larger than the prefix can hold -> full sort + walk
+    ("c3_val_stress_b32", 1, {"max_det": 3000}),
+    # ... and a prefix that is tried but does not yield max_det kept rows (aggressive threshold): prefix, then full walk
+    ("c3_val_stress_b32", 1, {"iou": 0.1, "max_det": 1000}),
 ]
 
 
@@ -134,11 +143,50 @@ def test_nms_rotated_matches_oracle(cuda_device):
     from ultralytics_pro_b200.nms import non_max_suppression
 
     cfg = CONFIGS["c5_obb_1024_b16"]
-    _, _, y = dense_from_oracle(cfg, 3, seed=23)
-    y = make_scores_unique(y, cfg.nc, cfg.conf)
-    want, want_idx = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc, rotated=True)
-    got, got_idx = non_max_suppression(y.to(cuda_device), cfg.conf, cfg.iou, nc=cfg.nc, rotated=True, return_idxs=True)
-    assert_rows_equal(got, got_idx, want, want_idx, "obb")
+    for batch, conf, iou in ((3, cfg.conf, cfg.iou), (16, cfg.conf, cfg.iou), (2, 0.01, 0.3)):  # 16 = the benchmarked batch
+        _, _, y = dense_from_oracle(cfg, batch, seed=23)
+        y = make_scores_unique(y, cfg.nc, conf)
+        want, want_idx = nms_oracle(y, conf, iou, nc=cfg.nc, rotated=True)
+        got, got_idx = non_max_suppression(y.to(cuda_device), conf, iou, nc=cfg.nc, rotated=True, return_idxs=True)
+        assert sum(w.shape[0] for w in want) > 0
+        assert_rows_equal(got, got_idx, want, want_idx, f"obb B={batch} conf={conf} iou={iou}")
+
+
+def test_fast_nms_cheap_rejection_is_safe_on_adversarial_boxes(cuda_device):
+    """The cluster Fast-NMS kernel skips the full ProbIoU formula for pairs its cheap bound proves to be below the threshold
+    (|d|^2 > K (T1 + T2), ypb_nms.cu).  Boxes chosen to stress that bound: extreme aspect ratios (irregular -> never
+    skipped), needle boxes at 45 degrees, tiny and huge boxes, heavy overlaps and near-touching neighbours, several
+    thresholds.  Kept indices must equal the oracle's (the N x N ProbIoU matrix of metrics.py:251-284)."""
+    from oracle.postproc_oracle import fast_nms
+    from ultralytics_pro_b200.nms import TorchNMS, batch_probiou
+
+    g = torch.Generator().manual_seed(77)
+    n = 1500
+    centres = torch.rand(40, 2, generator=g) * 900
+    own = torch.randint(0, 40, (n,), generator=g)
+    xy = centres[own] + torch.randn(n, 2, generator=g) * torch.rand(n, 1, generator=g) * 40
+    w = torch.exp(torch.rand(n, generator=g) * 9 - 2)            # 0.13 .. 1100 px
+    ar = torch.exp((torch.rand(n, generator=g) - 0.5) * 12)      # aspect ratios 1/400 .. 400
+    h = (w / ar).clamp(1e-3, 5e3)
+    ang = (torch.rand(n, generator=g) - 0.25) * 3.14159265
+    ang[::7] = 0.78539816                                        # needles on the diagonal: C ~ (a - b) / 2
+    obb = torch.cat([xy, w[:, None], h[:, None], ang[:, None]], 1)
+    obb[5::50, :2] = obb[4::50, :2]                              # exact duplicates of the centre
+    scores = torch.rand(n, generator=g)
+    for thr in (0.7, 0.45, 0.1, 0.01, 0.9):
+        want = fast_nms(obb, scores, thr, "probiou")
+        got = TorchNMS.fast_nms(obb.to(cuda_device), scores.to(cuda_device), thr, iou_func=batch_probiou).cpu()
+        if not torch.equal(got, want):
+            # a differing row must be a borderline pair (CUDA and SLEEF transcendentals differ in the last ulp), never a skipped one
+            from oracle.postproc_oracle import probiou_matrix, stable_desc_order
+
+            order = stable_desc_order(scores)
+            m = probiou_matrix(obb[order], obb[order]).triu_(1)
+            diff = set(got.tolist()) ^ set(want.tolist())
+            pos = {int(v): i for i, v in enumerate(order.tolist())}
+            for idx in diff:
+                col = m[:, pos[idx]]
+                assert float((col - thr).abs().min()) < 1e-5, f"thr={thr}: row {idx} differs without a borderline pair"
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -221,6 +269,12 @@ FUSED = [
     ("c3_val_stress_b32", 2, torch.float32),
     ("c4_p6_1280_b16", 2, torch.float32),
     ("c5_obb_1024_b16", 2, torch.float32),
+    # the benchmarked sizes
+    ("c2_v8x_640_b64", 64, torch.float32),
+    ("c2_v8x_640_b64", 64, torch.bfloat16),
+    ("c3_val_stress_b32", 8, torch.float32),
+    ("c4_p6_1280_b16", 16, torch.float32),
+    ("c5_obb_1024_b16", 16, torch.float32),
 ]
 
 
@@ -244,23 +298,60 @@ def test_fused_equals_two_call(cuda_device, name, batch, dtype):
     assert_rows_equal(one, one_idx, [t.cpu() for t in two], [t.cpu() for t in two_idx], f"fused {name} {dtype}")
 
 
+def _decision_margins(y_img: torch.Tensor, nc: int, conf: float, iou_thr: float, max_wh: float = 7680.0):
+    """How far the oracle's decisions on one decoded image are from flipping: (min |score - conf| over the anchors' best
+    scores, min |IoU - thr| over the comparisons the greedy walk actually makes - a kept row against every row still alive
+    below it, nms.py:276-294)."""
+    import numpy as np
+
+    best, cls = y_img[4:4 + nc].max(0)
+    conf_margin = float((best - conf).abs().min())
+    cand = torch.nonzero(best > conf).squeeze(1)
+    order = cand[torch.sort(best[cand], descending=True, stable=True).indices]
+    b = y_img[:4, order].t().numpy().astype(np.float32)
+    off = (cls[order].float() * max_wh).numpy().astype(np.float32)[:, None]
+    xyxy = np.concatenate([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], 1) + off
+    area = (xyxy[:, 2] - xyxy[:, 0]) * (xyxy[:, 3] - xyxy[:, 1])
+    dead = np.zeros(len(order), bool)
+    iou_margin = 1.0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(len(order)):
+            if dead[i] or i + 1 == len(order):
+                continue
+            w = np.maximum(0, np.minimum(xyxy[i, 2], xyxy[i + 1:, 2]) - np.maximum(xyxy[i, 0], xyxy[i + 1:, 0]))
+            h = np.maximum(0, np.minimum(xyxy[i, 3], xyxy[i + 1:, 3]) - np.maximum(xyxy[i, 1], xyxy[i + 1:, 1]))
+            inter = w * h
+            iou = inter / (area[i] + area[i + 1:] - inter)
+            live = ~dead[i + 1:] & (inter > 0)
+            if live.any():
+                iou_margin = min(iou_margin, float(np.abs(iou[live] - iou_thr).min()))
+            dead[i + 1:] |= iou > iou_thr
+    return conf_margin, iou_margin
+
+
 def test_fused_against_oracle_end_to_end(cuda_device):
-    """decode+NMS against the oracle's decode+NMS: kept anchors identical on tie-free, margin-free data; values within
-    the decode tolerance."""
+    """Our decode + NMS against the oracle's decode + NMS.  The two decodes agree to ~1e-4 px, which
+    moves a score by < 1e-6 and an IoU by < 1e-5; an image is compared only if none of the oracle's decisions sits inside
+    those margins (score within 1e-5 of conf; an IoU the greedy walk evaluates within 1e-5 of the threshold - nms.py:76,
+    292-294).  On every remaining image the kept anchors must be IDENTICAL and the row values within the decode tolerance."""
     from ultralytics_pro_b200.head import postprocess_from_head
 
     cfg = CONFIGS["c2_v8x_640_b64"]
-    levels, _ = make_head_batch(cfg, batch=4, seed=41)
+    nb = 16
+    levels, _ = make_head_batch(cfg, batch=nb, seed=41)
     y = decode_oracle(levels, cfg.strides, cfg.nc)
     want, want_idx = nms_oracle(y, cfg.conf, cfg.iou, nc=cfg.nc)
     got, got_idx = postprocess_from_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc, cfg.conf, cfg.iou, return_idxs=True)
-    same = 0
-    for b in range(4):
+    compared = 0
+    for b in range(nb):
+        conf_margin, iou_margin = _decision_margins(y[b], cfg.nc, cfg.conf, cfg.iou)
+        if conf_margin < 1e-5 or iou_margin < 1e-5:
+            continue
+        compared += 1
         gi, wi = got_idx[b].cpu(), want_idx[b]
-        if gi.shape == wi.shape and torch.equal(gi, wi):
-            same += 1
-            assert float((got[b].cpu() - want[b]).abs().max()) <= 1e-5 * cfg.imgsz + 1e-5 * float(want[b].abs().max())
-    assert same >= 3, "kept sets diverge beyond borderline effects"
+        assert gi.shape == wi.shape and torch.equal(gi, wi), f"image {b}: kept anchors differ (margins {conf_margin:.2e}, {iou_margin:.2e})"
+        assert float((got[b].cpu() - want[b]).abs().max()) <= 1e-5 * cfg.imgsz + 1e-5 * float(want[b].abs().max())
+    assert compared >= nb // 2, f"only {compared} of {nb} images had margin-free decisions"
 
 
 # ------------------------------------------------------------------------------------------------------------------

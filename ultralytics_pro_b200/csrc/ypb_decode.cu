@@ -372,19 +372,30 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
   if (my_rows > 0) {
     uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
     int rpos = s_base[0] + roff;
+    if constexpr (MULTI) {
+      // second streaming pass over the same class rows (now L2 hits), with the same coalesced 128-bit loads: anchor i of
+      // this thread owns the slots [cur[i], cur[i] + rows[i]) and fills them class by class.  In val mode (conf 0.001) nearly
+      // every anchor has a row, so a per-anchor scalar re-read would serialise 4 x nc uncoalesced loads per thread.
+      int cur[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      if (rows[i] == 0) continue;
-      const uint32_t row0 = static_cast<uint32_t>(a_glob + i) << f.cls_bits;
-      if constexpr (MULTI) {
-        for (int c = 0; c < nc; ++c) {
-          float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(csrc[static_cast<long long>(c) * cs + i])));
-          if (s > conf && class_allowed(f.class_mask, c)) {
-            if (rpos < f.rows_cap) keys[rpos] = make_key(s, row0 + c);
-            ++rpos;
+      for (int i = 0; i < VEC; ++i) { cur[i] = rpos; rpos += rows[i]; }
+      auto emit = [&](const Pack<TI, VEC>& p, int c) {
+        if (!class_allowed(f.class_mask, c)) return;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float s = DV::rnd(sigmoid_f(DType<DT_IN>::to_f(p.v[i])));
+          if (rows[i] > 0 && s > conf) {  // rows[i] == 0: NaN anchor (nms.py:76) or nothing above conf
+            if (cur[i] < f.rows_cap) keys[cur[i]] = make_key(s, (static_cast<uint32_t>(a_glob + i) << f.cls_bits) + c);
+            ++cur[i];
           }
         }
-      } else {
+      };
+      stream_rows<TI, VEC>(csrc, cs, nc, emit);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (rows[i] == 0) continue;
+        const uint32_t row0 = static_cast<uint32_t>(a_glob + i) << f.cls_bits;
         if (rpos < f.rows_cap) keys[rpos] = make_key(score[i], row0 + cls[i]);
         ++rpos;
       }

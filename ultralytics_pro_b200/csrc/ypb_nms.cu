@@ -11,7 +11,13 @@
 //
 // All IoU arithmetic uses explicit round-to-nearest intrinsics in the reference's operation order (no FMA
 // contraction), so kept sets are bit-exact against torchvision.ops.nms / TorchNMS (SURVEY.md section 7 "Hard parts").
+#include <cooperative_groups.h>
+
+#include <atomic>
+
 #include "ypb_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ypb {
 
@@ -371,9 +377,93 @@ __device__ const uint64_t* radix_sort_global(uint64_t* a, uint64_t* b, int n, Sm
   return src;
 }
 
+// Radix select of a PREFIX of the ascending key order: finds a threshold T such that k = |{key <= T}| lies in [lo, hi]
+// (1 <= lo <= hi <= n) and copies those k keys, unordered, to out.  MSD digits of SEL_BITS bits: one histogram pass over
+// the keys still matching the chosen high bits per digit; the pass ends the search as soon as a bucket boundary falls
+// inside [lo, hi] - typically the first or second digit - else the straddling bucket is refined.  Keys are unique, so the
+// search ends at the latest when all 64 bits are fixed.
+constexpr int SEL_BITS = 11;
+__device__ int select_prefix(const uint64_t* __restrict__ keys, int n, int lo, int hi, uint64_t* __restrict__ out, Smem& sm) {
+  static_assert((1 << SEL_BITS) * 4 <= NW * 256 * 4, "digit histogram fits the radix scratch");
+  uint32_t* hist = sm.u.rx.wc;  // (1 << SEL_BITS) bins
+  __shared__ unsigned long long s_thr;
+  __shared__ int s_state[3];    // [0] rows below the current bucket, [1] done flag, [2] compaction cursor
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long prefix = 0;  // chosen high bits, right-aligned
+  int fixed = 0;                  // how many high bits are chosen
+  int below = 0;                  // keys strictly below the current bucket
+  while (true) {
+    const int w = min(SEL_BITS, 64 - fixed);
+    const int shift = 64 - fixed - w;
+    const uint32_t dmask = (1u << w) - 1u;
+    for (int i = tid; i < (1 << SEL_BITS); i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long k = keys[i];
+      if (fixed == 0 || (k >> (64 - fixed)) == prefix) atomicAdd(&hist[static_cast<uint32_t>(k >> shift) & dmask], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {  // one warp scans the bins in order: first bin whose inclusive cumulative count reaches lo
+      int run = below, found = -1, cum_at = 0, before_at = 0;
+      for (int d0 = 0; d0 < (1 << w) && found < 0; d0 += 32) {
+        const int v = static_cast<int>(hist[d0 + lane]);
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const unsigned hitm = __ballot_sync(0xffffffffu, run + inc >= lo);
+        if (hitm) {
+          const int l = __ffs(hitm) - 1;
+          found = d0 + l;
+          cum_at = run + __shfl_sync(0xffffffffu, inc, l);
+          before_at = cum_at - __shfl_sync(0xffffffffu, v, l);
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) {
+        // found >= 0 always: the bucket holds >= lo - below keys by construction
+        const unsigned long long np = (prefix << w) | static_cast<unsigned long long>(found);
+        if (cum_at <= hi || shift == 0) {
+          s_thr = shift == 0 ? np : ((np << shift) | ((1ull << shift) - 1ull));
+          s_state[0] = cum_at;
+          s_state[1] = 1;
+        } else {
+          s_thr = np;
+          s_state[0] = before_at;
+          s_state[1] = 0;
+        }
+        s_state[2] = 0;
+      }
+    }
+    __syncthreads();
+    const bool done = s_state[1] != 0;
+    if (done) break;
+    prefix = s_thr;
+    below = s_state[0];
+    fixed += w;
+    __syncthreads();
+  }
+  const unsigned long long thr = s_thr;
+  const int k = s_state[0];
+  for (int base = 0; base < n; base += NT) {  // unordered compaction, one shared-memory atomic per warp
+    const int i = base + tid;
+    const unsigned long long key = i < n ? keys[i] : ~0ull;
+    const bool take = i < n && key <= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    int pos = 0;
+    if (lane == 0 && m) pos = atomicAdd(&s_state[2], __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (take) out[pos + __popc(m & ((1u << lane) - 1u))] = key;
+  }
+  __syncthreads();
+  return k;
+}
+
 // Optional phase timestamps (diagnostic, ypb_debug_set_phase_buffer): per CTA 32 clock64 marks.
-static long long* g_phase_buf = nullptr;
-void set_phase_buffer(long long* p) { g_phase_buf = p; }
+static std::atomic<long long*> g_phase_buf{nullptr};
+void set_phase_buffer(long long* p) { g_phase_buf.store(p, std::memory_order_relaxed); }
 #define YPB_MARK(slot)                                                                   \
   do {                                                                                   \
     if (a.dbg && threadIdx.x == 0 && (slot) < 32) a.dbg[blockIdx.x * 32 + (slot)] = clock64(); \
@@ -640,18 +730,122 @@ __device__ __forceinline__ float load_pred(const void* p, int dt, long long off)
   return load_as_float<YPB_BF16>(p, off);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// stage 3: gather the kept rows (nms.py:159-161), riders, optional rescale, zero padding and the one-sided peer push.
+// kk = kept keys in rank order (shared or global memory), kept_n <= max_det.  Called by every thread of ONE CTA.
+// ---------------------------------------------------------------------------------------------------------------
 template <int RULE>
-__global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant__ SuppressArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const int b = blockIdx.x;
+__device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, int kept_n) {
+  const int tid = threadIdx.x;
+  const int cbits = a.cls_bits;
+  const uint32_t cmask = (1u << cbits) - 1u;
+  const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
+  if (tid == 0) a.out_count[b] = kept_n;
+  const int cols = 6 + a.extra;
+  const float* cand_ang3 = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
+  for (int k = tid; k < kept_n; k += NT) {
+    const uint64_t key = kk[k];
+    const uint32_t row = key_row(key);
+    const uint32_t anchor = row >> cbits, cls = row & cmask;
+    if (a.out_idx) a.out_idx[static_cast<long long>(b) * a.max_det + k] = a.idx_as_row ? row : anchor;
+    if (a.out_rows) {
+      float* o = a.out_rows + (static_cast<long long>(b) * a.max_det + k) * cols;
+      float4 bx = cand_box[anchor];
+      o[4] = key_score(key);
+      o[5] = static_cast<float>(cls);
+      if (a.pred) {
+        const long long base = static_cast<long long>(b) * a.pred_sb + static_cast<long long>(anchor) * a.pred_sa;
+        for (int e = 0; e < a.extra; ++e)
+          o[6 + e] = load_pred(a.pred, a.pred_dtype, base + static_cast<long long>(4 + a.nc + e) * a.pred_sc);
+      } else if (a.extra == 1 && cand_ang3) {
+        o[6] = cand_ang3[anchor];
+      }
+      // (riders of the fused path are gathered below, one (row, channel) pair per thread)
+      if (a.scale_xforms) {
+        // detect/predict.py:120 (scale_boxes) or obb/predict.py:59-60 (regularize_rboxes + scale_boxes(xywh=True)),
+        // fused into the gather: the angle is the row's last column (nms.py:146)
+        const ypb_scale_xform xf = a.scale_xforms[b];
+        if constexpr (RULE == YPB_NMS_FAST_PROBIOU)
+          scale_box(bx.x, bx.y, bx.z, bx.w, o + cols - 1, xf, YPB_BOXES_XYWHR, a.scale_padding);
+        else
+          scale_box(bx.x, bx.y, bx.z, bx.w, nullptr, xf, YPB_BOXES_XYXY, a.scale_padding);
+      }
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    }
+  }
+  if (a.pad_zero && a.out_rows) {  // exporter.py:1478-1479: rows past the kept count are zeros
+    float* o = a.out_rows + static_cast<long long>(b) * a.max_det * cols;
+    for (int i = kept_n * cols + tid; i < a.max_det * cols; i += NT) o[i] = 0.f;
+  }
+  if (a.rider && a.out_rows) {
+    // Segment / Pose riders (head.py:837 mask coefficients, head.py:1252 decoded keypoints): only the kept anchors'
+    // values are ever read.  Keypoints are decoded here (head.py:1254-1273) and, when the gather rescales to the original
+    // image, scaled like pose/predict.py:73-75 (scale_coords).
+    const int total = kept_n * a.extra;
+    for (int t = tid; t < total; t += NT) {
+      const int k = t / a.extra, e = t - k * a.extra;
+      const uint32_t anchor = key_row(kk[k]) >> cbits;
+      float v = load_pred(a.rider, a.rider_dtype, static_cast<long long>(b) * a.rider_sb + static_cast<long long>(e) * a.rider_sc + anchor);
+      if (a.rider_kind == YPB_RIDER_KEYPOINTS) {
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < YPB_MAX_LEVELS; ++i)
+          if (i < a.lv_n && static_cast<int>(anchor) >= a.lv_start[i]) l = i;
+        const int loc = static_cast<int>(anchor) - a.lv_start[l];
+        const int gy = loc / a.lv_w[l], gx = loc - gy * a.lv_w[l];
+        const int d = e % a.rider_ndim;
+        const float fx = static_cast<float>(gx) + 0.5f, fy = static_cast<float>(gy) + 0.5f;
+        if (a.rider_dtype == YPB_F32) v = kpt_value<YPB_F32>(v, d, fx, fy, a.lv_stride[l]);
+        else if (a.rider_dtype == YPB_F16) v = kpt_value<YPB_F16>(v, d, DType<YPB_F16>::rnd(fx), DType<YPB_F16>::rnd(fy), a.lv_stride[l]);
+        else v = kpt_value<YPB_BF16>(v, d, DType<YPB_BF16>::rnd(fx), DType<YPB_BF16>::rnd(fy), a.lv_stride[l]);
+        if (a.scale_xforms) v = scale_coord(v, d, a.scale_xforms[b], a.scale_padding);
+      }
+      a.out_rows[(static_cast<long long>(b) * a.max_det + k) * cols + 6 + e] = v;
+    }
+  }
+  if (a.num_peers > 0 && a.out_rows) {
+    // ---- one-sided gather over NVLink (ypb_nms_out.peer_*): the kept rows of this image are contiguous floats in the
+    //      local result buffer; copy them and the count into every peer's buffer with plain (peer-mapped) stores, then
+    //      the last CTA of the launch publishes the launch sequence number in every peer's arrival flag.
+    __syncthreads();  // the local rows of this image are complete
+    const int nfl = kept_n * cols;
+    const long long img_off = static_cast<long long>(b) * a.max_det * cols;
+    const float* src = a.out_rows + img_off;
+    for (int p = 0; p < a.num_peers; ++p) {
+      float* dst = a.peer_rows[p] + img_off;
+      if (dst != src) {
+        if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+          for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+          for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
+        } else {
+          for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
+        }
+      }
+      if (tid == 0 && a.peer_count[p] + b != a.out_count + b) a.peer_count[p][b] = kept_n;
+    }
+    // every thread's remote stores are ordered before the barrier; ONE system-scope fence by the thread that then
+    // publishes (fences are cumulative), instead of 512 fences each waiting for its own remote acknowledgements
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const int prev = atomicAdd(&a.peer_state[0], 1);
+      if (prev == a.batch - 1) {  // last image of the launch
+        a.peer_state[0] = 0;
+        const int seq = a.peer_state[1] + 1;
+        a.peer_state[1] = seq;
+        __threadfence_system();
+        for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
+      }
+    }
+  }
+}
+
+// Ranks and walks the n candidate rows of image b with one CTA (stages 1 and 2 of the file header); returns the number of
+// kept rows (<= max_det) and, in *kk_out, their keys in rank order (shared or global memory).
+template <int RULE>
+__device__ int suppress_image(Smem& sm, const SuppressArgs& a, int b, int n, const uint64_t** kk_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-
-  YPB_MARK(0);
-  const int emitted = a.row_count[b];
-  const int n = min(emitted, a.rows_cap);
-  if (tid == 0 && a.out_cand) a.out_cand[b] = emitted;
 
   uint64_t* ka = a.keys_a + static_cast<long long>(b) * a.rows_cap;
   uint64_t* kb = a.keys_b + static_cast<long long>(b) * a.rows_cap;
@@ -664,12 +858,31 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   int kept_n = 0;
   const uint64_t* kk = nullptr;  // kept keys in rank order (stage 3 input)
 
+  // More rows than shared memory ranks at once (val mode: conf 0.001, multi_label - tens of thousands of rows): the walk
+  // stops at max_det kept rows (nms.py:157), which it normally reaches within the first few thousand ranks.  So first take a
+  // PREFIX of the ranking - the nn best keys, SORT_SMEM_MAX/2 <= nn <= SORT_SMEM_MAX, found by a radix select that never sorts
+  // the rest - and run the ordinary shared-memory paths on it.  The kept rows of a prefix are the kept rows of the full
+  // walk restricted to those ranks (a row is only ever suppressed by higher-ranked rows), so if the prefix yields max_det
+  // kept rows - or was the whole ranking - the result is exact; otherwise the full sort + walk below runs after all.
+  uint64_t* kin = ka;
+  int nn = n;
+  bool partial = false;
+  if constexpr (RULE == YPB_NMS_GREEDY) {
+    if (n > SORT_SMEM_MAX && a.max_det <= SORT_SMEM_MAX / 4) {  // a prefix can only pay off if max_det rows fit well inside it
+      const int L = min(n, a.max_nms);
+      nn = select_prefix(ka, n, min(L, SORT_SMEM_MAX / 2), min(L, SORT_SMEM_MAX), kb, sm);
+      kin = kb;
+      partial = nn < L;
+    }
+  }
+  while (true) {
+  kept_n = 0;
   // ---- fast path: class-wise walk (class-aware greedy rule, everything fits shared memory) ----------------------------
   bool done = false;
   if constexpr (RULE == YPB_NMS_GREEDY) {
-    if (a.max_wh > 0.f && a.box_div == 0.f && n <= SORT_SMEM_MAX && n <= a.max_nms && (1 << a.cls_bits) <= CW_CLASS_MAX &&
-        a.anchor_bits <= 20 && n > 0) {
-      const int r = classwise_greedy(sm, a, ka, n, cand_box, gthr);
+    if (a.max_wh > 0.f && a.box_div == 0.f && nn <= SORT_SMEM_MAX && nn <= a.max_nms && (1 << a.cls_bits) <= CW_CLASS_MAX &&
+        a.anchor_bits <= 20 && nn > 0) {
+      const int r = classwise_greedy(sm, a, kin, nn, cand_box, gthr);
       if (r >= 0) { kept_n = r; kk = reinterpret_cast<const uint64_t*>(sm.cbox); done = true; }
     }
   }
@@ -678,13 +891,13 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
   if (!done) {
   // ---- stage 1 ---------------------------------------------------------------------------------------------------
   const uint64_t* sorted;
-  if (n <= SORT_SMEM_MAX) {
-    bitonic_sort(sm.u.keys, ka, n, KeyIdentity{});
+  if (nn <= SORT_SMEM_MAX) {
+    bitonic_sort(sm.u.keys, kin, nn, KeyIdentity{});
     sorted = sm.u.keys;
   } else {
-    sorted = radix_sort_global(ka, kb, n, sm);
+    sorted = radix_sort_global(kin, kb, nn, sm);  // only reached with kin == ka
   }
-  const int m = min(n, a.max_nms);
+  const int m = min(nn, a.max_nms);
 
   // ---- stage 2 ---------------------------------------------------------------------------------------------------
   const float* cand_ang = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
@@ -890,107 +1103,256 @@ __global__ void __launch_bounds__(NT) sort_suppress_kernel(const __grid_constant
     __syncthreads();
     kk = kept_key;
   }  // !done
+  if (!partial || kept_n >= a.max_det) break;  // uniform
+  partial = false;  // the prefix did not yield max_det rows: rank and walk everything
+  kin = ka;
+  nn = n;
+  __syncthreads();
+  }  // attempts
 
+  *kk_out = kk;
+  return kept_n;
+}
+
+template <int RULE>
+__device__ __noinline__ int legacy_fast_walk(Smem& sm, const SuppressArgs& a, int b, int n, const uint64_t** kk_out) {
+  return suppress_image<RULE>(sm, a, b, n, kk_out);
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(NT, 1) sort_suppress_kernel(const __grid_constant__ SuppressArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  YPB_MARK(0);
+  const int emitted = a.row_count[b];
+  const int n = min(emitted, a.rows_cap);
+  if (tid == 0 && a.out_cand) a.out_cand[b] = emitted;
+  const uint64_t* kk = nullptr;
+  const int kept_n = suppress_image<RULE>(sm, a, b, n, &kk);
   // ---- stage 3 ---------------------------------------------------------------------------------------------------
   YPB_MARK(30);
-  if (tid == 0) a.out_count[b] = kept_n;
-  const int cols = 6 + a.extra;
-  const float* cand_ang3 = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
-  for (int k = tid; k < kept_n; k += NT) {
-    const uint64_t key = kk[k];
-    const uint32_t row = key_row(key);
-    const uint32_t anchor = row >> cbits, cls = row & cmask;
-    if (a.out_idx) a.out_idx[static_cast<long long>(b) * a.max_det + k] = a.idx_as_row ? row : anchor;
-    if (a.out_rows) {
-      float* o = a.out_rows + (static_cast<long long>(b) * a.max_det + k) * cols;
-      float4 bx = cand_box[anchor];
-      o[4] = key_score(key);
-      o[5] = static_cast<float>(cls);
-      if (a.pred) {
-        const long long base = static_cast<long long>(b) * a.pred_sb + static_cast<long long>(anchor) * a.pred_sa;
-        for (int e = 0; e < a.extra; ++e)
-          o[6 + e] = load_pred(a.pred, a.pred_dtype, base + static_cast<long long>(4 + a.nc + e) * a.pred_sc);
-      } else if (a.extra == 1 && cand_ang3) {
-        o[6] = cand_ang3[anchor];
-      }
-      // (riders of the fused path are gathered below, one (row, channel) pair per thread)
-      if (a.scale_xforms) {
-        // detect/predict.py:120 (scale_boxes) or obb/predict.py:59-60 (regularize_rboxes + scale_boxes(xywh=True)),
-        // fused into the gather: the angle is the row's last column (nms.py:146)
-        const ypb_scale_xform xf = a.scale_xforms[b];
-        if constexpr (RULE == YPB_NMS_FAST_PROBIOU)
-          scale_box(bx.x, bx.y, bx.z, bx.w, o + cols - 1, xf, YPB_BOXES_XYWHR, a.scale_padding);
-        else
-          scale_box(bx.x, bx.y, bx.z, bx.w, nullptr, xf, YPB_BOXES_XYXY, a.scale_padding);
-      }
-      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-    }
-  }
-  if (a.pad_zero && a.out_rows) {  // exporter.py:1478-1479: rows past the kept count are zeros
-    float* o = a.out_rows + static_cast<long long>(b) * a.max_det * cols;
-    for (int i = kept_n * cols + tid; i < a.max_det * cols; i += NT) o[i] = 0.f;
-  }
-  if (a.rider && a.out_rows) {
-    // Segment / Pose riders (head.py:837 mask coefficients, head.py:1252 decoded keypoints): only the kept anchors'
-    // values are ever read.  Keypoints are decoded here (head.py:1254-1273) and, when the gather rescales to the original
-    // image, scaled like pose/predict.py:73-75 (scale_coords).
-    const int total = kept_n * a.extra;
-    for (int t = tid; t < total; t += NT) {
-      const int k = t / a.extra, e = t - k * a.extra;
-      const uint32_t anchor = key_row(kk[k]) >> cbits;
-      float v = load_pred(a.rider, a.rider_dtype, static_cast<long long>(b) * a.rider_sb + static_cast<long long>(e) * a.rider_sc + anchor);
-      if (a.rider_kind == YPB_RIDER_KEYPOINTS) {
-        int l = 0;
-#pragma unroll
-        for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-          if (i < a.lv_n && static_cast<int>(anchor) >= a.lv_start[i]) l = i;
-        const int loc = static_cast<int>(anchor) - a.lv_start[l];
-        const int gy = loc / a.lv_w[l], gx = loc - gy * a.lv_w[l];
-        const int d = e % a.rider_ndim;
-        const float fx = static_cast<float>(gx) + 0.5f, fy = static_cast<float>(gy) + 0.5f;
-        if (a.rider_dtype == YPB_F32) v = kpt_value<YPB_F32>(v, d, fx, fy, a.lv_stride[l]);
-        else if (a.rider_dtype == YPB_F16) v = kpt_value<YPB_F16>(v, d, DType<YPB_F16>::rnd(fx), DType<YPB_F16>::rnd(fy), a.lv_stride[l]);
-        else v = kpt_value<YPB_BF16>(v, d, DType<YPB_BF16>::rnd(fx), DType<YPB_BF16>::rnd(fy), a.lv_stride[l]);
-        if (a.scale_xforms) v = scale_coord(v, d, a.scale_xforms[b], a.scale_padding);
-      }
-      a.out_rows[(static_cast<long long>(b) * a.max_det + k) * cols + 6 + e] = v;
-    }
-  }
-  if (a.num_peers > 0 && a.out_rows) {
-    // ---- one-sided gather over NVLink (ypb_nms_out.peer_*): the kept rows of this image are contiguous floats in the
-    //      local result buffer; copy them and the count into every peer's buffer with plain (peer-mapped) stores, then
-    //      the last CTA of the launch publishes the launch sequence number in every peer's arrival flag.
-    __syncthreads();  // the local rows of this image are complete
-    const int nfl = kept_n * cols;
-    const long long img_off = static_cast<long long>(b) * a.max_det * cols;
-    const float* src = a.out_rows + img_off;
-    for (int p = 0; p < a.num_peers; ++p) {
-      float* dst = a.peer_rows[p] + img_off;
-      if (dst != src) {
-        if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
-          for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-          for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
-        } else {
-          for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
-        }
-      }
-      if (tid == 0 && a.peer_count[p] + b != a.out_count + b) a.peer_count[p][b] = kept_n;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const int prev = atomicAdd(&a.peer_state[0], 1);
-      if (prev == static_cast<int>(gridDim.x) - 1) {  // last image of the launch
-        a.peer_state[0] = 0;
-        const int seq = a.peer_state[1] + 1;
-        a.peer_state[1] = seq;
-        __threadfence_system();
-        for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
-      }
-    }
-  }
+  gather_stage<RULE>(a, b, kk, kept_n);
   __syncthreads();
   YPB_MARK(31);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast-NMS over a thread-block CLUSTER (rotated ProbIoU / box_iou rules, nms.py:187-236)
+//
+// Fast-NMS has no sequential dependence: rank j is dropped iff ANY higher rank i < j (kept or not) overlaps it >= thr.
+// A cluster of FC (1, 2, 4 or 8, chosen at launch so that the grid fills the GPU once) CTAs serves one image:
+//   1. every CTA ranks the (<= SORT_SMEM_MAX) keys redundantly in its OWN shared memory (bitonic network) and builds the
+//      per-rank records (covariance terms of metrics.py:187-203) as structure-of-arrays - no cross-CTA traffic in the hot loop;
+//   2. the (target j, source i < j) tests are spread over all FC x NT threads: targets are dealt to the CTAs round-robin
+//      (the cost of a target grows with its rank) and P threads share one target, each taking every P-th source;
+//   3. a pair first takes a CHEAP EXACT-SAFE rejection (see fast_cheap_reject) - a handful of FMAs - and only the few
+//      survivors are queued per warp and then evaluated 32 at a time with the full formula (3 IEEE divisions, 2 square
+//      roots, log, exp), so the expensive path always runs with full lanes;
+//   4. the CTAs OR their "dropped" bitmaps into CTA 0's shared memory through distributed shared memory
+//      (cluster.map_shared_rank), one cluster barrier, and CTA 0 gathers the first max_det survivors in rank order.
+// Images with more rows than shared memory holds take the single-CTA kernel's chunked walk on CTA 0.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FC_MAX = 8;       // CTAs per image at most (portable cluster size limit)
+constexpr int FQ = 64;          // per-warp queue of pairs awaiting the full test
+
+struct __align__(16) FastSmem {
+  uint64_t keys[SORT_SMEM_MAX];   // sorted keys; afterwards the kept keys in rank order
+  float f0[SORT_SMEM_MAX];        // probiou: x        box_iou: x1
+  float f1[SORT_SMEM_MAX];        //          y                 y1
+  float f2[SORT_SMEM_MAX];        //          trace T (< 0: never reject cheaply)   x2
+  float f3[SORT_SMEM_MAX];        //          a                 y2
+  float f4[SORT_SMEM_MAX];        //          b                 area
+  float f5[SORT_SMEM_MAX];        //          c
+  float f6[SORT_SMEM_MAX];        //          det
+  uint32_t dead[SORT_SMEM_MAX / 32];
+  uint32_t queue[NW][FQ];
+  int wsum[NW];
+};
+
+union FastOrLegacy {
+  FastSmem f;
+  Smem legacy;
+};
+
+// Largest Bhattacharyya distance that still suppresses: 1 - sqrt(1 - exp(-bd) + eps) >= thr  <=>  bd <= -ln(1 + eps - (1-thr)^2).
+// Cheap rejection of a pair of REGULAR boxes (finite, w, h > 0, aspect ratio <= 50, so every determinant below is
+// well conditioned in fp32):  t1 + t2 = 0.25 * d^T (S1+S2)^-1 d >= 0.25 |d|^2 / trace(S1+S2)  (smallest eigenvalue of the
+// inverse), t3 >= -1e-3, fp32 evaluation error of t1 + t2 < 1 % under the aspect bound - so
+//     |d|^2 > K (T1 + T2),  K = (bd_max + 0.02) / 0.24   ==>   bd > bd_max   ==>   probiou < thr
+// with margin; the pair is then skipped without evaluating metrics.py:251-284.  Irregular boxes (trace stored as -1) and
+// thresholds below 1e-3 never take the shortcut.
+__device__ __forceinline__ float probiou_reject_factor(float thr) {
+  if (!(thr >= 1e-3f) || !(thr <= 1.0f)) return INFINITY;
+  const double om = 1.0 - static_cast<double>(thr);
+  const double arg = 1.0 + 1e-7 - om * om;
+  const double bd_max = -log(arg);
+  return static_cast<float>((bd_max + 0.02) / 0.24);
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(NT, 1) fast_nms_cluster_kernel(const __grid_constant__ SuppressArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem& fs = reinterpret_cast<FastOrLegacy*>(smem_raw)->f;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = static_cast<int>(cluster.block_rank());
+  const int FC = static_cast<int>(cluster.dim_blocks().x);  // CTAs serving this image
+  const int b = blockIdx.x / FC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  const int emitted = a.row_count[b];
+  const int n = min(emitted, a.rows_cap);
+  if (crank == 0 && tid == 0 && a.out_cand) a.out_cand[b] = emitted;
+  const int cbits = a.cls_bits;
+  const uint32_t cmask = (1u << cbits) - 1u;
+  const float thr = a.iou_thr;
+
+  if (n > SORT_SMEM_MAX) {
+    // uniform over the cluster: CTA 0 runs the single-CTA path (global radix sort + chunked walk), the others leave
+    if (crank != 0) return;
+    Smem& sm = reinterpret_cast<FastOrLegacy*>(smem_raw)->legacy;
+    const uint64_t* kk = nullptr;
+    const int kept_n = legacy_fast_walk<RULE>(sm, a, b, n, &kk);
+    gather_stage<RULE>(a, b, kk, kept_n);
+    return;
+  }
+
+  uint64_t* ka = a.keys_a + static_cast<long long>(b) * a.rows_cap;
+  const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
+  const float* cand_ang = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
+
+  // ---- 1. rank + records (every CTA, redundantly) ------------------------------------------------------------------------
+  for (int w = tid; w < SORT_SMEM_MAX / 32; w += NT) fs.dead[w] = 0u;
+  bitonic_sort(fs.keys, ka, n, KeyIdentity{});
+  const int m = min(n, a.max_nms);
+  for (int r = tid; r < m; r += NT) {
+    const uint32_t row = key_row(fs.keys[r]);
+    const uint32_t anchor = row >> cbits, cls = row & cmask;
+    const float4 bx = cand_box[anchor];
+    const float off = __fmul_rn(static_cast<float>(cls), a.max_wh);  // nms.py:143
+    if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+      const float ang = cand_ang[anchor];
+      const ObbRec o = obb_record(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), bx.z, bx.w, ang);  // nms.py:146
+      const float w = bx.z, h = bx.w;
+      const bool regular = isfinite(o.x) && isfinite(o.y) && isfinite(ang) && w > 0.f && h > 0.f && w <= 1e5f && h <= 1e5f &&
+                           fmaxf(w, h) <= 50.f * fminf(w, h) && fabsf(o.x) <= 1e8f && fabsf(o.y) <= 1e8f;
+      fs.f0[r] = o.x; fs.f1[r] = o.y;
+      fs.f2[r] = regular ? (w * w + h * h) * (1.0f / 12.0f) : -1.f;
+      fs.f3[r] = o.a; fs.f4[r] = o.b; fs.f5[r] = o.c; fs.f6[r] = o.det;
+    } else {
+      const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+      fs.f0[r] = ob.x; fs.f1[r] = ob.y; fs.f2[r] = ob.z; fs.f3[r] = ob.w; fs.f4[r] = box_area(ob);
+    }
+  }
+  cluster.sync();  // records visible in this CTA; every CTA of the cluster is running and has cleared its bitmap
+
+  // ---- 2. pair tests ----------------------------------------------------------------------------------------------------
+  const float K = RULE == YPB_NMS_FAST_PROBIOU ? probiou_reject_factor(thr) : 0.f;
+  int P = 1;                                    // threads per target: as many as the cluster has to spare
+  while (P < 32 && 2 * P * m <= FC * NT) P <<= 1;
+  const int q = tid & (P - 1);
+  const int slots = NT / P;                     // targets per CTA per pass
+  uint32_t* queue = fs.queue[warp];
+  int qn = 0;                                   // warp-uniform
+  auto full_test = [&](uint32_t packed) {
+    const int j = packed >> 16, i = packed & 0xffffu;
+    bool hit;
+    if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+      const ObbRec hi{fs.f0[i], fs.f1[i], fs.f3[i], fs.f4[i], fs.f5[i], fs.f6[i]};
+      const ObbRec me{fs.f0[j], fs.f1[j], fs.f3[j], fs.f4[j], fs.f5[j], fs.f6[j]};
+      hit = probiou_suppresses(hi, me, thr);
+    } else {
+      hit = boxiou_suppresses(make_float4(fs.f0[i], fs.f1[i], fs.f2[i], fs.f3[i]), fs.f4[i],
+                              make_float4(fs.f0[j], fs.f1[j], fs.f2[j], fs.f3[j]), fs.f4[j], thr);
+    }
+    if (hit) atomicOr(&fs.dead[j >> 5], 1u << (j & 31));
+  };
+  for (int base = 0; base < m; base += slots * FC) {
+    const int j = base + (tid / P) * FC + crank;
+    const bool valid = j < m;
+    float jx = 0.f, jy = 0.f, jt = -1.f, jx2 = 0.f, jy2 = 0.f;
+    if (valid) {
+      jx = fs.f0[j]; jy = fs.f1[j]; jt = fs.f2[j];
+      if constexpr (RULE != YPB_NMS_FAST_PROBIOU) { jx2 = fs.f2[j]; jy2 = fs.f3[j]; }
+    }
+    // longest chain of the warp (targets grow with the lane): uniform trip count, lanes past their own j idle
+    const int jmax = __reduce_max_sync(0xffffffffu, valid ? j : 0);
+    for (int i = q; i < jmax; i += P) {
+      bool near = false;
+      if (valid && i < j) {
+        if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {
+          const float dx = jx - fs.f0[i], dy = jy - fs.f1[i];
+          const float ti = fs.f2[i];
+          near = !(jt >= 0.f && ti >= 0.f && dx * dx + dy * dy > K * (jt + ti));
+        } else {
+          // box_iou: disjoint boxes have inter == 0 exactly -> iou == 0 < thr (thr > 0); NaNs fall through to the full test
+          near = !(fs.f0[i] >= jx2 || fs.f2[i] <= jx || fs.f1[i] >= jy2 || fs.f3[i] <= jy) || !(thr > 0.f);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, near);
+      if (bal) {
+        if (near) queue[qn + __popc(bal & lt_mask)] = (static_cast<uint32_t>(j) << 16) | static_cast<uint32_t>(i);
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+          qn -= 32;
+          full_test(queue[qn + lane]);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (lane < qn) full_test(queue[lane]);
+  __syncthreads();
+
+  // ---- 3. merge the bitmaps in CTA 0 (distributed shared memory) -----------------------------------------------------------
+  if (crank != 0) {
+    uint32_t* remote = cluster.map_shared_rank(fs.dead, 0);
+    for (int w = tid; w < (m + 31) / 32; w += NT) {
+      const uint32_t v = fs.dead[w];
+      if (v) atomicOr(remote + w, v);
+    }
+  }
+  cluster.sync();
+  if (crank != 0) return;
+
+  // ---- 4. first max_det survivors in rank order, then the gather ----------------------------------------------------------
+  const int nwords = (m + 31) / 32;
+  int kept_total = 0;
+  for (int w0 = 0; w0 < nwords && kept_total < a.max_det; w0 += NT) {
+    const int w = w0 + tid;
+    uint32_t alive = 0u;
+    if (w < nwords) {
+      alive = ~fs.dead[w];
+      if (w == nwords - 1 && (m & 31)) alive &= (1u << (m & 31)) - 1u;
+    }
+    const int c = __popc(alive);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) fs.wsum[warp] = inc;
+    __syncthreads();
+    int before = kept_total + inc - c, total = 0;
+    for (int x = 0; x < NW; ++x) { const int v = fs.wsum[x]; if (x < warp) before += v; total += v; }
+    // the kept keys overwrite the records' f0/f1 arrays (dead after the tests): max_det <= SORT_SMEM_MAX keys of 8 bytes
+    uint64_t* kkw = reinterpret_cast<uint64_t*>(fs.f0);
+    uint32_t rem = alive;
+    int pos = before;
+    while (rem && pos < a.max_det) {
+      const int bit = __ffs(rem) - 1;
+      rem &= rem - 1;
+      kkw[pos++] = fs.keys[w * 32 + bit];
+    }
+    kept_total += total;
+    __syncthreads();
+  }
+  const int kept_n = min(kept_total, a.max_det);
+  gather_stage<RULE>(a, b, reinterpret_cast<const uint64_t*>(fs.f0), kept_n);
 }
 
 __global__ void peer_wait_kernel(const int32_t* flags, int world, int32_t* state, int lag) {
@@ -1090,33 +1452,56 @@ cudaError_t launch_pairwise_iou(const float* a, int n, const float* b, int m, in
   return cudaGetLastError();
 }
 
+template <int RULE>
+static cudaError_t launch_fast_cluster(const SuppressArgs& a, int dev, cudaStream_t st) {
+  static std::atomic<bool> configured[64];
+  const size_t smem = sizeof(FastOrLegacy);
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(fast_nms_cluster_kernel<RULE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
+  }
+  int fc = FC_MAX;  // the largest cluster that still lets every image start in the first wave of 148 SMs
+  while (fc > 1 && static_cast<long long>(a.batch) * fc > 148) fc >>= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(a.batch) * fc);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = fc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fast_nms_cluster_kernel<RULE>, a);
+}
+
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
   const size_t smem = sizeof(Smem);
   // opt in to > 48 KB dynamic shared memory once per (device, rule); not a stream operation, safe under graph capture
-  static bool configured[64][3] = {};
+  static std::atomic<bool> configured[64][3];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (a.rule < 0 || a.rule > 2) return cudaErrorInvalidValue;
-  const bool need_cfg = dev < 0 || dev >= 64 || !configured[dev][a.rule];
+  if (a.batch <= 0) return cudaSuccess;
   SuppressArgs aa = a;
-  aa.dbg = g_phase_buf;
-#define YPB_SS(R)                                                                                                \
-  do {                                                                                                           \
-    if (need_cfg) {                                                                                              \
-      e = cudaFuncSetAttribute(sort_suppress_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) return e;                                                                            \
-    }                                                                                                            \
-    sort_suppress_kernel<R><<<a.batch, NT, smem, st>>>(aa);                                                      \
-  } while (0)
-  switch (a.rule) {
-    case YPB_NMS_GREEDY: YPB_SS(YPB_NMS_GREEDY); break;
-    case YPB_NMS_FAST_PROBIOU: YPB_SS(YPB_NMS_FAST_PROBIOU); break;
-    case YPB_NMS_FAST_BOXIOU: YPB_SS(YPB_NMS_FAST_BOXIOU); break;
-    default: return cudaErrorInvalidValue;
+  aa.dbg = g_phase_buf.load(std::memory_order_relaxed);
+  if (a.rule == YPB_NMS_FAST_PROBIOU || a.rule == YPB_NMS_FAST_BOXIOU) {
+    aa.dbg = nullptr;
+    e = a.rule == YPB_NMS_FAST_PROBIOU ? launch_fast_cluster<YPB_NMS_FAST_PROBIOU>(aa, dev, st)
+                                       : launch_fast_cluster<YPB_NMS_FAST_BOXIOU>(aa, dev, st);
+    return e != cudaSuccess ? e : cudaGetLastError();
   }
-#undef YPB_SS
-  if (dev >= 0 && dev < 64) configured[dev][a.rule] = true;
+  const bool need_cfg = dev < 0 || dev >= 64 || !configured[dev][a.rule].load(std::memory_order_acquire);
+  if (need_cfg) {
+    e = cudaFuncSetAttribute(sort_suppress_kernel<YPB_NMS_GREEDY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev][a.rule].store(true, std::memory_order_release);
+  }
+  sort_suppress_kernel<YPB_NMS_GREEDY><<<a.batch, NT, smem, st>>>(aa);
   return cudaGetLastError();
 }
 
