@@ -1279,7 +1279,8 @@ __global__ void __launch_bounds__(NT, 1) fast_nms_cluster_kernel(const __grid_co
     }
     // longest chain of the warp (targets grow with the lane): uniform trip count, lanes past their own j idle
     const int jmax = __reduce_max_sync(0xffffffffu, valid ? j : 0);
-    for (int i = q; i < jmax; i += P) {
+    for (int i0 = 0; i0 < jmax; i0 += P) {  // uniform trip count: the warp votes inside
+      const int i = i0 + q;
       bool near = false;
       if (valid && i < j) {
         if constexpr (RULE == YPB_NMS_FAST_PROBIOU) {

@@ -23,7 +23,8 @@ def _scratch(device: torch.device, nbytes: int) -> torch.Tensor:
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = pool.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        with torch.inference_mode(False):
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         pool[key] = buf
     return buf
 
@@ -31,7 +32,8 @@ def _scratch(device: torch.device, nbytes: int) -> torch.Tensor:
 def _pinned_counts(n: int) -> torch.Tensor:
     buf = getattr(_tls, "pinned", None)
     if buf is None or buf.numel() < n:
-        buf = _tls.pinned = torch.empty(max(n, 256), dtype=torch.int32, pin_memory=True)
+        with torch.inference_mode(False):  # a cached buffer must stay writable outside the inference_mode it was first needed in
+            buf = _tls.pinned = torch.empty(max(n, 256), dtype=torch.int32, pin_memory=True)
     return buf[:n]
 
 
@@ -138,6 +140,17 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
             cache.move_to_end(key)
             hit.scratch = _scratch(device, hit.scratch_bytes)  # the pool buffer may have been regrown since
             return hit
+    if key is not None and torch.is_inference_mode_enabled():
+        # tensors of a CACHED plan outlive this call: create them as normal tensors, so a later call outside
+        # inference_mode may still update them in place (set_transforms)
+        with torch.inference_mode(False):
+            plan = make_plan(device, batch, anchors, nc, extra, conf_t, iou_eff, max_det, max_nms, max_wh, multi_label, rule,
+                             classes, with_scale, scale_padding, None, nms_box, boxes_xyxy, pad_output, None, rows_cap, False)
+        cache = _plan_cache()
+        cache[key] = plan
+        while len(cache) > _PLAN_CACHE_MAX:
+            cache.popitem(last=False)
+        return plan
     rows_cap = (anchors * nc if multi_label else anchors) if rows_cap is None else int(rows_cap)
     rows_cap = max(rows_cap, 1)
     max_nms = max(1, min(int(max_nms), rows_cap))

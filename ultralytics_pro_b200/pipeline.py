@@ -50,14 +50,15 @@ class HeadPostProcessor:
                 rule, iou_eff = _cabi.RULE_FAST_PROBIOU, _cabi.f32_round(self.iou_thres)
             else:
                 rule, iou_eff = _cabi.RULE_GREEDY, _greedy_threshold(self.iou_thres)
-            plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
-                                    iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
-                                    self.multi_label, rule, self.classes, with_scale=self.scale_to_original,
-                                    peer_gather_group=self.peer_gather_group)
-            # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
-            nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
-                                                          plan.params.max_det, plan.params.max_nms, plan.params.rule)
-            plan.scratch = torch.empty(nbytes, dtype=torch.uint8, device=lv0.device)
+            with torch.inference_mode(False):  # the plan's tensors outlive this call (set_image_shapes updates them in place)
+                plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
+                                        iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
+                                        self.multi_label, rule, self.classes, with_scale=self.scale_to_original,
+                                        peer_gather_group=self.peer_gather_group)
+                # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
+                nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
+                                                              plan.params.max_det, plan.params.max_nms, plan.params.rule)
+                plan.scratch = torch.empty(nbytes, dtype=torch.uint8, device=lv0.device)
             self._plans[key] = plan
         return plan
 
@@ -129,8 +130,9 @@ class HeadPostProcessor:
         ent = self._graphs.get(key)
         if ent is None:
             plan = self.enqueue(levels, angle_logits)  # warm-up: plan, scratch and result buffers exist after this
-            out_rows, out_idx = engine.compact_results(plan, True)
-            host = torch.empty((plan.count.numel(),), dtype=torch.int32).pin_memory()
+            with torch.inference_mode(False):
+                out_rows, out_idx = engine.compact_results(plan, True)
+                host = torch.empty((plan.count.numel(),), dtype=torch.int32).pin_memory()
             host.copy_(plan.count, non_blocking=True)
             cur = torch.cuda.current_stream(dev)
             cur.synchronize()
