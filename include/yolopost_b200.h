@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 6
+#define YPB_ABI_VERSION 7
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -147,21 +147,30 @@ typedef struct {
   const ypb_scale_xform* scale_xforms;
   int32_t scale_padding;
   /* One-sided result gather over NVLink peer memory (multi-GPU): when num_peers > 0 the gather stage of
-   * the suppression kernel also stores this rank's kept rows and counts straight into every peer's result buffer
+   * the suppression kernel also stores this rank's kept rows and counts straight into every peer's gather buffer
    * (peer-mapped device pointers, e.g. torch symmetric memory / CUDA IPC) - the analogue of dist.gather_object(stats),
-   * detect/val.py:226-240, without a collective: no rank ever waits for another inside the step.
-   *   peer_rows[p] / peer_count[p] : where THIS rank's (B, max_det, cols) rows / (B) counts live in peer p's buffer
+   * detect/val.py:226-240, without a collective: no rank ever waits for another's KERNEL inside the step.
+   * Every rank's gather buffer is a RING of peer_depth entries, each entry = num_peers slots of one packed result
+   * ((B, max_det, cols) rows then (B) counts); launch number seq (1, 2, ...) of a rank goes to entry seq % peer_depth.
+   *   peer_rows[p] / peer_count[p] : where THIS rank's rows / counts live in ENTRY 0 of peer p's ring (p = my_rank: the local ring)
+   *   peer_entry_stride            : floats between consecutive ring entries
    *   peer_flag[p]                 : peer p's arrival flags, one int32 per rank; flag[my_rank] is set to the launch
    *                                  sequence number (system-scope release) once all images of the launch are stored
+   *   peer_ack                     : LOCAL int32 per rank, written by the peers' ypb_peer_wait: ack[p] = last launch whose
+   *                                  entry peer p has released.  The kernel does not overwrite entry seq % depth in peer p before
+   *                                  ack[p] >= seq - peer_depth (back-pressure; NULL = none, single-consumer diagnostics only)
    *   peer_state                   : local device int32[4], zero-initialised once by the caller ([0] CTAs done,
-   *                                  [1] launches sent so far = the sequence number ypb_peer_wait waits for) */
+   *                                  [1] launches sent so far = the sequence number ypb_peer_wait waits for,
+   *                                  [2] last batch handed to the consumer) */
   int32_t num_peers;
   int32_t my_rank;
-  int32_t reserved;
+  int32_t peer_depth;
   float* peer_rows[YPB_MAX_PEERS];
   int32_t* peer_count[YPB_MAX_PEERS];
   int32_t* peer_flag[YPB_MAX_PEERS];
   int32_t* peer_state;
+  const int32_t* peer_ack;
+  int64_t peer_entry_stride;
 } ypb_nms_out;
 
 YPB_API int ypb_abi_version(void);
@@ -265,12 +274,16 @@ YPB_API int ypb_match_predictions(const float* preds, int64_t pred_image_stride,
                                   int64_t iou_stride, const float* true_cls, const float* thresholds, int32_t nthr,
                                   uint8_t* correct, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Consumer side of the one-sided gather: enqueues a one-thread kernel that spins (system-scope acquire) until every one
- * of the `world` arrival flags of THIS rank has reached the sequence number of this rank's own latest launch (state[1];
- * all ranks run the same launch sequence), i.e. until the results of the matching launch of every rank have landed in
- * this rank's buffer.  lag > 0 waits for the launch `lag` launches back instead (a pipelined gather: the step never
- * stalls on a slower rank, results of launch i are complete everywhere once launch i+lag has been waited for). */
-YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, void* stream);
+/* Consumer side of the one-sided gather: enqueues a tiny kernel that (1) RELEASES the ring entry the previous ypb_peer_wait
+ * of this lane handed out - every read the consumer enqueued since is stream-ordered before it - by writing its sequence
+ * number into ack[my_rank] of every producer (peer_ack[p] = peer p's acknowledgement array, peer-mapped; NULL = no acks),
+ * then (2) spins (system-scope acquire) until every one of the `world` arrival flags of THIS rank has reached the sequence
+ * number of this rank's own latest launch minus `lag` (state[1]; all ranks run the same launch sequence), i.e. until the
+ * results of that launch of every rank have landed here, and (3) writes that entry's index (seq % depth) to *slot_index
+ * (device int64, may be NULL) for the consumer's kernels.  lag > 0 is a pipelined gather: the step never stalls on a slower
+ * rank; it needs depth >= lag + 2.  The entry stays valid until the NEXT ypb_peer_wait on this lane executes. */
+YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth,
+                          int32_t* const* peer_ack, int32_t my_rank, int64_t* slot_index, void* stream);
 
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode

@@ -220,7 +220,7 @@ def test_new_entry_points_validate_arguments_before_any_launch():
     thr = (C.c_float * 2)(0.5, 0.75)
     assert lib.ypb_match_predictions(None, 0, 6, 5, 1, 0, None, None, None, 0, 0, None, 0, None, thr, 2, None, None, 0, None) == 0
     assert lib.ypb_match_predictions(None, 0, 6, 5, 1, 4, None, None, None, 0, 0, None, 0, None, thr, 0, None, None, 0, None) == -1
-    assert lib.ypb_peer_wait(None, 2, None, 0, None) == -1
+    assert lib.ypb_peer_wait(None, 2, None, 0, 3, None, 0, None, None) == -1
     # ABI structs the header documents
     assert C.sizeof(_cabi.ScaleXform) == 32 and _cabi.MAX_PEERS == 8
     out = _cabi.NmsOut()

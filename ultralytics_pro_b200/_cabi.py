@@ -18,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -113,11 +113,13 @@ class NmsOut(C.Structure):
         ("scale_padding", C.c_int32),
         ("num_peers", C.c_int32),
         ("my_rank", C.c_int32),
-        ("reserved", C.c_int32),
+        ("peer_depth", C.c_int32),
         ("peer_rows", C.c_void_p * MAX_PEERS),
         ("peer_count", C.c_void_p * MAX_PEERS),
         ("peer_flag", C.c_void_p * MAX_PEERS),
         ("peer_state", C.c_void_p),
+        ("peer_ack", C.c_void_p),
+        ("peer_entry_stride", C.c_int64),
     ]
 
 
@@ -213,7 +215,8 @@ def load():
                                           C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]
     lib.ypb_peer_wait.restype = C.c_int
-    lib.ypb_peer_wait.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ypb_peer_wait.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
+                                  C.c_void_p, C.c_void_p]
     lib.ypb_dfl_expectation.restype = C.c_int
     lib.ypb_dfl_expectation.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]

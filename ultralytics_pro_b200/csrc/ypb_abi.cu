@@ -103,6 +103,7 @@ int check_params(const ypb_nms_params* p, const ypb_nms_out* out) {
   if (out->num_peers < 0 || out->num_peers > YPB_MAX_PEERS) return fail(YPB_ERR_INVALID_ARGUMENT, "num_peers=%d outside [0,%d]", out->num_peers, YPB_MAX_PEERS);
   if (out->num_peers > 0) {
     if (out->my_rank < 0 || out->my_rank >= out->num_peers || !out->peer_state) return fail(YPB_ERR_INVALID_ARGUMENT, "peer gather: my_rank / peer_state invalid");
+    if (out->peer_depth < 1 || (out->peer_depth > 1 && out->peer_entry_stride < 1)) return fail(YPB_ERR_INVALID_ARGUMENT, "peer gather: peer_depth=%d / peer_entry_stride invalid", out->peer_depth);
     for (int i = 0; i < out->num_peers; ++i)
       if (!out->peer_rows[i] || !out->peer_count[i] || !out->peer_flag[i]) return fail(YPB_ERR_INVALID_ARGUMENT, "peer gather: pointer of peer %d is NULL", i);
   }
@@ -123,6 +124,7 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_cand = out->cand_count;
   s.scale_xforms = out->scale_xforms; s.scale_padding = out->scale_padding;
   s.num_peers = out->num_peers; s.my_rank = out->my_rank; s.peer_state = out->peer_state;
+  s.peer_ack = out->peer_ack; s.peer_depth = out->peer_depth > 0 ? out->peer_depth : 1; s.peer_entry_stride = out->peer_entry_stride;
   for (int i = 0; i < YPB_MAX_PEERS; ++i) {
     s.peer_rows[i] = out->peer_rows[i]; s.peer_count[i] = out->peer_count[i]; s.peer_flag[i] = out->peer_flag[i];
   }
@@ -515,9 +517,16 @@ int ypb_match_predictions(const float* preds, int64_t pred_image_stride, int64_t
   return YPB_OK;
 }
 
-int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, void* stream) {
+int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth, int32_t* const* peer_ack,
+                  int32_t my_rank, int64_t* slot_index, void* stream) {
   if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
-  cudaError_t e = ypb::launch_peer_wait(flags, world, state, lag, static_cast<cudaStream_t>(stream));
+  if (depth < 1 || (peer_ack && depth < lag + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, lag + 2);
+  if (my_rank < 0 || my_rank >= world) return fail(YPB_ERR_INVALID_ARGUMENT, "my_rank=%d outside [0,%d)", my_rank, world);
+  if (peer_ack)
+    for (int i = 0; i < world; ++i)
+      if (!peer_ack[i]) return fail(YPB_ERR_INVALID_ARGUMENT, "peer_ack[%d] is NULL", i);
+  cudaError_t e = ypb::launch_peer_wait(flags, world, state, lag, depth, peer_ack, my_rank, reinterpret_cast<long long*>(slot_index),
+                                        static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "ypb_peer_wait");
   return YPB_OK;
 }

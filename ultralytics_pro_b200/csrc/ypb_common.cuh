@@ -415,6 +415,9 @@ struct SuppressArgs {
   int32_t* peer_count[YPB_MAX_PEERS];
   int32_t* peer_flag[YPB_MAX_PEERS];
   int32_t* peer_state;
+  const int32_t* peer_ack;        // local: acknowledgements written by the peers' ypb_peer_wait (or null: no back-pressure)
+  int peer_depth;                 // ring entries per rank
+  long long peer_entry_stride;    // floats between ring entries
   long long* dbg;  // diagnostic phase timestamps or null
 };
 void set_phase_buffer(long long* p);
@@ -509,7 +512,8 @@ cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, in
 cudaError_t launch_compact_results(const float* rows, const long long* idx, const int32_t* count, int batch, int max_det,
                                    int cols, float* out_rows, long long* out_idx, int32_t* out_offsets, cudaStream_t st);
 cudaError_t launch_pairwise_iou(const float* a, int n, const float* b, int m, int box_dim, float* out, cudaStream_t st);
-cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, cudaStream_t st);
+cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
+                             int my_rank, long long* slot_index, cudaStream_t st);
 cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st);
 
 }  // namespace ypb

@@ -805,23 +805,32 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
   }
   if (a.num_peers > 0 && a.out_rows) {
     // ---- one-sided gather over NVLink (ypb_nms_out.peer_*): the kept rows of this image are contiguous floats in the
-    //      local result buffer; copy them and the count into every peer's buffer with plain (peer-mapped) stores, then
-    //      the last CTA of the launch publishes the launch sequence number in every peer's arrival flag.
-    __syncthreads();  // the local rows of this image are complete
+    //      local result buffer; copy them and the count into ring entry (seq % depth) of every peer's buffer (this rank's
+    //      own included) with plain peer-mapped stores, then the last CTA of the launch publishes the launch sequence
+    //      number in every peer's arrival flag.  Back-pressure: entry seq % depth was last filled by launch seq - depth; a
+    //      peer has released it once its acknowledgement (written into OUR buffer by its ypb_peer_wait) reached seq - depth.
+    __shared__ int s_seq;
+    if (tid == 0) s_seq = a.peer_state[1] + 1;  // stable during the launch: only its LAST CTA advances peer_state[1]
+    __syncthreads();  // also: the local rows of this image are complete
+    const int seq = s_seq;
+    if (tid < a.num_peers && a.peer_ack) {
+      const volatile int32_t* ack = a.peer_ack + tid;
+      while (*ack - (seq - a.peer_depth) < 0) __nanosleep(64);
+    }
+    __syncthreads();
     const int nfl = kept_n * cols;
     const long long img_off = static_cast<long long>(b) * a.max_det * cols;
+    const long long entry = static_cast<long long>(seq % a.peer_depth) * a.peer_entry_stride;
     const float* src = a.out_rows + img_off;
     for (int p = 0; p < a.num_peers; ++p) {
-      float* dst = a.peer_rows[p] + img_off;
-      if (dst != src) {
-        if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
-          for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-          for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
-        } else {
-          for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
-        }
+      float* dst = a.peer_rows[p] + entry + img_off;
+      if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+        for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
+      } else {
+        for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
       }
-      if (tid == 0 && a.peer_count[p] + b != a.out_count + b) a.peer_count[p][b] = kept_n;
+      if (tid == 0) reinterpret_cast<int32_t*>(reinterpret_cast<float*>(a.peer_count[p]) + entry)[b] = kept_n;
     }
     // every thread's remote stores are ordered before the barrier; ONE system-scope fence by the thread that then
     // publishes (fences are cumulative), instead of 512 fences each waiting for its own remote acknowledgements
@@ -831,7 +840,6 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
       const int prev = atomicAdd(&a.peer_state[0], 1);
       if (prev == a.batch - 1) {  // last image of the launch
         a.peer_state[0] = 0;
-        const int seq = a.peer_state[1] + 1;
         a.peer_state[1] = seq;
         __threadfence_system();
         for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
@@ -840,8 +848,6 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
   }
 }
 
-// Ranks and walks the n candidate rows of image b with one CTA (stages 1 and 2 of the file header); returns the number of
-// kept rows (<= max_det) and, in *kk_out, their keys in rank order (shared or global memory).
 template <int RULE>
 __device__ int suppress_image(Smem& sm, const SuppressArgs& a, int b, int n, const uint64_t** kk_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1356,19 +1362,31 @@ __global__ void __launch_bounds__(NT, 1) fast_nms_cluster_kernel(const __grid_co
   gather_stage<RULE>(a, b, reinterpret_cast<const uint64_t*>(fs.f0), kept_n);
 }
 
-__global__ void peer_wait_kernel(const int32_t* flags, int world, int32_t* state, int lag) {
-  // the sequence number of this rank's own latest launch (set by its last CTA, earlier on this stream): every rank runs
-  // the same launch sequence, so the peers' matching launch carries the same number
+struct PeerAckPtrs { int32_t* p[YPB_MAX_PEERS]; };
+__global__ void peer_wait_kernel_byval(const int32_t* flags, int world, int32_t* state, int lag, int depth, PeerAckPtrs acks,
+                                       int has_ack, int my_rank, long long* slot_index) {
   const int want = state[1] - lag;
-  for (int r = 0; r < world; ++r) {
-    const volatile int32_t* f = flags + r;
-    while (*f - want < 0) __nanosleep(100);
+  const int done = state[2];
+  if (has_ack && threadIdx.x < world) *reinterpret_cast<volatile int32_t*>(acks.p[threadIdx.x] + my_rank) = done;
+  if (threadIdx.x == 0) {
+    if (want > 0) {
+      for (int r = 0; r < world; ++r) {
+        const volatile int32_t* f = flags + r;
+        while (*f - want < 0) __nanosleep(100);
+      }
+    }
+    __threadfence_system();
+    state[2] = want > done ? want : done;
+    if (slot_index) *slot_index = want > 0 ? want % depth : 0;
   }
-  __threadfence_system();
 }
 
-cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, cudaStream_t st) {
-  peer_wait_kernel<<<1, 1, 0, st>>>(flags, world, state, lag);
+cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
+                             int my_rank, long long* slot_index, cudaStream_t st) {
+  PeerAckPtrs acks{};
+  if (peer_ack_host)
+    for (int i = 0; i < world && i < YPB_MAX_PEERS; ++i) acks.p[i] = peer_ack_host[i];
+  peer_wait_kernel_byval<<<1, 32, 0, st>>>(flags, world, state, lag, depth > 0 ? depth : 1, acks, peer_ack_host ? 1 : 0, my_rank, slot_index);
   return cudaGetLastError();
 }
 

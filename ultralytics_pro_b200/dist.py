@@ -82,15 +82,19 @@ def split_packed(out: torch.Tensor, batch_per_rank: int, max_det: int, cols: int
 class PeerGather:
     """One-sided gather of the result buffers over NVLink peer memory (``ypb_nms_out.peer_*``).
 
-    Every rank owns a symmetric buffer ``[world x packed | world arrival flags]`` that all ranks of the node map
-    (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged once at construction).  Rank s's suppression kernel
-    stores its kept rows + counts directly into slot s of EVERY rank's buffer and then raises flag s there; nothing on the
-    step's critical path waits for another rank, unlike an all_gather whose kernels rendezvous.  ``wait()`` enqueues the
-    consumer-side spin (``ypb_peer_wait``) after which ``gathered()`` holds the results of the matching launch of all ranks.
+    Every rank owns a symmetric buffer ``[depth x world x packed | world arrival flags | world acknowledgements]`` that all
+    ranks of the node map (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged once at construction).  Rank
+    s's suppression kernel stores its kept rows + counts of launch number q directly into slot s of ring entry ``q % depth`` of
+    EVERY rank's buffer and then raises flag s there; nothing on the step's critical path waits for another rank's kernel,
+    unlike an all_gather whose kernels rendezvous.  ``wait(lag)`` enqueues the consumer side (``ypb_peer_wait``): it releases
+    the entry the previous ``wait`` handed out (an acknowledgement written into every producer's buffer - a producer never
+    overwrites an entry a peer has not released), then spins until launch ``latest - lag`` of every rank has landed, and
+    leaves that entry's index in ``slot_index`` (device int64) for the consumer's kernels: ``entry()`` / ``gathered()``.
+    The entry stays valid until the next ``wait`` on this instance executes.  ``depth = 3`` serves ``lag`` 0 and 1.
     Construction is collective (same order on every rank).  One instance serves one stream / lane.
-    Consumer contract: slot contents are overwritten by the owner's next launch on this lane; consume (or copy out) on the
-    lane's stream before enqueueing the launch after next.
     """
+
+    DEPTH = 3
 
     def __init__(self, packed_numel: int, nrow: int, device, group=None):
         import torch.distributed._symmetric_memory as symm
@@ -101,9 +105,11 @@ class PeerGather:
 
         if self.world > _cabi.MAX_PEERS:
             raise ValueError(f"peer gather spans one node: world {self.world} > {_cabi.MAX_PEERS}")
-        self.numel, self.nrow = int(packed_numel), int(nrow)
+        self.numel, self.nrow, self.depth = int(packed_numel), int(nrow), self.DEPTH
         self.slot = (self.numel + 3) // 4 * 4  # 16-byte aligned slots
-        total = self.world * self.slot + 16
+        self.entry = self.world * self.slot     # floats per ring entry
+        ring = self.depth * self.entry
+        total = ring + 32                       # + 16 arrival flags + 16 acknowledgements (int32)
         self.buf = symm.empty(total, dtype=torch.float32, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
@@ -114,31 +120,49 @@ class PeerGather:
             self.handle = symm.rendezvous(self.buf, group)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.state = torch.zeros(4, dtype=torch.int32, device=device)
-        self.flags = self.buf[self.world * self.slot: self.world * self.slot + 16].view(torch.int32)
-        self.my_packed = self.buf[self.rank * self.slot: self.rank * self.slot + self.numel]
-        self.peer_rows = [p + self.rank * self.slot * 4 for p in ptrs]
+        self.slot_index = torch.zeros(1, dtype=torch.int64, device=device)
+        self.flags = self.buf[ring: ring + 16].view(torch.int32)
+        self.acks = self.buf[ring + 16: ring + 32].view(torch.int32)
+        self.my_packed = torch.empty(self.numel, dtype=torch.float32, device=device)  # the plan's own result buffer
+        self.peer_rows = [p + self.rank * self.slot * 4 for p in ptrs]                 # my slot in entry 0 of peer p's ring
         self.peer_count = [p + self.nrow * 4 for p in self.peer_rows]
-        self.peer_flag = [p + self.world * self.slot * 4 for p in ptrs]
+        self.peer_flag = [p + ring * 4 for p in ptrs]
+        self.peer_ack = [p + (ring + 16) * 4 for p in ptrs]
+        import ctypes as C
+
+        self._ack_array = (C.c_void_p * self.world)(*self.peer_ack)
         dist.barrier(group)  # every rank has zeroed its buffer before anyone stores into it
 
     def bind(self, out) -> None:
         """Fill the peer fields of a ``_cabi.NmsOut``."""
-        out.num_peers, out.my_rank = self.world, self.rank
+        out.num_peers, out.my_rank, out.peer_depth = self.world, self.rank, self.depth
         for i in range(self.world):
             out.peer_rows[i], out.peer_count[i], out.peer_flag[i] = self.peer_rows[i], self.peer_count[i], self.peer_flag[i]
         out.peer_state = self.state.data_ptr()
+        out.peer_ack = self.acks.data_ptr()
+        out.peer_entry_stride = self.entry
 
     def wait(self, lag: int = 0) -> None:
-        """lag=0: the latest launch of every rank has landed; lag=k: the launch k launches back (pipelined gather)."""
+        """Release the previously returned entry, then wait: lag=0 for the latest launch of every rank, lag=k for the launch k
+        launches back (pipelined gather; k <= depth - 2)."""
         from . import _cabi
 
-        rc = _cabi.load().ypb_peer_wait(self.flags.data_ptr(), self.world, self.state.data_ptr(), int(lag),
-                                        _cabi.stream_ptr(self.buf.device))
+        rc = _cabi.load().ypb_peer_wait(self.flags.data_ptr(), self.world, self.state.data_ptr(), int(lag), self.depth,
+                                        self._ack_array, self.rank, self.slot_index.data_ptr(), _cabi.stream_ptr(self.buf.device))
         _cabi.check(rc, "ypb_peer_wait")
 
+    def ring(self) -> torch.Tensor:
+        """(depth, world, slot) view of the local ring."""
+        return self.buf[: self.depth * self.entry].view(self.depth, self.world, self.slot)
+
+    def entry_tensor(self) -> torch.Tensor:
+        """(world, packed) copy-free-on-host selection of the entry the last executed ``wait`` returned: one device-side
+        ``index_select`` with ``slot_index`` (capturable in a CUDA graph; no host synchronisation)."""
+        return self.ring().index_select(0, self.slot_index)[0][:, : self.numel]
+
     def gathered(self, batch_per_rank: int, max_det: int, cols: int):
-        """(world*B, max_det, cols) rows and (world*B,) int32 counts of the last waited-for launch (views / small copy)."""
-        g = self.buf[: self.world * self.slot].view(self.world, self.slot)[:, : self.numel]
+        """(world*B, max_det, cols) rows and (world*B,) int32 counts of the entry the last executed ``wait`` returned."""
+        g = self.entry_tensor()
         rows = g[:, : self.nrow].reshape(self.world * batch_per_rank, max_det, cols)
         count = g[:, self.nrow:].contiguous().view(torch.int32).reshape(self.world * batch_per_rank)
         return rows, count
