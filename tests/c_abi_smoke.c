@@ -17,7 +17,9 @@ int main(void) {
   if (strlen(ypb_last_error_string()) == 0) { printf("no error text\n"); return 4; }
   ypb_scale_xform xf = {1.f, 0.f, 0.f, 640.f, 640.f, 0.f, 0.f, 0.f};
   if (ypb_scale_rows(NULL, 0, 4, 1, 0, NULL, NULL, &xf, YPB_BOXES_XYXY, YPB_SCALE_PADDING, 0, NULL, 0, 0, 0, 0, NULL) != YPB_OK) return 5;
-  if (ypb_peer_wait(NULL, 2, NULL, 0, NULL) != YPB_ERR_INVALID_ARGUMENT) return 6;
+  if (ypb_peer_wait(NULL, 2, NULL, 0, 3, NULL, 0, NULL, NULL) != YPB_ERR_INVALID_ARGUMENT) return 6;
+  if (ypb_dist2bbox(NULL, 0, 0, NULL, 0, 0, 0, NULL, 0, YPB_F32, 1, 4, 1, NULL, 0, 0, NULL) != YPB_ERR_INVALID_ARGUMENT) return 8;
+  if (ypb_dfl_expectation(NULL, YPB_F32, 1, 8, 4, 0, 0, NULL, 0, 0, NULL) != YPB_ERR_UNSUPPORTED) return 9;
   if (sizeof(ypb_scale_xform) != 32 || YPB_MAX_PEERS != 8) return 7;
   printf("c abi ok, version %d, workspace C2 = %zu bytes\n", ypb_abi_version(), big);
   return 0;
