@@ -203,6 +203,270 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+def _post_for(cfg, gather_mode):
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+
+    return HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, multi_label=cfg.multi_label, agnostic=cfg.agnostic,
+                             rotated=cfg.rotated, max_det=cfg.max_det, max_nms=cfg.max_nms,
+                             peer_gather_group=True if gather_mode == "peer" else None)
+
+
+def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lane_groups=None):
+    """`nlanes` independent pipelines (own stream, plan, scratch, result buffers, CUDA graphs); lane i owns input sets i and
+    i + nlanes.  One step of a lane = [counter memset, class scan, survivor decode, sort+suppress (+ peer push)], then - all
+    inside the lane's CUDA graph - the consumer side: multi-GPU: wait for the gathered batch (`lag` batches back), copy the
+    gathered entry out of the ring (the consumer; the entry is released by the next wait); always: the per-image counts to
+    pinned HOST memory ("detections resident in HBM + counts on host")."""
+    from ultralytics_pro_b200 import dist as ypb_dist
+
+    main = torch.cuda.current_stream(dev)
+    lanes = []
+    for ln in range(nlanes):
+        st = torch.cuda.Stream(dev)
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            pp = _post_for(cfg, gather_mode)
+            my_sets = [sets[(ln + nlanes * j) % len(sets)] for j in range(2)]
+            pl = pp.enqueue(*my_sets[0])  # builds the plan / result buffers (collective when the peer gather is on)
+            host_counts = torch.empty((pl.count.numel(),), dtype=torch.int32).pin_memory()
+            gb = None
+            if gather_mode in ("nccl", "nccl-eager"):
+                gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
+            elif gather_mode == "peer":
+                gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)  # the consumer's copy
+            grp = lane_groups[ln] if lane_groups else None
+
+            def tail(pp=pp, pl=pl, gb=gb, host_counts=host_counts, grp=grp):
+                if gather_mode == "peer":
+                    pp.wait_gather(lag)
+                    gb.copy_(pl.peers.entry_tensor())
+                elif gather_mode == "nccl":
+                    ypb_dist.gather_packed(pl.packed, gb, group=grp)
+                host_counts.copy_(pl.count, non_blocking=True)
+
+            graphs = None
+            if use_graph:
+                graphs = [pp.capture(lv, ang, after=tail) for lv, ang in my_sets]
+        st.synchronize()
+        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": graphs, "plan": pl, "gather": gb, "tail": tail,
+                      "group": grp, "host_counts": host_counts})
+    return lanes
+
+
+def _lane_step(lanes, i, gather_mode):
+    from ultralytics_pro_b200 import dist as ypb_dist
+
+    ln = lanes[i % len(lanes)]
+    j = (i // len(lanes)) % 2
+    with torch.cuda.stream(ln["stream"]):
+        if ln["graphs"] is not None:
+            ln["graphs"][j].replay()
+        else:
+            ln["post"].enqueue(*ln["sets"][j])
+            ln["tail"]()
+        if gather_mode == "nccl-eager":
+            ypb_dist.gather_packed(ln["plan"].packed, ln["gather"], group=ln["group"])
+
+
+def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None):
+    """W warm-up steps, then EXACTLY K timed steps between a barrier + synchronize on both sides; CUDA events on the stream the
+    lanes fork from / join into; max over ranks.  Returns total ms."""
+    import torch.distributed as dist
+
+    main = torch.cuda.current_stream(dev)
+
+    def fork():
+        for ln in lanes:
+            ln["stream"].wait_stream(main)
+
+    def join():
+        for ln in lanes:
+            main.wait_stream(ln["stream"])
+
+    def drain():
+        if gather_mode == "peer" and lag > 0:  # every result of every rank has landed before the clock stops
+            for ln in lanes:
+                with torch.cuda.stream(ln["stream"]):
+                    ln["post"].wait_gather(0)
+
+    fork()
+    for i in range(W):
+        _lane_step(lanes, i, gather_mode)
+    drain()
+    join()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    fork()
+    for i in range(K):
+        _lane_step(lanes, i, gather_mode)
+    drain()
+    join()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _stage_times(dev, post, sets, K):
+    """Per-kernel durations with CUDA events on the launching stream: each prefix of the step (scan | scan+decode |
+    scan+decode+suppress) is captured as a CUDA graph of R back-to-back repetitions over rotating input sets (> L2) and
+    replayed between two events - no host launch gaps inside the timed region; durations = differences of the prefixes."""
+    R = len(sets)
+    tstream = torch.cuda.Stream(dev)
+    prefix_ms = []
+    with torch.cuda.stream(tstream):
+        for mask in (1, 3, 7):
+            post.enqueue(*sets[0], stage=mask)
+            tstream.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=tstream):
+                for r in range(R):
+                    post.enqueue(*sets[r % R], stage=mask)
+            for _ in range(3):
+                gph.replay()
+            tstream.synchronize()
+            KI = max(3, min(K, 200) // R)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(tstream)
+            for _ in range(KI):
+                gph.replay()
+            b.record(tstream)
+            tstream.synchronize()
+            prefix_ms.append(a.elapsed_time(b) / (KI * R))
+            del gph
+    return prefix_ms
+
+
+def _dense_decode_time(dev, cfg, sets, esize, peak, reps):
+    from ultralytics_pro_b200.head import decode_head
+
+    B = sets[0][0][0].shape[0]
+
+    def f(i):
+        lv, ang = sets[i % len(sets)]
+        if cfg.rotated:
+            return decode_head(lv, cfg.strides, cfg.nc, angle=ang, angle_is_logit=True, append_angle=True)
+        return decode_head(lv, cfg.strides, cfg.nc)
+
+    for i in range(3):
+        y = f(i)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    d0.record()
+    for i in range(reps):
+        y = f(i)
+    d1.record()
+    torch.cuda.synchronize(dev)
+    del y
+    t = d0.elapsed_time(d1) / reps
+    ne = 1 if cfg.rotated else 0
+    nbytes = B * cfg.anchors * ((cfg.no + ne) + (4 + cfg.nc + ne)) * esize
+    return {"launch_ms": t, "achieved": nbytes / (t * 1e-3) / 1e9, "unit": "GB/s", "frac": nbytes / (t * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_launch": nbytes}
+
+
+def _e2e(dev, cfg, sets, world, KE):
+    """The metric end to end through the public API with HOST buffers: every step copies that step's head tensors from
+    pinned host memory, runs postprocess_from_head and reads rows + counts back to the host.  Double-buffered: the H2D copy
+    of step k+1 (copy stream) runs under the kernels and the D2H of step k; the host waits for step k-1's results while
+    step k is in flight - every step's inputs still cross PCIe inside the timed region."""
+    import torch.distributed as dist
+
+    from ultralytics_pro_b200.head import postprocess_from_head
+
+    lv0 = sets[0][0]
+    B = lv0[0].shape[0]
+    host_sets = [[lv.cpu().pin_memory() for lv in s[0]] for s in sets[:2]]
+    dev_in = [[torch.empty_like(lv) for lv in lv0] for _ in range(2)]
+    copy_stream, comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    buf_free = [torch.cuda.Event() for _ in range(2)]
+    res_done = [torch.cuda.Event() for _ in range(2)]
+    md = min(cfg.max_det, cfg.anchors)
+    host_rows = [torch.empty((B, md, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_cnt = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    h2d = sum(lv.numel() * lv.element_size() for lv in lv0)
+    d2h = host_rows[0].numel() * 4 + B * 4
+    for e in buf_free:
+        e.record(comp)
+
+    def issue(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(buf_free[k])
+            for dst, src in zip(dev_in[k], host_sets[k]):
+                dst.copy_(src, non_blocking=True)
+            h2d_done[k].record(copy_stream)
+        with torch.cuda.stream(comp):
+            comp.wait_event(h2d_done[k])
+            p = postprocess_from_head(dev_in[k], cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det, sync=False)
+            buf_free[k].record(comp)
+            host_rows[k].copy_(p.rows, non_blocking=True)
+            host_cnt[k].copy_(p.count, non_blocking=True)
+            res_done[k].record(comp)
+
+    def run(n):
+        total = 0
+        for i in range(n):
+            issue(i)
+            if i >= 1:
+                res_done[(i - 1) % 2].synchronize()  # results of the previous step are on the host now
+                total += int(host_cnt[(i - 1) % 2].sum())
+        res_done[(n - 1) % 2].synchronize()
+        return total + int(host_cnt[(n - 1) % 2].sum())
+
+    run(4)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    kept = run(KE)
+    torch.cuda.synchronize(dev)
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    sec = float(el.item())
+    return {"value": world * B * KE / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
+            "h2d_gbs_per_gpu": h2d * KE / sec / 1e9, "kept_total": kept,
+            "note": "postprocess_from_head on pinned HOST head tensors, every step: H2D of the head (copy stream, double-buffered, "
+                    "overlapping the previous step's kernels), decode+NMS, D2H of rows and counts, host waits for each step's result; "
+                    "wall clock, max over ranks"}
+
+
+def _measure_config(dev, name, dtype, K, lanes_n=3):
+    """imgs/s of the fused path on another BASELINE.json config (device-resident inputs, 2 rotating sets, CUDA graphs)."""
+    from ultralytics_pro_b200.synth import CONFIGS, make_head_batch
+
+    cfg = CONFIGS[name]
+    sets = [make_head_batch(cfg, batch=cfg.batch, seed=2000 + s, device=dev, dtype=dtype) for s in range(2 * lanes_n)]
+    lanes = _build_lanes(dev, cfg, sets, lanes_n, 1, "none", 0, True)
+    ms = _time_lanes(dev, lanes, K, 5, 1, "none", 0)
+    pl = lanes[0]["plan"]
+    pre = _stage_times(dev, lanes[0]["post"], sets, K)
+    esize = 4 if dtype == torch.float32 else 2
+    in_bytes = cfg.batch * cfg.anchors * (cfg.no + (1 if cfg.rotated else 0)) * esize
+    rec = {"imgs_per_s": cfg.batch * K / (ms * 1e-3), "ms_per_step": ms / K, "batch": cfg.batch, "lanes": lanes_n,
+           "single_stream_ms": {"scan_classes": pre[0], "decode_tiles": pre[1] - pre[0], "sort_suppress": pre[2] - pre[1], "step": pre[2]},
+           "cand_per_img": float(pl.cand.float().mean()), "kept_per_img": float(pl.count.float().mean()),
+           "head_bytes_per_step": in_bytes, "head_gbs": in_bytes / (ms / K * 1e-3) / 1e9,
+           "l2": f"{len(sets)} rotating input sets of {in_bytes / 1e6:.0f} MB"}
+    del lanes, sets
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -231,9 +495,6 @@ def run_ours(args):
     # HBM-bound class scan of one batch overlaps the latency-bound survivor decode / suppression of the previous one.
     LANES = max(1, args.lanes)
     NSETS = 2 * LANES
-    # one NCCL communicator PER LANE: collectives of different lanes are then unordered with respect to each other, so
-    # each lane's all_gather can be captured inside that lane's CUDA graph and replayed concurrently with the others
-    # (on ONE communicator, replays from several streams have no defined cross-rank order and can deadlock)
     gather_mode = args.gather if world > 1 else "none"
     if gather_mode == "peer":
         # collective probe: if the symmetric-memory mapping is unavailable on this box on ANY rank, all ranks fall back together
@@ -247,114 +508,31 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             gather_mode = "nccl-eager"
-    lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager")
-                   else [None] * LANES)
-    graph_gather = gather_mode == "nccl"
-    sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B)[0]
-            for s in range(NSETS)]
+    # one NCCL communicator PER LANE: collectives of different lanes are then unordered with respect to each other, so each
+    # lane's all_gather can be captured inside that lane's CUDA graph (on ONE communicator, replays from several streams have
+    # no defined cross-rank order and can deadlock)
+    lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager") else None)
+    sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B) for s in range(NSETS)]
     use_graph = not args.no_graph
-    main = torch.cuda.current_stream(dev)
-    lanes = []
-    for ln in range(LANES):
-        st = torch.cuda.Stream(dev)
-        st.wait_stream(main)
-        with torch.cuda.stream(st):
-            pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms,
-                                   peer_gather_group=True if gather_mode == "peer" else None)
-            my_sets = [sets[ln + LANES * j] for j in range(2)]
-            pl = pp.enqueue(my_sets[0])  # builds the plan / result buffers (collective when the peer gather is on)
-            gb = (torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
-                  if gather_mode in ("nccl", "nccl-eager") else None)
-            gr, gather_in_graph = None, False
-            if use_graph:
-                if gather_mode == "peer":
-                    # the suppression kernel itself stores the results into every rank's buffer; the graph ends with the
-                    # consumer-side wait, so at step end every rank holds everyone's detections (all_gather semantics)
-                    # (--gather-lag 1, default: the wait is for the lane's PREVIOUS batch, which has long arrived, so no rank
-                    # ever stalls on a slower one inside a step; the lanes are drained with lag 0 before the timed region ends)
-                    gr = [pp.capture(lv, after=lambda: pp.wait_gather(args.gather_lag)) for lv in my_sets]
-                    gather_in_graph = True
-                if graph_gather:
-                    try:  # the collective rides inside the graph: zero host work per step
-                        grp = lane_groups[ln]
-                        gr = [pp.capture(lv, after=lambda: ypb_dist.gather_packed(pl.packed, gb, group=grp)) for lv in my_sets]
-                        gather_in_graph = True
-                    except Exception as exc:  # older NCCL/torch: capture of collectives unsupported
-                        sys.stderr.write(f"[bench] NCCL capture failed ({exc}); gathering eagerly\n")
-                        gr = None
-                if gr is None:
-                    gr = [pp.capture(lv) for lv in my_sets]
-        st.synchronize()
-        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": gr, "plan": pl, "gather": gb,
-                      "gather_in_graph": gather_in_graph, "group": lane_groups[ln]})
+    lanes = _build_lanes(dev, cfg, sets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups)
     post, plan = lanes[0]["post"], lanes[0]["plan"]
 
-    def step(i):
-        ln = lanes[i % LANES]
-        j = (i // LANES) % 2
-        with torch.cuda.stream(ln["stream"]):
-            if use_graph:
-                ln["graphs"][j].replay()
-            else:
-                ln["post"].enqueue(ln["sets"][j])
-            if gather_mode == "peer" and not use_graph:
-                ln["post"].wait_gather(args.gather_lag)
-            elif gather_mode in ("nccl", "nccl-eager") and not ln["gather_in_graph"]:
-                # the only collective of the path: ONE all_gather of the plan's packed rows+counts buffer (the analogue
-                # of gather_object(stats), detect/val.py:226-240); it overlaps the other lanes' compute
-                ypb_dist.gather_packed(ln["plan"].packed, ln["gather"], group=ln["group"])
-
-    def fork():
-        for ln in lanes:
-            ln["stream"].wait_stream(main)
-
-    def join():
-        for ln in lanes:
-            main.wait_stream(ln["stream"])
-
-    fork()
-    for i in range(W):
-        step(i)
-    join()
-    torch.cuda.synchronize(dev)
-    # everything with a variable host cost (NVML init of the clock sampler, event creation) happens BEFORE the barrier, so
-    # that the ranks enter the timed region together: the peer gather couples them, and a rank that starts late would be
-    # waited for by the others inside THEIR timed regions
+    # everything with a variable host cost (NVML init of the clock sampler, event creation) happens BEFORE the barrier inside
+    # _time_lanes, so that the ranks enter the timed region together
     sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    fork()
-    for i in range(K):
-        step(i)
-    if gather_mode == "peer" and args.gather_lag > 0:  # drain: every result of every rank has landed before the clock stops
-        for ln in lanes:
-            with torch.cuda.stream(ln["stream"]):
-                ln["post"].wait_gather(0)
-    join()
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    sampler.stop()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    sys.stderr.write(f"[bench] rank {rank}: {float(ms.item()) / K * 1e3:.2f} us/step, kept {int(plan.count.sum())} cand {int(plan.cand.sum())}\n")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    total_ms = _time_lanes(dev, lanes, K, W, world, gather_mode, args.gather_lag, sampler)
+    sys.stderr.write(f"[bench] rank {rank}: {total_ms / K * 1e3:.2f} us/step, kept {int(plan.count.sum())} cand {int(plan.cand.sum())}\n")
     value = world * B * K / (total_ms * 1e-3)
     kept = plan.count.sum().item()
     cand = plan.cand.sum().item()
+    counts_on_host = int(lanes[0]["host_counts"].sum())
 
     # ---- multi-GPU: check the one-sided gather against an NCCL all_gather of the same result buffers ------------------
     gather_verified = None
     if gather_mode == "peer":
         ln0 = lanes[0]
         with torch.cuda.stream(ln0["stream"]):
-            ln0["graphs"][0].replay() if use_graph else ln0["post"].enqueue(ln0["sets"][0])
+            ln0["graphs"][0].replay() if use_graph else (ln0["post"].enqueue(*ln0["sets"][0]), ln0["tail"]())
             ln0["post"].wait_gather(0)
         torch.cuda.synchronize(dev)
         dist.barrier()
@@ -369,33 +547,21 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         gather_verified = bool(flag.item())
 
+    # ---- strong scaling (SURVEY 8e / north_star): ONE 64-image batch partitioned over the ranks (data/build.py:171-188) --
+    strong = None
+    if world > 1:
+        lo, hi = ypb_dist.shard_range(B, rank, world)
+        if (hi - lo) * world == B:  # equal shards: the peer ring needs the same packed size on every rank
+            ssets = [([lv[lo:hi] for lv in s[0]], None) for s in sets]
+            slanes = _build_lanes(dev, cfg, ssets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups)
+            sms = _time_lanes(dev, slanes, K, W, world, gather_mode, args.gather_lag)
+            strong = {"global_batch": B, "batch_per_gpu": hi - lo, "value": B * K / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / K,
+                      "scaling": "strong", "note": "one 64-image batch per step split contiguously over the ranks; every rank ends "
+                                                   "each step holding all 64 images' detections"}
+            del slanes, ssets
+
     # ---- per-kernel timing with CUDA events on the launching stream (roofline of the dominant kernel) ---------------
-    # Each prefix of the step (scan | scan+decode | scan+decode+suppress) is captured as a CUDA graph of R back-to-back
-    # repetitions over rotating input sets (> L2) and replayed between two events on its stream: no host launch gaps
-    # inside the timed region, and the per-kernel durations are the differences of the prefix times.
-    R = NSETS
-    tstream = torch.cuda.Stream(dev)
-    prefix_ms = []
-    with torch.cuda.stream(tstream):
-        for mask in (1, 3, 7):
-            post.enqueue(sets[0], stage=mask)
-            tstream.synchronize()
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph, stream=tstream):
-                for r in range(R):
-                    post.enqueue(sets[r % NSETS], stage=mask)
-            for _ in range(3):
-                gph.replay()
-            tstream.synchronize()
-            KI = max(3, min(K, 200) // R)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(tstream)
-            for _ in range(KI):
-                gph.replay()
-            b.record(tstream)
-            tstream.synchronize()
-            prefix_ms.append(a.elapsed_time(b) / (KI * R))
-            del gph
+    prefix_ms = _stage_times(dev, post, sets, K)
     t_scan = prefix_ms[0]                  # ms: counter memset + class-scan/filter kernel
     t_decode = prefix_ms[1] - prefix_ms[0]  # ms: survivor tile box-decode kernel
     t_suppr = prefix_ms[2] - prefix_ms[1]   # ms: sort + suppress + gather kernel
@@ -421,84 +587,39 @@ def run_ours(args):
                                       "note": "all lanes overlapped: the timed region itself, per GPU"}
 
     # ---- dense decode kernel alone (the Detect._inference drop-in), same inputs --------------------------------------
-    from ultralytics_pro_b200.head import decode_head
-
-    for i in range(3):
-        y = decode_head(sets[i % NSETS], cfg.strides, cfg.nc)
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    KD = min(K, 50)
-    torch.cuda.synchronize(dev)
-    d0.record()
-    for i in range(KD):
-        y = decode_head(sets[i % NSETS], cfg.strides, cfg.nc)
-    d1.record()
-    torch.cuda.synchronize(dev)
-    t_dense = d0.elapsed_time(d1) / KD
-    dense_bytes = B * (in_bytes_img + (4 + cfg.nc) * cfg.anchors * esize)
-    dense = {"launch_ms": t_dense, "achieved": dense_bytes / (t_dense * 1e-3) / 1e9, "unit": "GB/s",
-             "frac": dense_bytes / (t_dense * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": dense_bytes}
-    del y
+    dense = _dense_decode_time(dev, cfg, sets, esize, peak, min(K, 50))
 
     # ---- the drop-in boundary: the reference's OWN call sequence (Detect._inference -> non_max_suppression,
     #      predictor.py:335-336 + detect/predict.py:54) through the wrappers patch.install() binds, on a stub module carrying
     #      Detect's attributes (head.py:70-93).  two_call = dense decode kernel + NMS-from-dense kernels; fused = the lazily
     #      decoded tensor hands the level tensors to the fused head->NMS kernels.  Wall clock per call INCLUDING the count
     #      read-back the list-of-tensors return type forces (one stream synchronisation per call, like the reference).
-    dropin = _bench_dropin(dev, cfg, sets, NSETS, min(K, 200))
+    dropin = _bench_dropin(dev, cfg, [s[0] for s in sets], NSETS, min(K, 200))
 
-    # ---- end to end through the public API with HOST buffers: H2D of the head, decode+NMS, D2H of rows+counts ---------
-    KE = min(K, 30)
-    host_sets = [[lv.cpu().pin_memory() for lv in s] for s in sets[:2]]
-    dev_in = [torch.empty_like(lv) for lv in sets[0]]
-    host_rows = torch.empty(plan.rows.shape, dtype=torch.float32).pin_memory()
-    h2d = sum(lv.numel() * lv.element_size() for lv in dev_in)
-    d2h = host_rows.numel() * 4 + B * 4
-
-    def e2e_step(i):
-        for dst, src in zip(dev_in, host_sets[i % 2]):
-            dst.copy_(src, non_blocking=True)
-        p = postprocess_from_head(dev_in, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det, sync=False)
-        host_rows.copy_(p.rows, non_blocking=True)
-        from ultralytics_pro_b200.engine import fetch_counts
-
-        return fetch_counts(p.count)  # D2H + stream synchronize: the result is usable on the host here
-
-    for i in range(3):
-        e2e_step(i)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(KE):
-        e2e_step(i)
-    g1.record()
-    torch.cuda.synchronize(dev)
-    ems = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * KE / (float(ems.item()) * 1e-3)
+    # ---- end to end through the public API with HOST buffers ---------------------------------------------------------------
+    e2e = _e2e(dev, cfg, sets, world, min(K, 30))
 
     # ---- p50 latency at B=1 through the public API (device-resident input, result counts on host) ---------------------
-    one = [lv[:1].contiguous() for lv in sets[0]]
-    lat = []
-    for i in range(20):
-        postprocess_from_head(one, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det)
-    for i in range(200):
-        t0 = time.perf_counter()
-        postprocess_from_head(one, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det)
-        lat.append((time.perf_counter() - t0) * 1e3)
-    lat.sort()
-    # the same through the cached-plan serving object (no per-call allocation; one C-ABI call + the count D2H)
-    pp1 = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
-    lat_pp = []
-    for i in range(20):
-        pp1(one)
-    for i in range(200):
-        t0 = time.perf_counter()
-        pp1(one)
-        lat_pp.append((time.perf_counter() - t0) * 1e3)
-    lat_pp.sort()
+    one = [lv[:1].contiguous() for lv in sets[0][0]]
+
+    def p50(fn, warm=20, reps=200):
+        for _ in range(warm):
+            fn()
+        lat = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        return lat[len(lat) // 2], lat[int(len(lat) * 0.9)]
+
+    lat50, lat90 = p50(lambda: postprocess_from_head(one, cfg.strides, cfg.nc, cfg.conf, cfg.iou, max_det=cfg.max_det))
+    # the same through the cached-plan serving object: static input buffers, ONE CUDA-graph launch (kernels + result
+    # packing + count copy to pinned memory) and one stream synchronisation per call
+    pp1 = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms, use_graph=True)
+    lat_pp50, lat_pp90 = p50(lambda: pp1(one))
+    pp1e = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms)
+    lat_e50, _ = p50(lambda: pp1e(one))
 
     line = None
     if rank == 0:
@@ -509,8 +630,10 @@ def run_ours(args):
             "config": {"workload": WORKLOAD_DESC, "batch_per_gpu": B, "global_batch": B * world,
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
                        "cuda_graph": use_graph, "lanes": LANES,
+                       "timed_region": "per step: counter memset, class scan, survivor decode, sort+suppress+gather, the per-image "
+                                       "counts copied to pinned HOST memory" + (", the gathered results of all ranks copied out of the peer ring" if gather_mode == "peer" else ""),
                        "parallelism": ("images sharded across ranks, no data-path collective; results gathered on every rank each step by "
-                                       + {"peer": f"one-sided NVLink peer-memory stores issued by the suppression kernel + an arrival-flag wait (lag {args.gather_lag} batch per lane, drained before the clock stops), all inside the lane's CUDA graph",
+                                       + {"peer": f"one-sided NVLink peer-memory stores issued by the suppression kernel into a 3-entry ring with consumer acknowledgements + an arrival-flag wait (lag {args.gather_lag} batch per lane; every gathered batch is CONSUMED - copied out - inside the step; drained before the clock stops), all inside the lane's CUDA graph",
                                           "nccl": "one packed NCCL all_gather (one communicator per lane) captured in the lane's CUDA graph",
                                           "nccl-eager": "one packed NCCL all_gather (one communicator per lane) issued from the host",
                                           "none": "NOTHING (diagnostic: independent replicas)"}[gather_mode]
@@ -518,18 +641,43 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "gpu_launches": ((2 if os.environ.get("YPB_FUSE_DECODE") == "1" else 3) + (1 if gather_mode == "peer" else 0)) * K,
             "gather_verified_against_nccl": gather_verified,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
-                    "note": "postprocess_from_head on pinned HOST head tensors: H2D + decode+NMS + D2H of rows and counts, "
-                            "synchronised every step"},
+            "strong_scaling": strong,
+            "e2e": e2e,
             "roofline": roofline,
             "decode_dense": dense,
             "dropin_two_call": dropin["two_call"],
             "dropin_fused": dropin["fused"],
-            "latency_b1_ms_p50": lat[len(lat) // 2],
-            "latency_b1_ms_p90": lat[int(len(lat) * 0.9)],
-            "latency_b1_ms_p50_cached_plan": lat_pp[len(lat_pp) // 2],
-            "detections_last_step": {"kept": int(kept), "candidates": int(cand)},
+            "latency_b1_ms_p50": lat50,
+            "latency_b1_ms_p90": lat90,
+            "latency_b1_ms_p50_cached_plan": lat_pp50,
+            "latency_b1_ms_p90_cached_plan": lat_pp90,
+            "latency_b1_ms_p50_cached_plan_no_graph": lat_e50,
+            "detections_last_step": {"kept": int(kept), "candidates": int(cand), "counts_on_host": counts_on_host},
         }
+    if world == 1 and not args.no_extra:
+        # ---- the other BASELINE.json configs and the 16-bit head, measured by the same machinery (driver-run numbers) ------
+        del lanes
+        extra = {}
+        for name in ("c3_val_stress_b32", "c4_p6_1280_b16", "c5_obb_1024_b16"):
+            extra[name] = _measure_config(dev, name, dtype, min(K, 200))
+        line["configs"] = extra
+        if args.dtype == "f32":
+            sets16 = [([lv.to(torch.bfloat16) for lv in s[0]], None) for s in sets]
+            del sets
+            torch.cuda.empty_cache()
+            l16 = _build_lanes(dev, cfg, sets16, LANES, 1, "none", 0, True)
+            ms16 = _time_lanes(dev, l16, K, W, 1, "none", 0)
+            pre16 = _stage_times(dev, l16[0]["post"], sets16, K)
+            sb16 = B * cfg.nc * cfg.anchors * 2
+            line["bf16"] = {"value": B * K / (ms16 * 1e-3), "unit": UNIT, "ms_per_step": ms16 / K,
+                            "roofline": {"kernel": "scan_classes_kernel", "achieved": sb16 / (pre16[0] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": sb16 / (pre16[0] * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": sb16,
+                                         "launch_ms": pre16[0], "traffic": _traffic("bf16"), "single_stream_step_ms": pre16[2],
+                                         "other_kernels_ms": {"decode_tiles_kernel": pre16[1] - pre16[0], "sort_suppress_kernel": pre16[2] - pre16[1]}},
+                            "decode_dense": _dense_decode_time(dev, cfg, sets16, 2, peak, min(K, 50)),
+                            "e2e": _e2e(dev, cfg, sets16, 1, min(K, 30))}
+            sets = None
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line))
@@ -543,6 +691,9 @@ def run_ours(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# the drop-in boundary
+# ----------------------------------------------------------------------------------------------------------------
 class _StubDetect:
     """Attribute surface of the reference's ``Detect`` (head.py:70-93) without the convolutions; the methods bound below
     are the wrappers ``patch.install()`` puts on the reference's classes."""
@@ -757,6 +908,7 @@ def main():
                          "(0 = the batch just processed); the lanes are drained with lag 0 before the timed region ends")
     ap.add_argument("--lanes", type=int, default=5, help="independent pipelines (streams) the steps are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4/C5 and bf16 sub-records (N=1 only)")
     ap.add_argument("--post-rows", action="store_true",
                     help="instead of the headline line, print one JSON line per SURVEY 8f row (rescale, keypoints, masks, matching, "
                          "NMSModel, top-k) with its CUDA-event time, roofline and CPU-oracle baseline")

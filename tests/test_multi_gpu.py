@@ -43,12 +43,40 @@ SCRIPT = textwrap.dedent('''
             lv = [t.to(dev) for t in make_head_batch(cfg, batch=B, seed=10 * step + rank, first_image=rank * B)[0]]
             pp.enqueue(lv); pp.wait_gather(0)
             check(lv, f"eager {step}")
-        lv = [t.to(dev) for t in make_head_batch(cfg, batch=B, seed=77 + rank)[0]]
-        g = pp.capture(lv, after=lambda: pp.wait_gather(1))
-        for _ in range(4):
+        # pipelined (lag 1) and CONSUMED every step: step k reads the ring entry of batch k-1 (device-side slot index, no host
+        # sync) while the producers already store batch k; 12 steps > 3 ring entries, so entries are reused under the
+        # acknowledgement protocol.  Every consumed batch must equal the NCCL all_gather of that batch.
+        sets = [[t.to(dev) for t in make_head_batch(cfg, batch=B, seed=100 + 7 * s + rank, first_image=rank * B)[0]] for s in range(4)]
+        consumed, wanted = [], []
+        for step in range(12):
+            pl = pp.enqueue(sets[step % 4])
+            ref = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(ref, pl.packed.clone())
+            wanted.append(ref)
+            pp.wait_gather(1)
+            if step >= 1:
+                consumed.append(pl.peers.entry_tensor().clone())
+        pp.wait_gather(0)
+        consumed.append(pp.last.peers.entry_tensor().clone())
+        torch.cuda.synchronize(dev)
+        nrow, md, cols = pp.last.peers.nrow, pp.last.rows.shape[1], pp.last.rows.shape[2]
+        for k, (got, ref) in enumerate(zip(consumed, wanted)):
+            rr, rc = ypb_dist.split_packed(ref, B, md, cols)
+            gr, gc = ypb_dist.split_packed(got.contiguous(), B, md, cols)
+            valid = (torch.arange(md, device=dev)[None, :] < rc[:, None]).unsqueeze(-1)
+            assert torch.equal(rc, gc), ("lag-1 consume", k, rc.tolist(), gc.tolist())
+            assert torch.equal(rr * valid, gr * valid), ("lag-1 consume", k)
+        # the same inside CUDA graphs (kernels + wait + consumer copy captured together)
+        lv = sets[0]
+        out = torch.zeros((world, pp.last.packed.numel()), dtype=torch.float32, device=dev)
+        g = pp.capture(lv, after=lambda: (pp.wait_gather(1), out.copy_(pp.last.peers.entry_tensor())))
+        for _ in range(7):
             g.replay()
         pp.wait_gather(0)
         check(lv, "graph, lag 1 + drain")
+        rr, rc = ypb_dist.split_packed(out, B, md, cols)
+        gr, gc = pp.gathered()
+        assert torch.equal(rc, gc), "graph-captured consumer copy"
     print("ok", rank, flush=True)
     dist.barrier(); torch.cuda.synchronize(dev); os._exit(0)
 ''')

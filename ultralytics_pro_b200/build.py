@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyolopost_b200.so")
 STAMP = os.path.join(LIB_DIR, "libyolopost_b200.stamp")
-SOURCES = ("ypb_decode.cu", "ypb_nms.cu", "ypb_post.cu", "ypb_abi.cu")
+SOURCES = ("ypb_decode.cu", "ypb_scan_tma.cu", "ypb_nms.cu", "ypb_post.cu", "ypb_abi.cu")
 HEADERS = ("ypb_common.cuh", os.path.join("..", "..", "include", "yolopost_b200.h"))
 
 NVCC_FLAGS = [
@@ -72,9 +72,27 @@ def _unit_digest(src: str) -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile the translation units (in parallel, objects cached per unit under _lib/obj) and link one shared object."""
+    """Compile the translation units (in parallel, objects cached per unit under _lib/obj) and link one shared object.
+
+    Safe under concurrent callers (torchrun ranks finding a stale library at the same time): the whole build runs under an
+    exclusive file lock, and the library is linked to a temporary name and renamed into place, so no process can ever
+    ``dlopen`` a partially written file."""
     if not force and is_current():
         return LIB_PATH
+    import fcntl
+
+    os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():  # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = _nvcc()
@@ -90,20 +108,24 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if force or verbose or not fresh:
             jobs.append((src, obj, tag, digest))
     with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as pool:
-        results = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+        results = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1] + ".tmp", verbose), jobs))
     for (src, obj, tag, digest), (_, cmd, proc) in zip(jobs, results):
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
         if verbose:
             sys.stderr.write(proc.stderr)
+        os.replace(obj + ".tmp", obj)
         with open(tag, "w") as fh:
             fh.write(digest)
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", *objs, "-o", LIB_PATH]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", *objs, "-o", tmp]
     proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
-    with open(STAMP, "w") as fh:
+    os.replace(tmp, LIB_PATH)
+    with open(STAMP + ".tmp", "w") as fh:
         fh.write(_source_digest())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB_PATH
 
 

@@ -31,6 +31,12 @@ bool split_decode_requested() {
   return v;
 }
 
+// Diagnostic switch: YPB_SCAN_TMA=0 forces the register-staged LDG class scan (the round-1 kernel) for comparison.
+bool tma_scan_requested() {
+  static const bool v = [] { const char* e = std::getenv("YPB_SCAN_TMA"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 size_t dtype_size(int dt) { return dt == YPB_F32 ? 4 : 2; }
 bool dtype_ok(int dt) { return dt == YPB_F32 || dt == YPB_F16 || dt == YPB_BF16; }
 
@@ -274,7 +280,12 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     f.fuse_decode = split_decode_requested() ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-    e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
+    // the persistent TMA-fed scan when the geometry fits it (16-byte vectorisable levels, nc <= 256), else the LDG kernel
+    e = (tma_scan_requested() && !f.fuse_decode) ? ypb::launch_scan_classes_tma(g, head->dtype, f, vec, st) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) {
+      (void)cudaGetLastError();
+      e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "scan_classes");
   }
   if (stage & 2) {

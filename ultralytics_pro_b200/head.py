@@ -210,7 +210,7 @@ def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch
     The reference takes the K anchors with the largest class maximum and then the K best pairs among their K*nc scores;
     for tie-free scores that is the global top-K over all pairs (an anchor outside the first set cannot own a pair that
     beats K anchors' maxima).  Two passes of the filter + sort kernels, no suppression: pass 1 ranks the anchors by their
-    maximum and yields each image's K-th value T; pass 2 emits every pair with score >= T (at most K*nc) and ranks them.
+    maximum and yields each image's K-th value T; pass 2 emits every pair with score >= T (K*nc at most unless scores tie) and ranks them.
     Index arithmetic between the passes (picking T, nextafter) is torch plumbing on the device; nothing is read back."""
     _cabi.require_cuda(preds, "detect_postprocess")
     if preds.dim() != 3 or preds.shape[2] != 4 + nc:
@@ -226,8 +226,11 @@ def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch
     engine.run_from_dense(dense, first)
     kth = first.rows[:, k - 1, 4].contiguous()
     thr = torch.nextafter(kth, torch.full_like(kth, ninf))  # score > thr  <=>  score >= K-th anchor maximum
-    second = engine.make_plan(dev, b, a, nc, 0, 0.0, 1.0, k, k * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
-                              conf_per_image=thr, rows_cap=k * nc)
+    # rows_cap stays at the worst case A*nc (like every multi-label call): with TIED scores (16-bit heads, constant inputs,
+    # nc == 1) more than K anchors reach T and more than K*nc pairs pass; a smaller cap would drop whichever rows lost the
+    # race for the last slots.  All of them are ranked (score desc, row asc) and the first K are taken - deterministic.
+    second = engine.make_plan(dev, b, a, nc, 0, 0.0, 1.0, k, a * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
+                              conf_per_image=thr)
     engine.run_from_dense(dense, second)
     return second.rows.to(preds.dtype)
 
