@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 7
+#define YPB_ABI_VERSION 8
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -109,6 +109,11 @@ typedef struct {
   /* Optional device array of B per-image confidence thresholds replacing conf_thres (ypb_nms_from_dense only): the
    * second pass of the end2end top-k (head.py:193-214 Detect.postprocess) thresholds each image at its own K-th score. */
   const float* conf_per_image;
+  /* Optional device int32[B + 1] (per-image row counters + the octet counter of the fused path), ZERO on entry: the calls
+   * then use it instead of the workspace's own counters and skip their cudaMemset node - the suppression kernel, the last
+   * reader, leaves it zeroed again ("clean on exit"), so a plan that owns such an array launches kernels only.
+   * NULL = the library clears its counters inside the workspace itself (one memset node per call). */
+  int32_t* clean_counters;
 } ypb_nms_params;
 
 /* Per-image letterbox transform, values exactly as the reference computes them on the host:
@@ -288,7 +293,8 @@ YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, i
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
  * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);
- * 0 or 7 = all three (== ypb_nms_from_head). */
+ * 0 or 7 = all three (== ypb_nms_from_head); 8 (with 1) = do not clear the counters first (kernel-only timing of the scan: the
+ * caller clears them once per batch of launches and accepts that row slots accumulate). */
 YPB_API int ypb_nms_from_head_stage(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit,
                                     int32_t value_dtype, const ypb_nms_params* p, const ypb_nms_out* out,
                                     void* workspace, size_t workspace_bytes, void* stream, int32_t stage);

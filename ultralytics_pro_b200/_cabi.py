@@ -18,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -100,6 +100,7 @@ class NmsParams(C.Structure):
         ("boxes_xyxy", C.c_int32),
         ("pad_output", C.c_int32),
         ("conf_per_image", C.c_void_p),
+        ("clean_counters", C.c_void_p),
     ]
 
 

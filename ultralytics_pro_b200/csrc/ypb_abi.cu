@@ -238,7 +238,9 @@ int ypb_nms_from_head_riders(const ypb_head_desc* head, const ypb_riders_desc* r
 static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int32_t angle_is_logit, int32_t value_dtype,
                               const ypb_riders_desc* riders, const ypb_nms_params* p, const ypb_nms_out* out,
                               void* workspace, size_t workspace_bytes, void* stream, int32_t stage) {
-  if (stage < 0 || stage > 7) return fail(YPB_ERR_INVALID_ARGUMENT, "stage mask=%d outside [0,7]", stage);
+  if (stage < 0 || stage > 15) return fail(YPB_ERR_INVALID_ARGUMENT, "stage mask=%d outside [0,15]", stage);
+  const bool keep_counters = (stage & 8) != 0;
+  stage &= 7;
   if (stage == 0) stage = 7;
   ypb::HeadGeom g;
   int vec;
@@ -272,14 +274,18 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
   if (head->batch == 0) return YPB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
+  // counters: the caller's clean-on-exit array (no memset node on the full path) or the workspace's own
+  int32_t* counters = p->clean_counters ? p->clean_counters : w.row_count;
   if (stage & 1) {
-    e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * (head->batch + 1), st);
-    if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+    if (!keep_counters && !(p->clean_counters && stage == 7)) {
+      e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * (head->batch + 1), st);
+      if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+    }
     ypb::FilterArgs f{};
-    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
+    f.tile_count = counters + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     f.fuse_decode = split_decode_requested() ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     // the persistent TMA-fed scan when the geometry fits it (16-byte vectorisable levels, nc <= 256), else the LDG kernel
     e = (tma_scan_requested() && !f.fuse_decode) ? ypb::launch_scan_classes_tma(g, head->dtype, f, vec, st) : cudaErrorNotSupported;
     if (e == cudaErrorNotSupported) {
@@ -291,14 +297,16 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
   if (stage & 2) {
     ypb::FilterArgs f{};
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-    f.tile_count = w.row_count + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
+    f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+    f.tile_count = counters + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
     f.fuse_decode = split_decode_requested() ? 0 : 1;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }
   if (stage & 4) {
     ypb::SuppressArgs s = suppress_args(p, out, w, head->batch, g.anchors);
+    s.row_count = counters;
+    s.tile_counter = counters + head->batch;
     if (riders) {
       s.rider = riders->ptr; s.rider_dtype = head->dtype; s.rider_kind = riders->kind; s.rider_ndim = riders->kpt_ndim > 0 ? riders->kpt_ndim : 1;
       s.rider_sb = riders->stride_b; s.rider_sc = riders->stride_c;
@@ -308,6 +316,10 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     }
     e = ypb::launch_sort_suppress(s, st);
     if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");
+  } else if (p->clean_counters && !keep_counters) {
+    // a partial (diagnostic) call without the suppression kernel leaves rows counted: restore the clean-on-exit state
+    e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * (head->batch + 1), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
   }
   return YPB_OK;
 }
@@ -366,15 +378,20 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
     return fail(YPB_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B (256-aligned) needed, %zu given", w.bytes, workspace_bytes);
   if (pred->batch == 0) return YPB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(w.row_count, 0, sizeof(int32_t) * pred->batch, st);
-  if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+  int32_t* counters = p->clean_counters ? p->clean_counters : w.row_count;
+  cudaError_t e = cudaSuccess;
+  if (!p->clean_counters) {
+    e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * pred->batch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset row_count");
+  }
   ypb::FilterArgs f{};
   f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
-  f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = w.row_count; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
+  f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
   f.boxes_xyxy = p->boxes_xyxy; f.conf_per_image = p->conf_per_image;
   e = ypb::launch_filter_from_dense(*pred, f, st);
   if (e != cudaSuccess) return cuda_fail(e, "filter_from_dense");
   ypb::SuppressArgs s = suppress_args(p, out, w, pred->batch, pred->anchors);
+  s.row_count = counters;
   s.pred = pred->ptr; s.pred_dtype = pred->dtype; s.pred_sb = pred->stride_b; s.pred_sc = pred->stride_c; s.pred_sa = pred->stride_a;
   e = ypb::launch_sort_suppress(s, st);
   if (e != cudaSuccess) return cuda_fail(e, "sort_suppress");

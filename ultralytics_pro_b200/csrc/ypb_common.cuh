@@ -377,7 +377,8 @@ struct SuppressArgs {
   int batch, anchors, nc, extra, max_det, max_nms, rule, rows_cap, multi_label;
   int cls_bits, anchor_bits;  // row id = (anchor << cls_bits) | cls; anchors < 2^anchor_bits
   float iou_thr, max_wh;
-  int32_t* row_count;
+  int32_t* row_count;     // per-image rows emitted by the filter; zeroed again by this kernel (clean on exit)
+  int32_t* tile_counter;  // octet counter of the fused path (or null); zeroed by the CTA of image 0
   uint64_t* keys_a;
   uint64_t* keys_b;
   const float4* cand_box;

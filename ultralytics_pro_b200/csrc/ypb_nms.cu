@@ -1140,6 +1140,10 @@ __global__ void __launch_bounds__(NT, 1) sort_suppress_kernel(const __grid_const
   // ---- stage 3 ---------------------------------------------------------------------------------------------------
   YPB_MARK(30);
   gather_stage<RULE>(a, b, kk, kept_n);
+  if (tid == 0) {  // clean on exit: this CTA was the only reader of its image's counter; the octet list was consumed by the previous kernel
+    a.row_count[b] = 0;
+    if (b == 0 && a.tile_counter) *a.tile_counter = 0;
+  }
   __syncthreads();
   YPB_MARK(31);
 }
@@ -1215,6 +1219,11 @@ __global__ void __launch_bounds__(NT, 1) fast_nms_cluster_kernel(const __grid_co
   const uint32_t cmask = (1u << cbits) - 1u;
   const float thr = a.iou_thr;
 
+  cluster.sync();  // every CTA of the cluster has read the image's counter: CTA 0 may clear it (clean on exit)
+  if (crank == 0 && tid == 0) {
+    a.row_count[b] = 0;
+    if (b == 0 && a.tile_counter) *a.tile_counter = 0;
+  }
   if (n > SORT_SMEM_MAX) {
     // uniform over the cluster: CTA 0 runs the single-CTA path (global radix sort + chunked walk), the others leave
     if (crank != 0) return;

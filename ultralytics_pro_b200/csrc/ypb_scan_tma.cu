@@ -17,16 +17,16 @@
 // Out-of-range anchors of a level's last tile are zero-filled by the TMA unit and masked per lane.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "ypb_common.cuh"
 
 namespace ypb {
 
 namespace {
 
-constexpr int TMA_ROW_BYTES = 512;   // bytes of one class row of a tile: 128 fp32 / 256 16-bit anchors, 16 B per lane
-constexpr int TMA_NCW = 4;           // consumer warps
-constexpr int TMA_THREADS = 32 * (TMA_NCW + 1);
-constexpr int TMA_MAX_STAGES = 8;
+constexpr int TMA_MAX_NCW = 16;      // consumer warps at most (+ 1 producer warp)
+constexpr int TMA_MAX_STAGES = 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
@@ -65,22 +65,30 @@ struct TmaScanGeom {
   int anchor_start[YPB_MAX_LEVELS + 1];
   int group_start[YPB_MAX_LEVELS + 1];   // prefix of H*W / VEC (the octet index space shared with decode_tiles_kernel)
   int G;                                 // groups reserved per image in that space
-  int stages;
+  int stages, ncw;                       // ring depth, consumer warps
 };
 
 struct TmaMaps { CUtensorMap m[YPB_MAX_LEVELS]; };
 
-template <int DT_IN, bool MULTI>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+// LB = bytes per lane and class row (16, 8 or 4): a tile row is 32 * LB bytes, a lane owns VEC = LB / sizeof(T) anchors.  Narrower
+// lanes mean smaller tiles, hence more stages and more consumer warps per SM for the same shared memory - the scan is a
+// dependent max chain per anchor, so it wants several warps per scheduler to hide its own latency.
+template <int DT_IN, bool MULTI, int LB>
+__global__ void __launch_bounds__(32 * (TMA_MAX_NCW + 1), 1)
 scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaScanGeom g, const __grid_constant__ FilterArgs f) {
   using TI = typename DType<DT_IN>::type;
   using DV = DType<DT_IN>;
-  constexpr int VEC = 16 / static_cast<int>(sizeof(TI));  // anchors per lane
+  constexpr int TMA_ROW_BYTES = 32 * LB;
+  constexpr int VEC = LB / static_cast<int>(sizeof(TI));            // anchors per lane
+  constexpr int VEC_CANON = 16 / static_cast<int>(sizeof(TI));      // anchors per group of the octet index space (decode_tiles_kernel)
+  constexpr int RG = VEC_CANON / VEC;                               // lanes per canonical group
   constexpr int TW = TMA_ROW_BYTES / static_cast<int>(sizeof(TI));
-  constexpr int LPO = VEC >= 8 ? 1 : 8 / VEC;  // lanes per octet
+  constexpr int LPO = 8 / VEC;                                      // lanes per octet (8 anchors)
+  constexpr int LPO_CANON = VEC_CANON >= 8 ? 1 : 8 / VEC_CANON;     // canonical groups per octet
   constexpr int NOCT = 32 / LPO;
+  static_assert(VEC >= 1 && VEC <= 8 && RG >= 1 && LPO >= 1, "lane width");
   extern __shared__ __align__(128) unsigned char smem[];
-  const int S = g.stages, nc = g.nc;
+  const int S = g.stages, nc = g.nc, NCW = g.ncw;
   const int stage_bytes = nc * TMA_ROW_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
   uint64_t* empty = full + TMA_MAX_STAGES;
@@ -93,32 +101,34 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
   }
   __syncthreads();
 
-  if (warp == TMA_NCW) {
-    // ---- producer: one elected thread, one TMA per tile ------------------------------------------------------------------
+  const int total32 = static_cast<int>(total);  // the launcher guarantees total < 2^31
+  if (warp == NCW) {
+    // ---- producer: one elected thread, one TMA per tile.  Stage and phase advance incrementally (no modulo per tile). -------
     if (lane == 0) {
-      int it = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
-        const int b = static_cast<int>(t / g.tiles_per_image), r = static_cast<int>(t - static_cast<long long>(b) * g.tiles_per_image);
+      int s = 0, fill = 0;  // fill = how many times stage s has been filled before
+      for (int t = blockIdx.x; t < total32; t += gridDim.x) {
+        if (fill > 0) mbar_wait(&empty[s], (fill - 1) & 1);
+        const int b = t / g.tiles_per_image, r = t - b * g.tiles_per_image;
         int l = 0;
 #pragma unroll
         for (int i = 1; i < YPB_MAX_LEVELS; ++i)
           if (i < g.num_levels && r >= g.tile_start[i]) l = i;
         mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
         tma_load_3d(smem + static_cast<size_t>(s) * stage_bytes, &maps.m[l], (r - g.tile_start[l]) * TW, 64, b, &full[s]);
+        if (++s == S) { s = 0; ++fill; }
       }
     }
     return;
   }
 
-  // ---- consumers: warp w takes the stages s with s % NCW == w, i.e. whole tiles ---------------------------------------------
+  // ---- consumers: warp w takes this CTA's tiles number w, w + NCW, ... (whole tiles); tile number `it` sits in stage it % S,
+  //      filled for the (it / S)-th time - both tracked incrementally ------------------------------------------------------------
   const float conf = f.conf;
-  int it = 0;
-  for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-    const int s = it % S;
-    if (s % TMA_NCW != warp) continue;
-    const int b = static_cast<int>(t / g.tiles_per_image), r = static_cast<int>(t - static_cast<long long>(b) * g.tiles_per_image);
+  int s = warp % S, fill = warp / S;
+  const int s_step = NCW % S, fill_step = NCW / S;
+  for (long long tt = blockIdx.x + static_cast<long long>(warp) * gridDim.x; tt < total; tt += static_cast<long long>(NCW) * gridDim.x) {
+    const int t = static_cast<int>(tt);
+    const int b = t / g.tiles_per_image, r = t - b * g.tiles_per_image;
     int l = 0;
 #pragma unroll
     for (int i = 1; i < YPB_MAX_LEVELS; ++i)
@@ -126,8 +136,8 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
     const int a_local = (r - g.tile_start[l]) * TW + lane * VEC;   // first anchor of this lane inside the level
     const bool in_level = a_local < g.level_anchors[l];            // VEC divides H*W: a lane is inside or outside as a whole
     const int a_glob = g.anchor_start[l] + a_local;
-    mbar_wait(&full[s], (it / S) & 1);
-    const unsigned char* tile = smem + static_cast<size_t>(s) * stage_bytes + lane * 16;
+    mbar_wait(&full[s], fill & 1);
+    const unsigned char* tile = smem + static_cast<size_t>(s) * stage_bytes + lane * LB;
     auto row = [&](int c) { return *reinterpret_cast<const Pack<TI, VEC>*>(tile + static_cast<size_t>(c) * TMA_ROW_BYTES); };
 
     int rows[VEC];
@@ -159,17 +169,18 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
       if constexpr (DT_IN != YPB_F32) {
         // 16-bit inputs: the whole scan stays in packed x2 arithmetic (comparisons and max/min of 16-bit floats are exact)
         using T2 = typename Packed2<DT_IN>::type;
-        T2 pm[4], pm2[4];
-        uint32_t pidx[4];
+        constexpr int NP = VEC / 2;
+        T2 pm[NP], pm2[NP];
+        uint32_t pidx[NP];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { pm[j] = Packed2<DT_IN>::neg_inf(); pm2[j] = pm[j]; pidx[j] = 0u; }
+        for (int j = 0; j < NP; ++j) { pm[j] = Packed2<DT_IN>::neg_inf(); pm2[j] = pm[j]; pidx[j] = 0u; }
 #pragma unroll 4
         for (int c = 0; c < nc; ++c) {
           const Pack<TI, VEC> p = row(c);
           const T2* v2 = reinterpret_cast<const T2*>(&p);
           const uint32_t cc = static_cast<uint32_t>(c) * 0x00010001u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NP; ++j) {
             const uint32_t gt = __hgt2_mask(v2[j], pm[j]);
             pm2[j] = __hmax2(pm2[j], __hmin2(pm[j], v2[j]));
             pm[j] = __hmax2_nan(pm[j], v2[j]);
@@ -177,7 +188,7 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NP; ++j) {
           m[2 * j] = Packed2<DT_IN>::lo(pm[j]);   m[2 * j + 1] = Packed2<DT_IN>::hi(pm[j]);
           m2[2 * j] = Packed2<DT_IN>::lo(pm2[j]); m2[2 * j + 1] = Packed2<DT_IN>::hi(pm2[j]);
           cls[2 * j] = static_cast<int>(pidx[j] & 0xffffu); cls[2 * j + 1] = static_cast<int>(pidx[j] >> 16);
@@ -215,6 +226,12 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
       }
     }
 
+    if constexpr (!MULTI) {
+      // single-label: everything the epilogue needs is in registers now - hand the stage back BEFORE the global atomics of
+      // the epilogue (two round trips to L2), so the TMA engine refills it while this warp waits for them
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
     // ---- per-warp epilogue: compaction of the keys, octet work list for decode_tiles_kernel ------------------------------
     int my_rows = 0;
     uint32_t flags = 0;
@@ -240,13 +257,19 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
       }
       base_rows = __shfl_sync(0xffffffffu, base_rows, 0);
       base_oct = __shfl_sync(0xffffffffu, base_oct, 0);
-      // octet ids index a dense per-lane space shared with decode_tiles_kernel: lane index = b * G + group-in-image
-      const int lane_idx = b * g.G + g.group_start[l] + a_local / VEC;
+      // octet ids index the dense space of CANONICAL anchor groups (16 bytes of a row: VEC_CANON anchors) shared with
+      // decode_tiles_kernel: group index = b * G + group-in-image; an octet = LPO_CANON consecutive groups = LPO lanes here
+      const int group0 = b * g.G + g.group_start[l] + (r - g.tile_start[l]) * (TW / VEC_CANON);  // first group of this tile
       if (lane < NOCT && ((oct_mask >> lane) & 1u)) {
         const int slot = base_oct + __popc(oct_mask & lt_mask);
-        if (slot < f.tile_cap) f.tile_list[slot] = (lane_idx - lane) / LPO + lane;
+        if (slot < f.tile_cap) f.tile_list[slot] = group0 / LPO_CANON + lane;
       }
-      if (in_level) f.tile_flags[lane_idx] = static_cast<uint8_t>(flags);  // a lane past the level's end would alias the next level's groups
+      // the group's flag byte: bit i = anchor i of the group survived; RG lanes hold one group
+      uint32_t gflags = flags << ((lane % RG) * VEC);
+#pragma unroll
+      for (int o = 1; o < RG; o <<= 1) gflags |= __shfl_xor_sync(0xffffffffu, gflags, o);
+      // (a lane past the level's end would alias the next level's groups: not written)
+      if (in_level && (lane % RG) == 0) f.tile_flags[group0 + lane / RG] = static_cast<uint8_t>(gflags);
       if (my_rows > 0) {
         uint64_t* keys = f.keys + static_cast<long long>(b) * f.rows_cap;
         int rpos = base_rows + inc - my_rows;
@@ -276,8 +299,13 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // the stage may be refilled
+    if constexpr (MULTI) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);  // the stage may be refilled (the key emission above re-read it)
+    }
+    s += s_step;
+    fill += fill_step;
+    if (s >= S) { s -= S; ++fill; }
   }
 }
 
@@ -305,19 +333,25 @@ int sm_count() {
   return n;
 }
 
-template <int DT_IN>
+template <int DT_IN, int LB>
 cudaError_t launch_tma(const TmaMaps& maps, const TmaScanGeom& g, const FilterArgs& f, size_t smem, int grid, cudaStream_t st) {
   cudaError_t e;
+  const int threads = 32 * (g.ncw + 1);
   if (f.multi_label) {
-    e = cudaFuncSetAttribute(scan_classes_tma_kernel<DT_IN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(scan_classes_tma_kernel<DT_IN, true, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    scan_classes_tma_kernel<DT_IN, true><<<grid, TMA_THREADS, smem, st>>>(maps, g, f);
+    scan_classes_tma_kernel<DT_IN, true, LB><<<grid, threads, smem, st>>>(maps, g, f);
   } else {
-    e = cudaFuncSetAttribute(scan_classes_tma_kernel<DT_IN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(scan_classes_tma_kernel<DT_IN, false, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    scan_classes_tma_kernel<DT_IN, false><<<grid, TMA_THREADS, smem, st>>>(maps, g, f);
+    scan_classes_tma_kernel<DT_IN, false, LB><<<grid, threads, smem, st>>>(maps, g, f);
   }
   return cudaGetLastError();
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e && e[0] ? std::atoi(e) : dflt;
 }
 
 }  // namespace
@@ -328,14 +362,24 @@ cudaError_t launch_scan_classes_tma(const HeadGeom& hg, int in_dtype, const Filt
   const int wide = 16 / es;
   EncodeTiledFn enc = encode_fn();
   if (!enc || vec != wide || hg.nc > 256 || hg.nc < 1 || hg.batch < 1) return cudaErrorNotSupported;
-  const size_t stage_bytes = static_cast<size_t>(hg.nc) * TMA_ROW_BYTES;
+  // tuning knobs (diagnostic): bytes per lane and row, consumer warps
+  static const int lb_env = env_int("YPB_TMA_LB", 0), ncw_env = env_int("YPB_TMA_NCW", 0);
+  static const int multi_env = env_int("YPB_TMA_MULTI", 0);
+  // multi-label (val mode) evaluates a sigmoid per ELEMENT and walks every tile twice: compute-bound in the consumer warps,
+  // where the one-wave LDG kernel with its ~30 resident warps per SM is the faster form (measured, profiles/r02_scan_tune.jsonl)
+  if (f.multi_label && !multi_env) return cudaErrorNotSupported;
+  int lb = lb_env == 16 || lb_env == 8 || lb_env == 4 ? lb_env : 8;
+  int ncw = ncw_env >= 1 && ncw_env <= TMA_MAX_NCW ? ncw_env : 12;
+  const int row_bytes = 32 * lb;
+  const size_t stage_bytes = static_cast<size_t>(hg.nc) * row_bytes;
   int stages = static_cast<int>((200u * 1024u) / stage_bytes);
   if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
   if (stages < 2) return cudaErrorNotSupported;
-  const int tw = TMA_ROW_BYTES / es;
+  if (ncw > stages) ncw = stages;
+  const int tw = row_bytes / es;
   TmaScanGeom g{};
   TmaMaps maps{};
-  g.num_levels = hg.num_levels; g.batch = hg.batch; g.nc = hg.nc; g.stages = stages;
+  g.num_levels = hg.num_levels; g.batch = hg.batch; g.nc = hg.nc; g.stages = stages; g.ncw = ncw;
   int ts = 0;
   for (int l = 0; l < hg.num_levels; ++l) {
     const int hw = hg.h[l] * hg.w[l];
@@ -344,7 +388,7 @@ cudaError_t launch_scan_classes_tma(const HeadGeom& hg, int in_dtype, const Filt
     g.level_anchors[l] = hw;
     g.anchor_start[l] = hg.anchor_start[l];
     g.group_start[l] = hg.group_start[l];
-    if (hg.group_start[l] % (wide >= 8 ? 1 : 8 / wide)) return cudaErrorNotSupported;  // octets must not straddle tiles
+    if (hg.group_start[l] % (wide >= 8 ? 1 : 8 / wide) || hw % 8) return cudaErrorNotSupported;  // octets must not straddle levels
     // tensor map over (B, 64 + nc, H*W): innermost = anchors
     const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(hw), static_cast<cuuint64_t>(64 + hg.nc), static_cast<cuuint64_t>(hg.batch)};
     const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(hg.cstride[l]) * es, static_cast<cuuint64_t>(hg.bstride[l]) * es};
@@ -359,22 +403,30 @@ cudaError_t launch_scan_classes_tma(const HeadGeom& hg, int in_dtype, const Filt
   }
   for (int l = hg.num_levels; l <= YPB_MAX_LEVELS; ++l) {
     g.tile_start[l] = ts;
-    g.anchor_start[l] = hg.anchor_start[l > YPB_MAX_LEVELS ? YPB_MAX_LEVELS : l];
-    g.group_start[l] = hg.group_start[l > YPB_MAX_LEVELS ? YPB_MAX_LEVELS : l];
+    g.anchor_start[l] = hg.anchor_start[l];
+    g.group_start[l] = hg.group_start[l];
   }
   g.tiles_per_image = ts;
   // the same per-image span of the octet index space as the LDG kernel (its grid covers ceil(groups / 128) * 128 lanes), so
   // decode_tiles_kernel is launched identically after either scan
   g.G = (hg.group_start[hg.num_levels] + 127) / 128 * 128;
   const long long total = static_cast<long long>(hg.batch) * ts;
+  if (total >= (1ll << 31)) return cudaErrorNotSupported;
   int grid = sm_count();
   if (grid > total) grid = static_cast<int>(total);
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 2 * TMA_MAX_STAGES * sizeof(uint64_t);
+#define YPB_TMA(DT)                                                                  \
+  do {                                                                               \
+    if (lb == 16) return launch_tma<DT, 16>(maps, g, f, smem, grid, st);             \
+    if (lb == 8) return launch_tma<DT, 8>(maps, g, f, smem, grid, st);               \
+    return launch_tma<DT, 4>(maps, g, f, smem, grid, st);                            \
+  } while (0)
   switch (in_dtype) {
-    case YPB_F32: return launch_tma<YPB_F32>(maps, g, f, smem, grid, st);
-    case YPB_F16: return launch_tma<YPB_F16>(maps, g, f, smem, grid, st);
-    case YPB_BF16: return launch_tma<YPB_BF16>(maps, g, f, smem, grid, st);
+    case YPB_F32: YPB_TMA(YPB_F32);
+    case YPB_F16: YPB_TMA(YPB_F16);
+    case YPB_BF16: YPB_TMA(YPB_BF16);
   }
+#undef YPB_TMA
   return cudaErrorInvalidValue;
 }
 

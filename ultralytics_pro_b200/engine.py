@@ -106,6 +106,7 @@ class NmsPlan:
     xforms: torch.Tensor = None  # (B, 8) ypb_scale_xform array when the gather rescales to the original images
     peers: object = None         # dist.PeerGather when the kernel also stores the results into every peer's buffer
     scratch_bytes: int = 0
+    counters: torch.Tensor = None  # int32[B + 1] clean-on-exit row / octet counters (ypb_nms_params.clean_counters)
 
 
 _PLAN_CACHE_MAX = 32
@@ -183,6 +184,10 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     p.boxes_xyxy, p.pad_output = int(bool(boxes_xyxy)), int(bool(pad_output))
     if conf_per_image is not None:
         p.conf_per_image = conf_per_image.data_ptr()
+    # clean-on-exit counters owned by the plan: the calls then enqueue kernels only (no memset node); zeroed here, left
+    # zeroed by the suppression kernel of every completed call (run_* re-zero them if a call fails half-way)
+    counters = torch.zeros((batch + 1,), dtype=torch.int32, device=device)
+    p.clean_counters = counters.data_ptr()
     o = _cabi.NmsOut()
     o.rows, o.idx, o.count, o.cand_count = rows.data_ptr(), idx.data_ptr(), count.data_ptr(), cand.data_ptr()
     xforms = None
@@ -192,7 +197,8 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         o.scale_xforms, o.scale_padding = xforms.data_ptr(), int(bool(scale_padding))
     if peers is not None:
         peers.bind(o)
-    plan = NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image), xforms, peers)
+    plan = NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image, counters), xforms, peers)
+    plan.counters = counters
     plan.scratch_bytes = nbytes
     if key is not None:
         cache = _plan_cache()
@@ -253,6 +259,12 @@ def split_results(plan: NmsPlan, return_idxs: bool):
     return cut_results(out_rows, out_idx, fetch_counts(plan.count), return_idxs)
 
 
+def _check_plan(rc: int, what: str, plan: NmsPlan) -> None:
+    if rc != 0 and plan.counters is not None:
+        plan.counters.zero_()  # a call that failed half-way may have left rows counted: restore the clean-on-exit invariant
+    _cabi.check(rc, what)
+
+
 def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:
     d = _cabi.DenseDesc()
     d.ptr, d.dtype = pred.data_ptr(), _cabi.dtype_code(pred.dtype)
@@ -261,7 +273,7 @@ def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:
     lib = _cabi.load()
     rc = lib.ypb_nms_from_dense(C.byref(d), C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
                                 plan.scratch.numel(), _cabi.stream_ptr(pred.device))
-    _cabi.check(rc, "ypb_nms_from_dense")
+    _check_plan(rc, "ypb_nms_from_dense", plan)
 
 
 def geometry_desc(level_hw, strides, batch: int, dtype):
@@ -292,7 +304,7 @@ def run_from_head_riders(desc, riders, plan: NmsPlan, device) -> None:
     lib = _cabi.load()
     rc = lib.ypb_nms_from_head_riders(C.byref(desc), C.byref(riders), desc.dtype, C.byref(plan.params), C.byref(plan.out),
                                       plan.scratch.data_ptr(), plan.scratch.numel(), _cabi.stream_ptr(device))
-    _cabi.check(rc, "ypb_nms_from_head_riders")
+    _check_plan(rc, "ypb_nms_from_head_riders", plan)
 
 
 def run_from_head(desc, angle, angle_is_logit: bool, plan: NmsPlan, device) -> None:
@@ -300,4 +312,4 @@ def run_from_head(desc, angle, angle_is_logit: bool, plan: NmsPlan, device) -> N
     rc = lib.ypb_nms_from_head(C.byref(desc), angle.data_ptr() if angle is not None else None, int(angle_is_logit),
                                desc.dtype, C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
                                plan.scratch.numel(), _cabi.stream_ptr(device))
-    _cabi.check(rc, "ypb_nms_from_head")
+    _check_plan(rc, "ypb_nms_from_head", plan)

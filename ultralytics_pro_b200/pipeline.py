@@ -84,7 +84,7 @@ class HeadPostProcessor:
         rc = lib.ypb_nms_from_head_stage(C.byref(desc), ang.data_ptr() if ang is not None else None, 1, desc.dtype,
                                          C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
                                          plan.scratch.numel(), _cabi.stream_ptr(dev), stage)
-        _cabi.check(rc, "ypb_nms_from_head_stage")
+        engine._check_plan(rc, "ypb_nms_from_head_stage", plan)
         self.last = plan
         return plan
 
