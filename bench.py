@@ -203,15 +203,15 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
-def _post_for(cfg, gather_mode):
+def _post_for(cfg, gather_mode, scan_kernel="auto"):
     from ultralytics_pro_b200.pipeline import HeadPostProcessor
 
     return HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, multi_label=cfg.multi_label, agnostic=cfg.agnostic,
                              rotated=cfg.rotated, max_det=cfg.max_det, max_nms=cfg.max_nms,
-                             peer_gather_group=True if gather_mode == "peer" else None)
+                             peer_gather_group=True if gather_mode == "peer" else None, scan_kernel=scan_kernel)
 
 
-def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lane_groups=None):
+def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lane_groups=None, scan_kernel="auto"):
     """`nlanes` independent pipelines (own stream, plan, scratch, result buffers, CUDA graphs); lane i owns input sets i and
     i + nlanes.  One step of a lane = [class scan, survivor decode, sort+suppress (+ peer push)], then - all
     inside the lane's CUDA graph - the consumer side: multi-GPU: wait for the gathered batch (`lag` batches back), copy the
@@ -225,7 +225,7 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
         st = torch.cuda.Stream(dev)
         st.wait_stream(main)
         with torch.cuda.stream(st):
-            pp = _post_for(cfg, gather_mode)
+            pp = _post_for(cfg, gather_mode, scan_kernel)
             my_sets = [sets[(ln + nlanes * j) % len(sets)] for j in range(2)]
             pl = pp.enqueue(*my_sets[0])  # builds the plan / result buffers (collective when the peer gather is on)
             host_counts = torch.empty((pl.count.numel(),), dtype=torch.int32).pin_memory()
@@ -592,7 +592,7 @@ def run_ours(args):
     scan_bytes = B * cfg.nc * cfg.anchors * esize  # the class rows: what this kernel must read
     t_scan_kernel = prefix_ms[3] if len(prefix_ms) > 3 else t_scan  # the kernel alone, no counter memset in front
     achieved = scan_bytes / (t_scan_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_classes_tma_kernel (persistent TMA-fed class scan + sigmoid/confidence filter + compaction)",
+    roofline = {"bound": "hbm", "kernel": "scan_classes_kernel (class scan + sigmoid/confidence filter + compaction; one-wave grid, software-pipelined 128-bit loads)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(args.dtype),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
                 "algorithmic_bytes_full_head": B * in_bytes_img,
@@ -687,6 +687,24 @@ def run_ours(args):
         for name in ("c3_val_stress_b32", "c4_p6_1280_b16", "c5_obb_1024_b16"):
             extra[name] = _measure_config(dev, name, dtype, min(K, 200))
         line["configs"] = extra
+        # ---- the persistent TMA-fed form of the class scan (scan_kernel="tma"), same workload: faster as a single kernel,
+        #      slower in the multi-lane pipeline (its ring fills the SM's shared memory, so other lanes' CTAs cannot co-reside)
+        def tma_record(tsets, esz):
+            tl = _build_lanes(dev, cfg, tsets, LANES, 1, "none", 0, True, None, "tma")
+            tms = _time_lanes(dev, tl, K, W, 1, "none", 0)
+            tpre = _stage_times(dev, tl[0]["post"], tsets, K)
+            tk = tpre[3] if len(tpre) > 3 else tpre[0]
+            sb = B * cfg.nc * cfg.anchors * esz
+            pp_t = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, max_det=cfg.max_det, max_nms=cfg.max_nms, use_graph=True,
+                                     scan_kernel="tma")
+            one_t = [lv[:1].contiguous() for lv in tsets[0][0]]
+            l50, _ = p50(lambda: pp_t(one_t))
+            return {"kernel": "scan_classes_tma_kernel (cp.async.bulk.tensor.3d ring, 1 CTA per SM)", "launch_ms": tk,
+                    "achieved": sb / (tk * 1e-3) / 1e9, "frac": sb / (tk * 1e-3) / 1e9 / peak, "unit": "GB/s", "peak": peak,
+                    "single_stream_step_ms": tpre[2], "pipelined_value": B * K / (tms * 1e-3), "pipelined_ms_per_step": tms / K,
+                    "latency_b1_ms_p50_cached_plan": l50}
+
+        line["scan_tma"] = {"f32" if args.dtype == "f32" else args.dtype: tma_record(sets, esize)}
         if args.dtype == "f32":
             sets16 = [([lv.to(torch.bfloat16) for lv in s[0]], None) for s in sets]
             del sets
@@ -697,12 +715,14 @@ def run_ours(args):
             sb16 = B * cfg.nc * cfg.anchors * 2
             t16 = pre16[3] if len(pre16) > 3 else pre16[0]
             line["bf16"] = {"value": B * K / (ms16 * 1e-3), "unit": UNIT, "ms_per_step": ms16 / K,
-                            "roofline": {"kernel": "scan_classes_tma_kernel", "achieved": sb16 / (t16 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "roofline": {"kernel": "scan_classes_kernel", "achieved": sb16 / (t16 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                          "frac": sb16 / (t16 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": sb16,
                                          "launch_ms": t16, "launch_ms_with_counter_memset": pre16[0], "traffic": _traffic("bf16"), "single_stream_step_ms": pre16[2],
                                          "other_kernels_ms": {"decode_tiles_kernel": pre16[1] - pre16[0], "sort_suppress_kernel": pre16[2] - pre16[1]}},
                             "decode_dense": _dense_decode_time(dev, cfg, sets16, 2, peak, min(K, 50)),
                             "e2e": _e2e(dev, cfg, sets16, 1, min(K, 30))}
+            del l16
+            line["scan_tma"]["bf16"] = tma_record(sets16, 2)
             sets = None
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

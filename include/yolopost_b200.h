@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 8
+#define YPB_ABI_VERSION 9
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -114,6 +114,13 @@ typedef struct {
    * reader, leaves it zeroed again ("clean on exit"), so a plan that owns such an array launches kernels only.
    * NULL = the library clears its counters inside the workspace itself (one memset node per call). */
   int32_t* clean_counters;
+  /* Class-scan kernel of the fused path (ypb_nms_from_head*): YPB_SCAN_LDG = one-wave grid of small CTAs with register-staged,
+   * software-pipelined 128-bit loads - shares every SM with the kernels of other streams, the form a multi-stream pipeline
+   * wants; YPB_SCAN_TMA = persistent one-CTA-per-SM kernel fed by TMA tensor loads through a shared-memory ring - the
+   * faster single kernel (16-bit heads especially) when nothing else needs the SMs; YPB_SCAN_AUTO = LDG unless the
+   * environment variable YPB_SCAN_TMA=1 is set. */
+  int32_t scan_kernel;
+  int32_t reserved2;
 } ypb_nms_params;
 
 /* Per-image letterbox transform, values exactly as the reference computes them on the host:
@@ -222,6 +229,7 @@ YPB_API int ypb_nms_from_head(const ypb_head_desc* head, const void* angle, int3
  * keypoints (head.py:1248: raw (B, nk*ndim, A)) are decoded on the way (head.py:1254-1273 kpts_decode) - for the kept
  * anchors only, the dense (B, nk*ndim, A) decode of the reference is never computed. */
 typedef enum { YPB_RIDER_RAW = 0, YPB_RIDER_KEYPOINTS = 1 } ypb_rider_kind;
+typedef enum { YPB_SCAN_AUTO = 0, YPB_SCAN_LDG = 1, YPB_SCAN_TMA = 2 } ypb_scan_kernel;
 typedef struct {
   const void* ptr;     /* (B, channels, A), anchors contiguous, same dtype as the head */
   int32_t channels;    /* == ypb_nms_params.extra */

@@ -298,6 +298,46 @@ def test_fused_equals_two_call(cuda_device, name, batch, dtype):
     assert_rows_equal(one, one_idx, [t.cpu() for t in two], [t.cpu() for t in two_idx], f"fused {name} {dtype}")
 
 
+@pytest.mark.parametrize("name,batch,dtype", [("c2_v8x_640_b64", 64, torch.float32), ("c2_v8x_640_b64", 5, torch.bfloat16),
+                                              ("c2_v8x_640_b64", 3, torch.float16), ("c4_p6_1280_b16", 3, torch.float32),
+                                              ("c5_obb_1024_b16", 4, torch.float32), ("c3_val_stress_b32", 2, torch.float32)])
+def test_tma_scan_kernel_equals_ldg_scan_kernel(cuda_device, name, batch, dtype):
+    """The two forms of the class-scan kernel (ypb_nms_params.scan_kernel): one-wave register-staged LDG grid vs the
+    persistent TMA-fed ring (cp.async.bulk.tensor + mbarrier, ypb_scan_tma.cu) must hand identical candidates to the rest of
+    the fused path - rows, kept anchors and counts bit for bit, partial last tiles of a level and 15-class heads included."""
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+
+    cfg = CONFIGS[name]
+    levels, ang = make_head_batch(cfg, batch=batch, seed=51, dtype=dtype)
+    dl, da = _to(cuda_device, levels, ang)
+    res = {}
+    for kern in ("ldg", "tma"):
+        pp = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, multi_label=cfg.multi_label, rotated=cfg.rotated,
+                               max_det=cfg.max_det, max_nms=cfg.max_nms, scan_kernel=kern)
+        rows, idx = pp(dl, da, return_idxs=True)
+        res[kern] = (rows, idx, pp.last.cand.clone())
+    assert sum(r.shape[0] for r in res["ldg"][0]) > 0
+    assert torch.equal(res["ldg"][2], res["tma"][2]), "candidate counts differ"
+    for a, b, ia, ib in zip(res["ldg"][0], res["tma"][0], res["ldg"][1], res["tma"][1]):
+        assert torch.equal(a, b) and torch.equal(ia, ib)
+
+
+def test_tma_scan_falls_back_on_geometries_outside_its_envelope(cuda_device):
+    """Odd grids (not 16-byte vectorisable) silently take the LDG kernel: same results as the reference path."""
+    from ultralytics_pro_b200.head import decode_head
+    from ultralytics_pro_b200.nms import non_max_suppression
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+
+    torch.manual_seed(5)
+    nc = 7
+    levels = [torch.randn(2, 64 + nc, 9, 7) * 2, torch.randn(2, 64 + nc, 5, 3) * 2]
+    dl = [lv.to(cuda_device) for lv in levels]
+    pp = HeadPostProcessor(nc, (8, 16), 0.25, 0.7, scan_kernel="tma")
+    got = pp(dl)
+    want = non_max_suppression(decode_head(dl, (8, 16), nc), 0.25, 0.7)
+    assert sum(w.shape[0] for w in want) > 0 and all(torch.equal(g, w) for g, w in zip(got, want))
+
+
 def _decision_margins(y_img: torch.Tensor, nc: int, conf: float, iou_thr: float, max_wh: float = 7680.0):
     """How far the oracle's decisions on one decoded image are from flipping: (min |score - conf| over the anchors' best
     scores, min |IoU - thr| over the comparisons the greedy walk actually makes - a kept row against every row still alive

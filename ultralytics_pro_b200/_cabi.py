@@ -18,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -47,6 +47,7 @@ EXPORTS = (
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
+SCAN_AUTO, SCAN_LDG, SCAN_TMA = 0, 1, 2
 
 BOXES_NONE, BOXES_XYXY, BOXES_XYWH, BOXES_XYWHR, BOXES_CLIP_ONLY, BOXES_REGULARIZE_ONLY = range(6)
 SCALE_PADDING, SCALE_NORMALIZE, SCALE_COORDS_CLIP_ONLY = 1, 2, 4
@@ -101,6 +102,8 @@ class NmsParams(C.Structure):
         ("pad_output", C.c_int32),
         ("conf_per_image", C.c_void_p),
         ("clean_counters", C.c_void_p),
+        ("scan_kernel", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 

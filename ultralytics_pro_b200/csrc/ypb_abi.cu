@@ -31,10 +31,11 @@ bool split_decode_requested() {
   return v;
 }
 
-// Diagnostic switch: YPB_SCAN_TMA=0 forces the register-staged LDG class scan (the round-1 kernel) for comparison.
-bool tma_scan_requested() {
-  static const bool v = [] { const char* e = std::getenv("YPB_SCAN_TMA"); return !(e && e[0] == '0'); }();
-  return v;
+// ypb_nms_params.scan_kernel == YPB_SCAN_AUTO: the one-wave LDG class scan unless YPB_SCAN_TMA=1 asks for the persistent
+// TMA-fed kernel (ypb_scan_tma.cu) process-wide.
+bool tma_scan_requested(int scan_kernel) {
+  static const bool env = [] { const char* e = std::getenv("YPB_SCAN_TMA"); return e && e[0] == '1'; }();
+  return scan_kernel == YPB_SCAN_TMA || (scan_kernel == YPB_SCAN_AUTO && env);
 }
 
 size_t dtype_size(int dt) { return dt == YPB_F32 ? 4 : 2; }
@@ -286,8 +287,8 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     f.fuse_decode = split_decode_requested() ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
-    // the persistent TMA-fed scan when the geometry fits it (16-byte vectorisable levels, nc <= 256), else the LDG kernel
-    e = (tma_scan_requested() && !f.fuse_decode) ? ypb::launch_scan_classes_tma(g, head->dtype, f, vec, st) : cudaErrorNotSupported;
+    // the persistent TMA-fed scan when asked for and the geometry fits it (16-byte vectorisable levels, nc <= 256), else the LDG kernel
+    e = (tma_scan_requested(p->scan_kernel) && !f.fuse_decode) ? ypb::launch_scan_classes_tma(g, head->dtype, f, vec, st) : cudaErrorNotSupported;
     if (e == cudaErrorNotSupported) {
       (void)cudaGetLastError();
       e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 1, st);

@@ -21,6 +21,12 @@ namespace ypb {
 #ifndef YPB_SCAN_DEPTH16
 #define YPB_SCAN_DEPTH16 16
 #endif
+#ifndef YPB_SCAN_PIPE16
+#define YPB_SCAN_PIPE16 8   // loads per software-pipeline batch, 16-bit heads (two batches live in registers)
+#endif
+#ifndef YPB_SCAN_PIPE32
+#define YPB_SCAN_PIPE32 8
+#endif
 constexpr int DEC_THREADS = YPB_DEC_THREADS;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -90,6 +96,35 @@ __device__ __forceinline__ void stream_rows(const TI* base, long long cs, int n,
 #pragma unroll
     for (int j = 0; j < DEPTH; ++j) visit(p[j], c + j);
   }
+  for (; c < n; ++c) {
+    Pack<TI, VEC> p = load_pack<TI, VEC>(base + static_cast<long long>(c) * cs);
+    visit(p, c);
+  }
+}
+
+// The same walk, software-pipelined: the loads of batch k+1 are issued BEFORE batch k is consumed, so DEPTH independent
+// loads per thread are in flight during the arithmetic as well, not only between batches.  (Measured with the read-only
+// probe of this access shape, tools/read_bw_bench.cu: 16-bit rows 16.3 us pipelined vs 18.4-18.7 us batch-by-batch.)
+template <typename TI, int VEC, int DEPTH, typename F>
+__device__ __forceinline__ void stream_rows_pipelined(const TI* base, long long cs, int n, F&& visit) {
+  if (n < 2 * DEPTH) {
+    stream_rows<TI, VEC, DEPTH>(base, cs, n, visit);
+    return;
+  }
+  Pack<TI, VEC> cur[DEPTH], nxt[DEPTH];
+#pragma unroll
+  for (int j = 0; j < DEPTH; ++j) cur[j] = load_pack<TI, VEC>(base + static_cast<long long>(j) * cs);
+  int c = DEPTH;
+  for (; c + DEPTH <= n; c += DEPTH) {
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) nxt[j] = load_pack<TI, VEC>(base + static_cast<long long>(c + j) * cs);
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) visit(cur[j], c - DEPTH + j);
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) cur[j] = nxt[j];
+  }
+#pragma unroll
+  for (int j = 0; j < DEPTH; ++j) visit(cur[j], c - DEPTH + j);
   for (; c < n; ++c) {
     Pack<TI, VEC> p = load_pack<TI, VEC>(base + static_cast<long long>(c) * cs);
     visit(p, c);
@@ -289,7 +324,7 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
             pidx[j] = (cc & gt) | (pidx[j] & ~gt);
           }
         };
-        stream_rows<TI, VEC, YPB_SCAN_DEPTH16>(csrc, cs, nc, visit);  // 16-bit rows: half the bytes per load, twice the loads in flight
+        stream_rows_pipelined<TI, VEC, YPB_SCAN_PIPE16>(csrc, cs, nc, visit);  // 16-bit rows: loads of the next batch in flight during the math
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           m[2 * j] = Packed2<DT_IN>::lo(pm[j]);   m[2 * j + 1] = Packed2<DT_IN>::hi(pm[j]);
@@ -309,7 +344,7 @@ scan_classes_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
             cls[i] = gt ? c : cls[i];
           }
         };
-        stream_rows<TI, VEC>(csrc, cs, nc, visit);
+        stream_rows_pipelined<TI, VEC, YPB_SCAN_PIPE32>(csrc, cs, nc, visit);
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {

@@ -372,7 +372,10 @@ cudaError_t launch_scan_classes_tma(const HeadGeom& hg, int in_dtype, const Filt
   int ncw = ncw_env >= 1 && ncw_env <= TMA_MAX_NCW ? ncw_env : 12;
   const int row_bytes = 32 * lb;
   const size_t stage_bytes = static_cast<size_t>(hg.nc) * row_bytes;
-  int stages = static_cast<int>((200u * 1024u) / stage_bytes);
+  // ring size: all the shared memory of an SM by default; YPB_TMA_SMEM_KB caps it (leaves room for other streams' CTAs)
+  static const int smem_kb_env = env_int("YPB_TMA_SMEM_KB", 0);
+  const size_t ring_bytes = (smem_kb_env >= 16 && smem_kb_env <= 200 ? smem_kb_env : 200) * 1024u;
+  int stages = static_cast<int>(ring_bytes / stage_bytes);
   if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
   if (stages < 2) return cudaErrorNotSupported;
   if (ncw > stages) ncw = stages;

@@ -125,7 +125,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
               scale_padding: bool = True, peer_gather_group=None, nms_box=None, boxes_xyxy: bool = False,
               pad_output: bool = False, conf_per_image: torch.Tensor | None = None, rows_cap: int | None = None,
-              cached: bool = False) -> NmsPlan:
+              cached: bool = False, scan_kernel: int = 0) -> NmsPlan:
     """cached=True: the plan (parameter structs, fixed-stride result buffers) is kept per (thread, stream, geometry,
     parameters) and REUSED by the next call with the same key - only for callers that copy the results out before
     returning (``split_results`` packs them into fresh tensors); everything is stream-ordered, so reuse is safe."""
@@ -134,7 +134,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         ckey = None if classes is None else tuple(int(c) for c in (classes.tolist() if isinstance(classes, torch.Tensor) else classes))
         key = (device.index, torch.cuda.current_stream(device).cuda_stream, batch, anchors, nc, extra, conf_t, iou_eff, int(max_det),
                int(max_nms), float(max_wh), bool(multi_label), rule, ckey, bool(with_scale), bool(scale_padding),
-               None if nms_box is None else tuple(nms_box), bool(boxes_xyxy), bool(pad_output), rows_cap)
+               None if nms_box is None else tuple(nms_box), bool(boxes_xyxy), bool(pad_output), rows_cap, scan_kernel)
         cache = _plan_cache()
         hit = cache.get(key)
         if hit is not None:
@@ -146,7 +146,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         # inference_mode may still update them in place (set_transforms)
         with torch.inference_mode(False):
             plan = make_plan(device, batch, anchors, nc, extra, conf_t, iou_eff, max_det, max_nms, max_wh, multi_label, rule,
-                             classes, with_scale, scale_padding, None, nms_box, boxes_xyxy, pad_output, None, rows_cap, False)
+                             classes, with_scale, scale_padding, None, nms_box, boxes_xyxy, pad_output, None, rows_cap, False, scan_kernel)
         cache = _plan_cache()
         cache[key] = plan
         while len(cache) > _PLAN_CACHE_MAX:
@@ -182,6 +182,7 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
     if nms_box is not None:  # exporter NMSModel flavour: suppression on multiplier * (box / divisor)
         p.nms_box_divisor, p.nms_box_multiplier = float(nms_box[0]), float(nms_box[1])
     p.boxes_xyxy, p.pad_output = int(bool(boxes_xyxy)), int(bool(pad_output))
+    p.scan_kernel = int(scan_kernel)
     if conf_per_image is not None:
         p.conf_per_image = conf_per_image.data_ptr()
     # clean-on-exit counters owned by the plan: the calls then enqueue kernels only (no memset node); zeroed here, left

@@ -19,7 +19,7 @@ class HeadPostProcessor:
     def __init__(self, nc: int, strides, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                  agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                  max_wh: int = 7680, reg_max: int = 16, rotated: bool = False, scale_to_original: bool = False,
-                 peer_gather_group=None, use_graph: bool = False):
+                 peer_gather_group=None, use_graph: bool = False, scan_kernel: str = "auto"):
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
         self.nc, self.strides, self.reg_max = nc, tuple(float(s) for s in strides), reg_max
@@ -36,6 +36,9 @@ class HeadPostProcessor:
         # copy to pinned memory): a serving loop with static input buffers pays one graph launch and one stream
         # synchronisation per batch.  The returned views are then valid until the next call on the same inputs.
         self.use_graph = bool(use_graph)
+        # class-scan kernel of the fused path: "ldg" (one-wave grid, co-resident with other streams' kernels: multi-stream
+        # pipelines), "tma" (persistent TMA-fed ring: fastest single kernel, latency mode / 16-bit heads), "auto" = ldg
+        self.scan_kernel = {"auto": _cabi.SCAN_AUTO, "ldg": _cabi.SCAN_LDG, "tma": _cabi.SCAN_TMA}[scan_kernel]
         self._graphs = {}
         self._plans = {}
         self.last = None
@@ -54,7 +57,7 @@ class HeadPostProcessor:
                 plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
                                         iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
                                         self.multi_label, rule, self.classes, with_scale=self.scale_to_original,
-                                        peer_gather_group=self.peer_gather_group)
+                                        peer_gather_group=self.peer_gather_group, scan_kernel=self.scan_kernel)
                 # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
                 nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
                                                               plan.params.max_det, plan.params.max_nms, plan.params.rule)
