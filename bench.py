@@ -233,13 +233,14 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
             if gather_mode in ("nccl", "nccl-eager"):
                 gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
             elif gather_mode == "peer":
-                gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)  # the consumer's copy
+                gb = torch.empty((1, world, pl.peers.slot), dtype=torch.float32, device=dev)  # the consumer's copy of the entry
             grp = lane_groups[ln] if lane_groups else None
 
             def tail(pp=pp, pl=pl, gb=gb, host_counts=host_counts, grp=grp):
                 if gather_mode == "peer":
                     pp.wait_gather(lag)
-                    gb.copy_(pl.peers.entry_tensor())
+                    if not os.environ.get("YPB_BENCH_NO_CONSUME"):
+                        pl.peers.copy_entry(gb)
                 elif gather_mode == "nccl":
                     ypb_dist.gather_packed(pl.packed, gb, group=grp)
                 host_counts.copy_(pl.count, non_blocking=True)
@@ -584,7 +585,9 @@ def run_ours(args):
             del slanes, ssets
 
     # ---- per-kernel timing with CUDA events on the launching stream (roofline of the dominant kernel) ---------------
-    prefix_ms = _stage_times(dev, post, sets, K)
+    # (a post-processor of its own, WITHOUT the peer gather: nobody consumes - and acknowledges - ring entries here)
+    post_local = _post_for(cfg, "none")
+    prefix_ms = _stage_times(dev, post_local, sets, K)
     t_scan = prefix_ms[0]                  # ms: counter memset + class-scan/filter kernel
     t_decode = prefix_ms[1] - prefix_ms[0]  # ms: survivor tile box-decode kernel
     t_suppr = prefix_ms[2] - prefix_ms[1]   # ms: sort + suppress + gather kernel

@@ -173,7 +173,8 @@ typedef struct {
    *                                  ack[p] >= seq - peer_depth (back-pressure; NULL = none, single-consumer diagnostics only)
    *   peer_state                   : local device int32[4], zero-initialised once by the caller ([0] CTAs done,
    *                                  [1] launches sent so far = the sequence number ypb_peer_wait waits for,
-   *                                  [2] last batch handed to the consumer) */
+   *                                  [2] last batch handed to the consumer, [3] protocol overrun marker: both spin loops
+   *                                  are bounded (seconds) so a missing consumer / dead peer cannot hang the GPU) */
   int32_t num_peers;
   int32_t my_rank;
   int32_t peer_depth;

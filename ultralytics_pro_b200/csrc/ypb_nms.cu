@@ -814,8 +814,14 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
     __syncthreads();  // also: the local rows of this image are complete
     const int seq = s_seq;
     if (tid < a.num_peers && a.peer_ack) {
+      // bounded (~2 s): a consumer that never calls ypb_peer_wait must not hang the GPU - the entry is then overwritten and
+      // the overrun is recorded in peer_state[3] for the host to see
       const volatile int32_t* ack = a.peer_ack + tid;
-      while (*ack - (seq - a.peer_depth) < 0) __nanosleep(64);
+      int spins = 0;
+      while (*ack - (seq - a.peer_depth) < 0) {
+        __nanosleep(128);
+        if (++spins > (1 << 24)) { a.peer_state[3] = seq; break; }
+      }
     }
     __syncthreads();
     const int nfl = kept_n * cols;
@@ -1381,7 +1387,11 @@ __global__ void peer_wait_kernel_byval(const int32_t* flags, int world, int32_t*
     if (want > 0) {
       for (int r = 0; r < world; ++r) {
         const volatile int32_t* f = flags + r;
-        while (*f - want < 0) __nanosleep(100);
+        int spins = 0;
+        while (*f - want < 0) {  // bounded (~4 s): a peer that died must not hang this GPU; recorded in state[3] (negative)
+          __nanosleep(256);
+          if (++spins > (1 << 24)) { state[3] = -want; break; }
+        }
       }
     }
     __threadfence_system();

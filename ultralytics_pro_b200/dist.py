@@ -151,6 +151,12 @@ class PeerGather:
                                         self._ack_array, self.rank, self.slot_index.data_ptr(), _cabi.stream_ptr(self.buf.device))
         _cabi.check(rc, "ypb_peer_wait")
 
+    def overrun(self) -> int:
+        """0, or evidence of a broken protocol (reads the device state: synchronises): > 0 = a launch of this rank gave up
+        waiting for a consumer's acknowledgement and overwrote a ring entry (some rank never calls ``wait``); < 0 = a ``wait``
+        gave up waiting for a peer's launch."""
+        return int(self.state[3].item())
+
     def ring(self) -> torch.Tensor:
         """(depth, world, slot) view of the local ring."""
         return self.buf[: self.depth * self.entry].view(self.depth, self.world, self.slot)
@@ -159,6 +165,11 @@ class PeerGather:
         """(world, packed) copy-free-on-host selection of the entry the last executed ``wait`` returned: one device-side
         ``index_select`` with ``slot_index`` (capturable in a CUDA graph; no host synchronisation)."""
         return self.ring().index_select(0, self.slot_index)[0][:, : self.numel]
+
+    def copy_entry(self, out: torch.Tensor) -> torch.Tensor:
+        """Copy the entry the last executed ``wait`` returned into ``out`` ((1, world, slot) float32) with ONE device-side gather
+        (no temporary, no host synchronisation; capturable): the cheapest complete consumer."""
+        return torch.index_select(self.ring(), 0, self.slot_index, out=out)
 
     def gathered(self, batch_per_rank: int, max_det: int, cols: int):
         """(world*B, max_det, cols) rows and (world*B,) int32 counts of the entry the last executed ``wait`` returned."""
