@@ -238,9 +238,10 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
 
             def tail(pp=pp, pl=pl, gb=gb, host_counts=host_counts, grp=grp):
                 if gather_mode == "peer":
-                    pp.wait_gather(lag)
-                    if not os.environ.get("YPB_BENCH_NO_CONSUME"):
-                        pl.peers.copy_entry(gb)
+                    if os.environ.get("YPB_BENCH_NO_CONSUME"):
+                        pp.wait_gather(lag)
+                    else:
+                        pl.peers.wait_copy(gb, lag)  # wait + consume (copy the gathered entry out) in one kernel
                 elif gather_mode == "nccl":
                     ypb_dist.gather_packed(pl.packed, gb, group=grp)
                 host_counts.copy_(pl.count, non_blocking=True)

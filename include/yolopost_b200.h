@@ -299,6 +299,12 @@ YPB_API int ypb_match_predictions(const float* preds, int64_t pred_image_stride,
 YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth,
                           int32_t* const* peer_ack, int32_t my_rank, int64_t* slot_index, void* stream);
 
+/* ypb_peer_wait with the simplest complete consumer attached, in ONE kernel: after the wait, the returned ring entry
+ * (`entry_floats` floats at ring + index * entry_floats; a multiple of 4, 16-byte aligned) is copied to `out`. */
+YPB_API int ypb_peer_wait_copy(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth,
+                               int32_t* const* peer_ack, int32_t my_rank, int64_t* slot_index, const float* ring,
+                               int64_t entry_floats, float* out, void* stream);
+
 /* Same call restricted to some of its kernels, for per-kernel timing with CUDA events (bench.py roofline) and
  * profiling.  `stage` is a bit mask: 1 = clear counters + class-scan/filter/compaction kernel, 2 = survivor box-decode
  * kernel, 4 = sort + suppression + gather kernel (each on what the earlier stages left in `workspace`);

@@ -20,6 +20,7 @@ int main(void) {
   if (ypb_peer_wait(NULL, 2, NULL, 0, 3, NULL, 0, NULL, NULL) != YPB_ERR_INVALID_ARGUMENT) return 6;
   if (ypb_dist2bbox(NULL, 0, 0, NULL, 0, 0, 0, NULL, 0, YPB_F32, 1, 4, 1, NULL, 0, 0, NULL) != YPB_ERR_INVALID_ARGUMENT) return 8;
   if (ypb_dfl_expectation(NULL, YPB_F32, 1, 8, 4, 0, 0, NULL, 0, 0, NULL) != YPB_ERR_UNSUPPORTED) return 9;
+  if (ypb_peer_wait_copy(NULL, 2, NULL, 0, 3, NULL, 0, NULL, NULL, 0, NULL, NULL) != YPB_ERR_INVALID_ARGUMENT) return 10;
   if (sizeof(ypb_scale_xform) != 32 || YPB_MAX_PEERS != 8) return 7;
   printf("c abi ok, version %d, workspace C2 = %zu bytes\n", ypb_abi_version(), big);
   return 0;

@@ -68,15 +68,18 @@ SCRIPT = textwrap.dedent('''
             assert torch.equal(rr * valid, gr * valid), ("lag-1 consume", k)
         # the same inside CUDA graphs (kernels + wait + consumer copy captured together)
         lv = sets[0]
-        out = torch.zeros((world, pp.last.packed.numel()), dtype=torch.float32, device=dev)
-        g = pp.capture(lv, after=lambda: (pp.wait_gather(1), out.copy_(pp.last.peers.entry_tensor())))
+        peers = pp.last.peers
+        out = torch.zeros((world, peers.slot), dtype=torch.float32, device=dev)
+        g = pp.capture(lv, after=lambda: peers.wait_copy(out, 1))  # wait + consumer copy in ONE captured kernel
         for _ in range(7):
             g.replay()
         pp.wait_gather(0)
         check(lv, "graph, lag 1 + drain")
-        rr, rc = ypb_dist.split_packed(out, B, md, cols)
+        peers.wait_copy(out, 0)
+        torch.cuda.synchronize(dev)
+        rr, rc = ypb_dist.split_packed(out[:, : peers.numel].contiguous(), B, md, cols)
         gr, gc = pp.gathered()
-        assert torch.equal(rc, gc), "graph-captured consumer copy"
+        assert torch.equal(rc, gc) and int(gc.sum()) > 0, "wait_copy consumer"
     print("ok", rank, flush=True)
     dist.barrier(); torch.cuda.synchronize(dev); os._exit(0)
 ''')

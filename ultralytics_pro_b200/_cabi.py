@@ -44,6 +44,7 @@ EXPORTS = (
     "ypb_dist2bbox",
     "ypb_pairwise_iou",
     "ypb_compact_results",
+    "ypb_peer_wait_copy",
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
@@ -232,6 +233,9 @@ def load():
     lib.ypb_compact_results.restype = C.c_int
     lib.ypb_compact_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ypb_peer_wait_copy.restype = C.c_int
+    lib.ypb_peer_wait_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     if lib.ypb_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.ypb_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -560,6 +560,22 @@ int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t l
   return YPB_OK;
 }
 
+int ypb_peer_wait_copy(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth, int32_t* const* peer_ack,
+                       int32_t my_rank, int64_t* slot_index, const float* ring, int64_t entry_floats, float* out, void* stream) {
+  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
+  if (depth < 1 || (peer_ack && depth < lag + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, lag + 2);
+  if (my_rank < 0 || my_rank >= world) return fail(YPB_ERR_INVALID_ARGUMENT, "my_rank=%d outside [0,%d)", my_rank, world);
+  if (!ring || !out || entry_floats < 4 || entry_floats % 4 || !aligned(ring, 16) || !aligned(out, 16))
+    return fail(YPB_ERR_INVALID_ARGUMENT, "ring / out NULL or not 16-byte aligned, or entry_floats=%lld not a positive multiple of 4", (long long)entry_floats);
+  if (peer_ack)
+    for (int i = 0; i < world; ++i)
+      if (!peer_ack[i]) return fail(YPB_ERR_INVALID_ARGUMENT, "peer_ack[%d] is NULL", i);
+  cudaError_t e = ypb::launch_peer_wait_copy(flags, world, state, lag, depth, peer_ack, my_rank, reinterpret_cast<long long*>(slot_index),
+                                             ring, entry_floats, out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ypb_peer_wait_copy");
+  return YPB_OK;
+}
+
 void ypb_debug_set_phase_buffer(void* device_buffer) { ypb::set_phase_buffer(static_cast<long long*>(device_buffer)); }
 
 int ypb_selftest_sigmoid_monotone(int32_t dtype, unsigned long long* violations, void* stream) {

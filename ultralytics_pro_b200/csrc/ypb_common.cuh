@@ -517,6 +517,9 @@ cudaError_t launch_compact_results(const float* rows, const long long* idx, cons
 cudaError_t launch_pairwise_iou(const float* a, int n, const float* b, int m, int box_dim, float* out, cudaStream_t st);
 cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
                              int my_rank, long long* slot_index, cudaStream_t st);
+cudaError_t launch_peer_wait_copy(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
+                                  int my_rank, long long* slot_index, const float* ring, long long entry_floats, float* out,
+                                  cudaStream_t st);
 cudaError_t launch_sigmoid_selftest(int dtype, unsigned long long* violations, cudaStream_t st);
 
 }  // namespace ypb

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "ypb_common.cuh"
 
@@ -730,6 +731,64 @@ __device__ __forceinline__ float load_pred(const void* p, int dt, long long off)
   return load_as_float<YPB_BF16>(p, off);
 }
 
+// One-sided gather over NVLink (ypb_nms_out.peer_*), image b: the kept rows are contiguous floats in the local result buffer;
+// copy them and the count into ring entry (seq % depth) of every peer's buffer (this rank's own included) with plain
+// peer-mapped stores, then the last CTA of the launch publishes the launch sequence number in every peer's arrival flag.
+// Back-pressure: entry seq % depth was last filled by launch seq - depth; a peer has released it once its acknowledgement
+// (written into OUR buffer by its ypb_peer_wait) reached seq - depth.  Called by all `nthr` threads of a CTA.
+__device__ void peer_push(const SuppressArgs& a, int b, int kept_n, int nthr) {
+  const int tid = threadIdx.x;
+  const int cols = 6 + a.extra;
+    __shared__ int s_seq;
+    if (tid == 0) s_seq = a.peer_state[1] + 1;  // stable during the launch: only its LAST CTA advances peer_state[1]
+    __syncthreads();  // also: the local rows of this image are complete
+    const int seq = s_seq;
+    if (tid < a.num_peers && a.peer_ack) {
+      // bounded (~2 s): a consumer that never calls ypb_peer_wait must not hang the GPU - the entry is then overwritten and
+      // the overrun is recorded in peer_state[3] for the host to see
+      const volatile int32_t* ack = a.peer_ack + tid;
+      int spins = 0;
+      while (*ack - (seq - a.peer_depth) < 0) {
+        __nanosleep(128);
+        if (++spins > (1 << 24)) { a.peer_state[3] = seq; break; }
+      }
+    }
+    __syncthreads();
+    const int nfl = kept_n * cols;
+    const long long img_off = static_cast<long long>(b) * a.max_det * cols;
+    const long long entry = static_cast<long long>(seq % a.peer_depth) * a.peer_entry_stride;
+    const float* src = a.out_rows + img_off;
+    for (int p = 0; p < a.num_peers; ++p) {
+      float* dst = a.peer_rows[p] + entry + img_off;
+      if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+        for (int i = tid; i < (nfl >> 2); i += nthr) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int i = (nfl & ~3) + tid; i < nfl; i += nthr) dst[i] = src[i];
+      } else {
+        for (int i = tid; i < nfl; i += nthr) dst[i] = src[i];
+      }
+      if (tid == 0) reinterpret_cast<int32_t*>(reinterpret_cast<float*>(a.peer_count[p]) + entry)[b] = kept_n;
+    }
+    // every thread's remote stores are ordered before the barrier; ONE system-scope fence by the thread that then
+    // publishes (fences are cumulative), instead of 512 fences each waiting for its own remote acknowledgements
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const int prev = atomicAdd(&a.peer_state[0], 1);
+      if (prev == a.batch - 1) {  // last image of the launch
+        a.peer_state[0] = 0;
+        a.peer_state[1] = seq;
+        __threadfence_system();
+        for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
+      }
+    }
+}
+
+// The push as a kernel of its own (YPB_PEER_PUSH_SPLIT=1): light CTAs (no shared memory) wait for the remote stores'
+// acknowledgement instead of the suppression CTAs with their 170 KB of shared memory.
+__global__ void __launch_bounds__(128) peer_push_kernel(const __grid_constant__ SuppressArgs a) {
+  peer_push(a, blockIdx.x, min(a.out_count[blockIdx.x], a.max_det), 128);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // stage 3: gather the kept rows (nms.py:159-161), riders, optional rescale, zero padding and the one-sided peer push.
 // kk = kept keys in rank order (shared or global memory), kept_n <= max_det.  Called by every thread of ONE CTA.
@@ -803,55 +862,7 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
       a.out_rows[(static_cast<long long>(b) * a.max_det + k) * cols + 6 + e] = v;
     }
   }
-  if (a.num_peers > 0 && a.out_rows) {
-    // ---- one-sided gather over NVLink (ypb_nms_out.peer_*): the kept rows of this image are contiguous floats in the
-    //      local result buffer; copy them and the count into ring entry (seq % depth) of every peer's buffer (this rank's
-    //      own included) with plain peer-mapped stores, then the last CTA of the launch publishes the launch sequence
-    //      number in every peer's arrival flag.  Back-pressure: entry seq % depth was last filled by launch seq - depth; a
-    //      peer has released it once its acknowledgement (written into OUR buffer by its ypb_peer_wait) reached seq - depth.
-    __shared__ int s_seq;
-    if (tid == 0) s_seq = a.peer_state[1] + 1;  // stable during the launch: only its LAST CTA advances peer_state[1]
-    __syncthreads();  // also: the local rows of this image are complete
-    const int seq = s_seq;
-    if (tid < a.num_peers && a.peer_ack) {
-      // bounded (~2 s): a consumer that never calls ypb_peer_wait must not hang the GPU - the entry is then overwritten and
-      // the overrun is recorded in peer_state[3] for the host to see
-      const volatile int32_t* ack = a.peer_ack + tid;
-      int spins = 0;
-      while (*ack - (seq - a.peer_depth) < 0) {
-        __nanosleep(128);
-        if (++spins > (1 << 24)) { a.peer_state[3] = seq; break; }
-      }
-    }
-    __syncthreads();
-    const int nfl = kept_n * cols;
-    const long long img_off = static_cast<long long>(b) * a.max_det * cols;
-    const long long entry = static_cast<long long>(seq % a.peer_depth) * a.peer_entry_stride;
-    const float* src = a.out_rows + img_off;
-    for (int p = 0; p < a.num_peers; ++p) {
-      float* dst = a.peer_rows[p] + entry + img_off;
-      if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
-        for (int i = tid; i < (nfl >> 2); i += NT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-        for (int i = (nfl & ~3) + tid; i < nfl; i += NT) dst[i] = src[i];
-      } else {
-        for (int i = tid; i < nfl; i += NT) dst[i] = src[i];
-      }
-      if (tid == 0) reinterpret_cast<int32_t*>(reinterpret_cast<float*>(a.peer_count[p]) + entry)[b] = kept_n;
-    }
-    // every thread's remote stores are ordered before the barrier; ONE system-scope fence by the thread that then
-    // publishes (fences are cumulative), instead of 512 fences each waiting for its own remote acknowledgements
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      const int prev = atomicAdd(&a.peer_state[0], 1);
-      if (prev == a.batch - 1) {  // last image of the launch
-        a.peer_state[0] = 0;
-        a.peer_state[1] = seq;
-        __threadfence_system();
-        for (int p = 0; p < a.num_peers; ++p) *reinterpret_cast<volatile int32_t*>(a.peer_flag[p] + a.my_rank) = seq;
-      }
-    }
-  }
+  if (a.num_peers > 0 && a.out_rows) peer_push(a, b, kept_n, NT);
 }
 
 template <int RULE>
@@ -1400,6 +1411,50 @@ __global__ void peer_wait_kernel_byval(const int32_t* flags, int world, int32_t*
   }
 }
 
+// ypb_peer_wait with a consumer attached: after the wait, all threads copy the returned ring entry (world x slot floats)
+// into `out` - one kernel instead of wait + gather, for consumers that just want the gathered batch in a stable buffer.
+__global__ void __launch_bounds__(1024)
+peer_wait_copy_kernel(const int32_t* flags, int world, int32_t* state, int lag, int depth, PeerAckPtrs acks, int has_ack,
+                      int my_rank, long long* slot_index, const float* ring, long long entry_floats, float* out) {
+  __shared__ int s_slot;
+  if (threadIdx.x < 32) {
+    const int want = state[1] - lag;
+    const int done = state[2];
+    if (has_ack && threadIdx.x < world) *reinterpret_cast<volatile int32_t*>(acks.p[threadIdx.x] + my_rank) = done;
+    if (threadIdx.x == 0) {
+      if (want > 0) {
+        for (int r = 0; r < world; ++r) {
+          const volatile int32_t* f = flags + r;
+          int spins = 0;
+          while (*f - want < 0) {
+            __nanosleep(256);
+            if (++spins > (1 << 24)) { state[3] = -want; break; }
+          }
+        }
+      }
+      __threadfence_system();
+      state[2] = want > done ? want : done;
+      s_slot = want > 0 ? want % depth : 0;
+      if (slot_index) *slot_index = s_slot;
+    }
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(ring + static_cast<long long>(s_slot) * entry_floats);
+  float4* dst = reinterpret_cast<float4*>(out);
+  for (long long i = threadIdx.x; i < entry_floats / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t launch_peer_wait_copy(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
+                                  int my_rank, long long* slot_index, const float* ring, long long entry_floats, float* out,
+                                  cudaStream_t st) {
+  PeerAckPtrs acks{};
+  if (peer_ack_host)
+    for (int i = 0; i < world && i < YPB_MAX_PEERS; ++i) acks.p[i] = peer_ack_host[i];
+  peer_wait_copy_kernel<<<1, 1024, 0, st>>>(flags, world, state, lag, depth > 0 ? depth : 1, acks, peer_ack_host ? 1 : 0, my_rank,
+                                            slot_index, ring, entry_floats, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_wait(const int32_t* flags, int world, int32_t* state, int lag, int depth, int32_t* const* peer_ack_host,
                              int my_rank, long long* slot_index, cudaStream_t st) {
   PeerAckPtrs acks{};
@@ -1527,11 +1582,16 @@ cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
   if (a.batch <= 0) return cudaSuccess;
   SuppressArgs aa = a;
   aa.dbg = g_phase_buf.load(std::memory_order_relaxed);
+  static const bool split_push = [] { const char* e = std::getenv("YPB_PEER_PUSH_SPLIT"); return e && e[0] == '1'; }();
+  const bool push_after = split_push && a.num_peers > 0 && a.out_rows;
+  if (push_after) aa.num_peers = 0;  // the suppression kernel writes the local rows only; peer_push_kernel follows
   if (a.rule == YPB_NMS_FAST_PROBIOU || a.rule == YPB_NMS_FAST_BOXIOU) {
     aa.dbg = nullptr;
     e = a.rule == YPB_NMS_FAST_PROBIOU ? launch_fast_cluster<YPB_NMS_FAST_PROBIOU>(aa, dev, st)
                                        : launch_fast_cluster<YPB_NMS_FAST_BOXIOU>(aa, dev, st);
-    return e != cudaSuccess ? e : cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && push_after) { peer_push_kernel<<<a.batch, 128, 0, st>>>(a); e = cudaGetLastError(); }
+    return e;
   }
   const bool need_cfg = dev < 0 || dev >= 64 || !configured[dev][a.rule].load(std::memory_order_acquire);
   if (need_cfg) {
@@ -1540,7 +1600,9 @@ cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
     if (dev >= 0 && dev < 64) configured[dev][a.rule].store(true, std::memory_order_release);
   }
   sort_suppress_kernel<YPB_NMS_GREEDY><<<a.batch, NT, smem, st>>>(aa);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e == cudaSuccess && push_after) { peer_push_kernel<<<a.batch, 128, 0, st>>>(a); e = cudaGetLastError(); }
+  return e;
 }
 
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,

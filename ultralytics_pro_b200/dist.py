@@ -151,6 +151,17 @@ class PeerGather:
                                         self._ack_array, self.rank, self.slot_index.data_ptr(), _cabi.stream_ptr(self.buf.device))
         _cabi.check(rc, "ypb_peer_wait")
 
+    def wait_copy(self, out: torch.Tensor, lag: int = 0) -> None:
+        """``wait(lag)`` and the copy of the returned entry into ``out`` (>= world*slot float32, 16-byte aligned) in ONE kernel."""
+        from . import _cabi
+
+        if out.numel() < self.entry or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 tensor of >= {self.entry} elements")
+        rc = _cabi.load().ypb_peer_wait_copy(self.flags.data_ptr(), self.world, self.state.data_ptr(), int(lag), self.depth,
+                                             self._ack_array, self.rank, self.slot_index.data_ptr(), self.buf.data_ptr(),
+                                             self.entry, out.data_ptr(), _cabi.stream_ptr(self.buf.device))
+        _cabi.check(rc, "ypb_peer_wait_copy")
+
     def overrun(self) -> int:
         """0, or evidence of a broken protocol (reads the device state: synchronises): > 0 = a launch of this rank gave up
         waiting for a consumer's acknowledgement and overwrote a ring entry (some rank never calls ``wait``); < 0 = a ``wait``
