@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 9
+#define YPB_ABI_VERSION 10
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -272,7 +272,13 @@ YPB_API int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs,
                              int64_t coef_row_stride, const float* boxes, int64_t box_image_stride, int64_t box_row_stride,
                              const int32_t* offsets, int32_t batch, int32_t total, int32_t out_h, int32_t out_w,
                              int32_t win_top, int32_t win_left, int32_t win_h, int32_t win_w, int32_t crop_mode,
-                             float ratio_w, float ratio_h, uint8_t* out, void* stream);
+                             float ratio_w, float ratio_h, uint8_t* out, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* workspace (optional): ypb_process_mask_workspace_bytes(total, out_h, out_w) bytes of device scratch.  With it the call
+ * takes its two-step form - cudaMemset of the result, a work list of the (detection, 128x128 tile) pairs that can see their
+ * box, and a kernel that computes only those (typically ~15 % of the tiles); without it (NULL) one kernel zero-fills and
+ * computes every tile. */
+YPB_API size_t ypb_process_mask_workspace_bytes(int32_t total, int32_t out_h, int32_t out_w);
 
 /* Validator matching: engine/validator.py:267-307 match_predictions (non-scipy branch) with, optionally, the pairwise
  * metrics.py:54 box_iou of detect/val.py:287 computed on the fly.  correct: (B, rows_per_image, nthr) uint8.

@@ -211,7 +211,7 @@ def test_new_entry_points_validate_arguments_before_any_launch():
     assert lib.ypb_kpts_decode(C.byref(g), None, 0, 16, 6, 3, None, None) == -1 and "NULL" in err()
     pd = _cabi.ProtosDesc()
     pd.dtype, pd.channels, pd.mh, pd.mw, pd.stride_c = _cabi.YPB_F32, 32, 8, 8, 64
-    args = [None, 0, 32, None, 0, 4, None, 1, 0, 16, 16, 0, 0, 8, 8, _cabi.MASK_CROP_PROTO, 1.0, 1.0, None, None]
+    args = [None, 0, 32, None, 0, 4, None, 1, 0, 16, 16, 0, 0, 8, 8, _cabi.MASK_CROP_PROTO, 1.0, 1.0, None, None, 0, None]
     assert lib.ypb_process_mask(C.byref(pd), *args) == 0                                            # no detections: OK
     bad = list(args); bad[13] = 9                                                                  # window taller than the grid
     assert lib.ypb_process_mask(C.byref(pd), *bad) == -1 and "window" in err()

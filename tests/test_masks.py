@@ -98,6 +98,41 @@ def test_batched_masks_equal_per_image_calls(cuda_device):
     assert ops.process_mask(protos[0], rows[0, :0, 6:], rows[0, :0, :4], (160, 160), upsample=True).shape == (0, 160, 160)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["process_mask_up", "process_mask_native", "process_mask"])
+def test_two_step_masks_equal_single_kernel(cuda_device, kind, monkeypatch):
+    """The memset + work-list + compute-listed-tiles form (used for results >= ops.TWO_STEP_MIN_BYTES) writes exactly the
+    bytes the single kernel writes: boxes from a few pixels to the whole image, batched, odd sizes, repeated launches."""
+    from ultralytics_pro_b200 import ops
+
+    g = torch.Generator().manual_seed(17)
+    B, M, C, mh, mw = 3, 40, 32, 48, 64
+    protos = torch.randn(B, C, mh, mw, generator=g).to(cuda_device)
+    rows = torch.zeros(B, M, 6 + C)
+    xy = torch.rand(B, M, 2, generator=g) * torch.tensor([200.0, 150.0])
+    size = torch.exp(torch.rand(B, M, 2, generator=g) * 5)            # 1 .. 150 px
+    rows[..., :2], rows[..., 2:4] = xy, xy + size
+    rows[0, 0, :4] = torch.tensor([0.0, 0.0, 256.0, 192.0])            # the whole image
+    rows[..., 6:] = torch.randn(B, M, C, generator=g)
+    rows = rows.to(cuda_device)
+    shape = (192, 256) if kind != "process_mask_native" else (381, 509)
+
+    def run():
+        if kind == "process_mask_up":
+            return ops.process_masks_batched(protos, rows, [M, 7, 0], shape, upsample=True)
+        if kind == "process_mask_native":
+            return [ops.process_mask_native(protos[0], rows[0, :, 6:], rows[0, :, :4], shape)]
+        return [ops.process_mask(protos[1], rows[1, :, 6:], rows[1, :, :4], shape, upsample=False)]
+
+    monkeypatch.setattr(ops, "TWO_STEP_MIN_BYTES", 1 << 60)
+    single = run()
+    monkeypatch.setattr(ops, "TWO_STEP_MIN_BYTES", 0)
+    for _ in range(2):
+        two = run()
+        assert len(two) == len(single) and all(torch.equal(a, b) for a, b in zip(two, single))
+    assert sum(int(t.sum()) for t in single) > 0
+
+
 def test_mask_symbols_exported():
     from ultralytics_pro_b200 import _cabi
 

@@ -18,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -45,6 +45,7 @@ EXPORTS = (
     "ypb_pairwise_iou",
     "ypb_compact_results",
     "ypb_peer_wait_copy",
+    "ypb_process_mask_workspace_bytes",
 )
 MASK_CROP_PROTO, MASK_CROP_OUTPUT = 1, 2
 RIDER_RAW, RIDER_KEYPOINTS = 0, 1
@@ -213,7 +214,9 @@ def load():
     lib.ypb_process_mask.argtypes = [C.POINTER(ProtosDesc), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p,
-                                     C.c_void_p]
+                                     C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ypb_process_mask_workspace_bytes.restype = C.c_size_t
+    lib.ypb_process_mask_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.ypb_match_predictions.restype = C.c_int
     lib.ypb_match_predictions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,

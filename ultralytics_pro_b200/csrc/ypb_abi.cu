@@ -477,11 +477,17 @@ int ypb_scale_rows(float* rows, int64_t image_stride, int64_t row_stride, int32_
   return YPB_OK;
 }
 
+size_t ypb_process_mask_workspace_bytes(int32_t total, int32_t out_h, int32_t out_w) {
+  if (total <= 0 || out_h <= 0 || out_w <= 0) return 0;
+  const long long tiles = static_cast<long long>((out_w + 127) / 128) * ((out_h + 127) / 128) * total;
+  return static_cast<size_t>(tiles + 1) * sizeof(int32_t);
+}
+
 int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t coef_image_stride, int64_t coef_row_stride,
                      const float* boxes, int64_t box_image_stride, int64_t box_row_stride, const int32_t* offsets,
                      int32_t batch, int32_t total, int32_t out_h, int32_t out_w, int32_t win_top, int32_t win_left,
                      int32_t win_h, int32_t win_w, int32_t crop_mode, float ratio_w, float ratio_h, uint8_t* out,
-                     void* stream) {
+                     void* workspace, size_t workspace_bytes, void* stream) {
   if (!protos) return fail(YPB_ERR_INVALID_ARGUMENT, "protos descriptor is NULL");
   if (!dtype_ok(protos->dtype)) return fail(YPB_ERR_INVALID_ARGUMENT, "unknown dtype %d", protos->dtype);
   if (protos->channels < 1 || protos->mh < 1 || protos->mw < 1) return fail(YPB_ERR_INVALID_ARGUMENT, "empty prototypes");
@@ -505,7 +511,7 @@ int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t
   a.scale_h = static_cast<float>(win_h) / static_cast<float>(out_h);
   a.scale_w = static_cast<float>(win_w) / static_cast<float>(out_w);
   a.ratio_w = ratio_w; a.ratio_h = ratio_h; a.crop_mode = crop_mode; a.out = out;
-  cudaError_t e = ypb::launch_process_mask(a, static_cast<cudaStream_t>(stream));
+  cudaError_t e = ypb::launch_process_mask(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   if (e == cudaErrorInvalidConfiguration) return fail(YPB_ERR_UNSUPPORTED, "resize ratio %dx%d -> %dx%d needs too large a shared-memory footprint", win_h, win_w, out_h, out_w);
   if (e != cudaSuccess) return cuda_fail(e, "ypb_process_mask");
   return YPB_OK;

@@ -465,7 +465,7 @@ struct MaskArgs {  // ypb_process_mask
   int crop_mode;
   uint8_t* out;
 };
-cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st);
+cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 struct MatchArgs {  // ypb_match_predictions
   const float* preds;      // rows: x1,y1,x2,y2,...,cls at cls_col

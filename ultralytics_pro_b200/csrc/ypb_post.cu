@@ -110,19 +110,67 @@ __device__ __forceinline__ void bilinear_tap(float scale, int dst, int in_size, 
   w0 = __fsub_rn(1.f, w1);
 }
 
+// detection d -> (image, row) through the offsets prefix (binary search; offsets[lo] <= d < offsets[hi])
+__device__ __forceinline__ void mask_locate(const MaskArgs& a, int d, int& b, int& k) {
+  b = 0; k = d;
+  if (a.offsets) {
+    int lo = 0, hi = a.batch;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.offsets[mid] <= d) lo = mid; else hi = mid; }
+    b = lo; k = d - a.offsets[lo];
+  }
+}
+
+// Can the output tile [X0, X1] x [Y0, Y1] of detection (b, k) see the box at all?  (crop_mask keeps column r iff x1 <= r < x2,
+// row c iff y1 <= c < y2, ops.py:464-486).  Exactly the test the tile kernel makes before it computes anything.
+__device__ __forceinline__ bool mask_tile_empty(const MaskArgs& a, int b, int k, int X0, int Y0, int X1, int Y1) {
+  const float* bp = a.boxes + static_cast<long long>(b) * a.box_image_stride + static_cast<long long>(k) * a.box_row_stride;
+  float bx1 = bp[0], by1 = bp[1], bx2 = bp[2], by2 = bp[3];
+  if (a.crop_mode == YPB_MASK_CROP_PROTO) {
+    bx1 = __fmul_rn(bx1, a.ratio_w); by1 = __fmul_rn(by1, a.ratio_h); bx2 = __fmul_rn(bx2, a.ratio_w); by2 = __fmul_rn(by2, a.ratio_h);
+    int ry0, ry1, rx0, rx1, t0, t1;
+    float f0, f1;
+    bilinear_tap(a.scale_h, Y0, a.win_h, ry0, t1, f0, f1);
+    bilinear_tap(a.scale_h, Y1, a.win_h, t0, ry1, f0, f1);
+    bilinear_tap(a.scale_w, X0, a.win_w, rx0, t1, f0, f1);
+    bilinear_tap(a.scale_w, X1, a.win_w, t0, rx1, f0, f1);
+    return !(static_cast<float>(rx1 + a.win_left) >= bx1 && static_cast<float>(rx0 + a.win_left) < bx2 &&
+             static_cast<float>(ry1 + a.win_top) >= by1 && static_cast<float>(ry0 + a.win_top) < by2);
+  }
+  return !(static_cast<float>(X1) >= bx1 && static_cast<float>(X0) < bx2 && static_cast<float>(Y1) >= by1 && static_cast<float>(Y0) < by2);
+}
+
+// Work list of the two-step form: one thread per (detection, tile); tiles that can see their box are appended (unordered) to
+// list[1..], list[0] = their number.  Everything else of the (total, H, W) result is zero: a plain memset writes it at the
+// write-only ceiling of the memory system and no CTA is spent on it.
+__global__ void __launch_bounds__(256)
+mask_tile_list_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, int32_t* __restrict__ list) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per = tiles_x * tiles_y;
+  bool live = false;
+  if (t < static_cast<long long>(a.total) * per) {
+    const int d = static_cast<int>(t / per), r = static_cast<int>(t - static_cast<long long>(d) * per);
+    const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    int b, k;
+    mask_locate(a, d, b, k);
+    const int X0 = tx * MT_W, Y0 = ty * MT_H;
+    live = !mask_tile_empty(a, b, k, X0, Y0, min(X0 + MT_W, a.iw) - 1, min(Y0 + MT_H, a.ih) - 1);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(&list[0], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (live) list[1 + base + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(t);
+}
+
 template <int DT>
-__global__ void __launch_bounds__(MT_THREADS, 3)
-process_mask_kernel(const __grid_constant__ MaskArgs a) {
+__device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s_img, int d, int X0, int Y0, bool fill_empty) {
   using T = typename DType<DT>::type;
-  extern __shared__ __align__(16) float sm_f[];
   float* coef = sm_f;                 // [C]
   float4* xtap = reinterpret_cast<float4*>(sm_f + ((a.C + 3) & ~3));  // [MT_W] (x0, x1 as int bits, w0, w1) of every tile column
   float4* ytap = xtap + MT_W;                                          // [MT_H] the same for every tile row
   float* reg = reinterpret_cast<float*>(ytap + MT_H);  // [rh][rw] prototype-resolution values of this tile's footprint
-  __shared__ int s_img[2];
   const int tid = threadIdx.x;
-  const int d = blockIdx.z;
-  const int X0 = blockIdx.x * MT_W, Y0 = blockIdx.y * MT_H;
   const int X1 = min(X0 + MT_W, a.iw) - 1, Y1 = min(Y0 + MT_H, a.ih) - 1;  // inclusive
 
   // detection -> (image, row)
@@ -203,6 +251,7 @@ process_mask_kernel(const __grid_constant__ MaskArgs a) {
   }
 
   if (XS > X1) return;
+  if (empty && !fill_empty) return;  // two-step form: the memset already wrote the zeros
   const int XE = min(XS + 15, X1);
   // a segment / row whose taps all fall outside the crop box is zero (PROTO mode: the footprint values are zero there)
   bool seg_live = !empty;
@@ -259,6 +308,30 @@ process_mask_kernel(const __grid_constant__ MaskArgs a) {
     } else {
       for (int i = 0; i < 16 && XS + i <= X1; ++i) o[i] = static_cast<uint8_t>((w4[i >> 2] >> ((i & 3) * 8)) & 0xffu);
     }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(MT_THREADS, 3)
+process_mask_kernel(const __grid_constant__ MaskArgs a) {
+  extern __shared__ __align__(16) float sm_f[];
+  __shared__ int s_img[2];
+  mask_tile<DT>(a, sm_f, s_img, blockIdx.z, blockIdx.x * MT_W, blockIdx.y * MT_H, true);
+}
+
+// Two-step form: grid-stride over the work list of mask_tile_list_kernel (only tiles that can see their box).
+template <int DT>
+__global__ void __launch_bounds__(MT_THREADS, 3)
+process_mask_list_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, const int32_t* __restrict__ list) {
+  extern __shared__ __align__(16) float sm_f[];
+  __shared__ int s_img[2];
+  const int n = list[0], per = tiles_x * tiles_y;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int t = list[1 + e];
+    const int d = t / per, r = t - d * per;
+    const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    mask_tile<DT>(a, sm_f, s_img, d, tx * MT_W, ty * MT_H, false);
+    __syncthreads();  // shared memory is reused by the next tile
   }
 }
 
@@ -337,7 +410,7 @@ cudaError_t launch_match_predictions(const MatchArgs& a, int max_labels, cudaStr
   return cudaGetLastError();
 }
 
-cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
+cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (a.total <= 0 || a.ih <= 0 || a.iw <= 0) return cudaSuccess;
   // worst-case footprint of a tile in the prototype grid
   auto span = [](float scale, int n_out, int tile, int in) {
@@ -348,15 +421,34 @@ cudaError_t launch_process_mask(const MaskArgs& a, cudaStream_t st) {
   const int rh = span(a.scale_h, a.ih, MT_H, a.win_h), rw = span(a.scale_w, a.iw, MT_W, a.win_w);
   const size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float) + (MT_W + MT_H) * sizeof(float4);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  dim3 grid((a.iw + MT_W - 1) / MT_W, (a.ih + MT_H - 1) / MT_H, a.total);
-  if (grid.z > 65535u || grid.y > 65535u) return cudaErrorInvalidConfiguration;
+  const int tiles_x = (a.iw + MT_W - 1) / MT_W, tiles_y = (a.ih + MT_H - 1) / MT_H;
+  const long long ntiles = static_cast<long long>(a.total) * tiles_x * tiles_y;
+  // two-step form when the caller lends a work list: memset the result (the zeros of every tile that cannot see its box are
+  // written at the write-only ceiling, no CTA spent on them), list the tiles that can, compute only those
+  const bool two_step = workspace && workspace_bytes >= (static_cast<size_t>(ntiles) + 1) * sizeof(int32_t) && ntiles < (1ll << 31);
+  dim3 grid(tiles_x, tiles_y, a.total);
+  if (!two_step && (grid.z > 65535u || grid.y > 65535u)) return cudaErrorInvalidConfiguration;
+  int32_t* list = static_cast<int32_t*>(workspace);
+  if (two_step) {
+    cudaError_t e = cudaMemsetAsync(a.out, 0, static_cast<size_t>(a.total) * a.ih * a.iw, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(list, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    mask_tile_list_kernel<<<static_cast<unsigned>((ntiles + 255) / 256), 256, 0, st>>>(a, tiles_x, tiles_y, list);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned list_grid = static_cast<unsigned>(ntiles < 148 * 6 ? ntiles : 148 * 6);
 #define YPB_PM(DT)                                                                                                  \
   do {                                                                                                              \
     if (smem > 48 * 1024) {                                                                                         \
       cudaError_t e = cudaFuncSetAttribute(process_mask_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return e;                                                                               \
+      e = cudaFuncSetAttribute(process_mask_list_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                               \
     }                                                                                                               \
-    process_mask_kernel<DT><<<grid, MT_THREADS, smem, st>>>(a);                                                     \
+    if (two_step) process_mask_list_kernel<DT><<<list_grid, MT_THREADS, smem, st>>>(a, tiles_x, tiles_y, list);     \
+    else process_mask_kernel<DT><<<grid, MT_THREADS, smem, st>>>(a);                                                \
   } while (0)
   if (a.proto_dtype == YPB_F32) YPB_PM(YPB_F32);
   else if (a.proto_dtype == YPB_F16) YPB_PM(YPB_F16);

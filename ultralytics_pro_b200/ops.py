@@ -18,6 +18,7 @@ import torch
 from . import _cabi
 
 _f32 = _cabi.f32_round
+TWO_STEP_MIN_BYTES = 1 << 20  # process_mask results of at least this size take the memset + work-list form
 
 
 def letterbox_transform(img1_shape, img0_shape, ratio_pad=None) -> _cabi.ScaleXform:
@@ -221,10 +222,20 @@ def _scale_masks_window(mh: int, mw: int, shape, padding: bool = True):
 def _run_masks(pd, coeffs, cis, crs, boxes, bis, brs, offsets, batch, total, out_hw, window, crop_mode, ratios, device):
     out = torch.empty((total, out_hw[0], out_hw[1]), dtype=torch.uint8, device=device)
     if total:
-        rc = _cabi.load().ypb_process_mask(C.byref(pd), coeffs.data_ptr(), cis, crs, boxes.data_ptr(), bis, brs,
-                                           offsets.data_ptr() if offsets is not None else None, batch, total,
-                                           out_hw[0], out_hw[1], window[0], window[1], window[2], window[3], crop_mode,
-                                           ratios[0], ratios[1], out.data_ptr(), _cabi.stream_ptr(device))
+        lib = _cabi.load()
+        # two-step form (memset + work list + compute only the tiles that can see their box) when the result is large enough
+        # for the zero-fill to matter; TWO_STEP_MIN_BYTES = 0 / huge forces one or the other (tests cover both)
+        ws, ws_bytes = None, 0
+        if out.numel() >= TWO_STEP_MIN_BYTES:
+            from . import engine
+
+            ws_bytes = lib.ypb_process_mask_workspace_bytes(total, out_hw[0], out_hw[1])
+            ws = engine._scratch(device, ws_bytes)
+        rc = lib.ypb_process_mask(C.byref(pd), coeffs.data_ptr(), cis, crs, boxes.data_ptr(), bis, brs,
+                                  offsets.data_ptr() if offsets is not None else None, batch, total,
+                                  out_hw[0], out_hw[1], window[0], window[1], window[2], window[3], crop_mode,
+                                  ratios[0], ratios[1], out.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
+                                  _cabi.stream_ptr(device))
         _cabi.check(rc, "ypb_process_mask")
     return out
 
