@@ -508,6 +508,8 @@ cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_d
                                     int angle_is_logit, const FilterArgs& f, int vec, int which, cudaStream_t st);
 cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st);
 // persistent TMA-fed form of the class scan (ypb_scan_tma.cu); cudaErrorNotSupported = geometry outside its envelope
+cudaError_t launch_decode_dense_tma(const HeadGeom& g, int dtype, const void* angle, int angle_is_logit, int append_angle, int xyxy,
+                                    void* out, long long osb, long long osc, int vec, cudaStream_t st);
 cudaError_t launch_scan_classes_tma(const HeadGeom& g, int in_dtype, const FilterArgs& f, int vec, cudaStream_t st);
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,
