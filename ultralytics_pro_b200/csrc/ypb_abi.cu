@@ -166,15 +166,8 @@ int ypb_decode_dense(const ypb_head_desc* head, const void* angle, int32_t angle
   if (head->batch == 0) return YPB_OK;
   // 16-bit heads: 4 anchors (64-bit accesses) per thread instead of 8.  The 8-wide form needs 168-192 registers (3 CTAs
   // per SM, 1.3 waves) and is latency-bound at half the bytes; YPB_DENSE16_VEC=8 restores it for comparison.
-  // 16-bit heads: the persistent TMA-fed form (ypb_scan_tma.cu) when the geometry fits it; YPB_DENSE_TMA=0 forces the LDG kernel
-  static const bool dense_tma = [] { const char* e = std::getenv("YPB_DENSE_TMA"); return !(e && e[0] == '0'); }();
-  if (dense_tma && dtype_size(head->dtype) == 2 && vec == 8) {
-    cudaError_t et = ypb::launch_decode_dense_tma(g, head->dtype, angle, angle_is_logit, append_angle, xyxy, out, out_stride_b,
-                                                  out_stride_c, vec, static_cast<cudaStream_t>(stream));
-    if (et == cudaSuccess) return YPB_OK;
-    (void)cudaGetLastError();
-    if (et != cudaErrorNotSupported) return cuda_fail(et, "ypb_decode_dense (tma)");
-  }
+  // (a persistent TMA-fed form of this kernel was built and measured in round 2: 65 us vs 56 us for the bf16 C2 batch - the dense
+  // decode is bound by instruction issue (31 M warp instructions, 224 MUFU per anchor), not by bytes in flight; removed)
   static const int dense16_vec = [] { const char* e = std::getenv("YPB_DENSE16_VEC"); return (e && e[0] == '8') ? 8 : 4; }();
   if (dtype_size(head->dtype) == 2 && vec == 8 && dense16_vec == 4) {
     vec = 4;

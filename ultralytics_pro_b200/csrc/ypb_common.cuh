@@ -119,7 +119,24 @@ __device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& r) {
 // math of the decode (head.py:151-169, block.py:250-253, tal.py:367-403), fp32 opmath.
 // The SAME functions are used by the dense kernel and by the fused filter so the two agree bit for bit.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// exp / reciprocal as ONE special-function instruction each: `ex2.approx.ftz` / `rcp.approx.ftz`.  The non-ftz forms that
+// __expf / __fdividef compile to (no -ftz flag: the exact fp32 arithmetic of the IoU tests must keep denormals) wrap every
+// MUFU in a range check and two scalings - 3 extra instructions per exp, 144 exps + 84 reciprocals per anchor in the dense
+// decode, which is bound by instruction issue.  The values are the same: e^(v-m) <= 1 is only ever added to a sum >= 1 and
+// 1 + e^-x absorbs a denormal, so flushing changes no result bit; 1 / (1 + e^-x) for the overflowing x < -87 is 0 in
+// both forms (div.approx returns 0 for 2^126 < y).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_exp(float x) { return ex2_ftz(__fmul_rn(x, 1.4426950408889634f)); }  // == __expf
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(__fadd_rn(1.0f, fast_exp(-x))); }
 
 // torch max semantics: NaN is sticky.
 __device__ __forceinline__ float nanmax(float m, float v) { return (v > m || v != v) ? v : m; }
@@ -146,10 +163,10 @@ __device__ __forceinline__ float dfl_expect(const float (&v)[REG]) {
   float e[REG], p[REG];
 #pragma unroll
   for (int k = 0; k < REG; ++k) {
-    e[k] = __expf(__fsub_rn(v[k], m));
+    e[k] = fast_exp(__fsub_rn(v[k], m));
     p[k] = __fmul_rn(static_cast<float>(k), e[k]);
   }
-  return __fdividef(tree16(p), tree16(e));
+  return __fmul_rn(tree16(p), rcp_ftz(tree16(e)));  // == __fdividef: x * rcp(y), sum of e in [1, 16]
 }
 
 // Same expectation with the 16 bins spread over 16 consecutive lanes (lane & 15 = bin); every lane of the segment
@@ -158,14 +175,14 @@ __device__ __forceinline__ float dfl_expect_lanes16(float v, int bin) {
   float m = v;
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float e = __expf(__fsub_rn(v, m));
+  float e = fast_exp(__fsub_rn(v, m));
   float p = __fmul_rn(static_cast<float>(bin), e);
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     e = __fadd_rn(e, __shfl_xor_sync(0xffffffffu, e, o));
     p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o));
   }
-  return __fdividef(p, e);
+  return __fmul_rn(p, rcp_ftz(e));
 }
 
 struct BoxXYWH { float cx, cy, w, h; };
@@ -508,8 +525,6 @@ cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_d
                                     int angle_is_logit, const FilterArgs& f, int vec, int which, cudaStream_t st);
 cudaError_t launch_filter_from_dense(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st);
 // persistent TMA-fed form of the class scan (ypb_scan_tma.cu); cudaErrorNotSupported = geometry outside its envelope
-cudaError_t launch_decode_dense_tma(const HeadGeom& g, int dtype, const void* angle, int angle_is_logit, int append_angle, int xyxy,
-                                    void* out, long long osb, long long osc, int vec, cudaStream_t st);
 cudaError_t launch_scan_classes_tma(const HeadGeom& g, int in_dtype, const FilterArgs& f, int vec, cudaStream_t st);
 cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st);
 cudaError_t launch_boxes_prep(const float* boxes, const float* scores, int n, int box_dim, uint64_t* keys,

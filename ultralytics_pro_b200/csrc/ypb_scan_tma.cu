@@ -309,155 +309,6 @@ scan_classes_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_const
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Dense decode (Detect._inference drop-in, head.py:151-169 / OBB head.py:1026-1042) for 16-BIT heads as the same kind of
-// persistent TMA pipeline.  The register-staged kernel (decode_dense_kernel) needs 16 bin rows of a side in flight per
-// thread: at 8 anchors per thread that is 168-192 registers, at 4 anchors the loads are 64-bit and too few bytes are in
-// flight (0.62-0.69 of the copy peak).  Here ONE TMA box brings all 64 + nc rows of 128 anchors into a stage; the consumer
-// warps read them from shared memory (LDS.64), run the identical arithmetic (dfl_expect / decode_* / sigmoid_f of
-// ypb_common.cuh, so the result is bit-identical to the LDG kernel) and store 256 contiguous bytes per warp and row.
-// ---------------------------------------------------------------------------------------------------------------
-struct DenseTmaArgs {
-  const void* angle;   // (B, A) or null
-  int angle_is_logit, append_angle, mode;  // mode: 0 xywh, 1 xyxy, 2 rotated
-  void* out;
-  long long osb, osc;
-  int w[YPB_MAX_LEVELS];
-  float stride[YPB_MAX_LEVELS];
-  int anchors;
-};
-
-template <int DT>
-__global__ void __launch_bounds__(32 * (TMA_MAX_NCW + 1), 1)
-decode_dense_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaScanGeom g, const __grid_constant__ DenseTmaArgs d) {
-  using T = typename DType<DT>::type;
-  using D = DType<DT>;
-  constexpr int LB = 8, VEC = 4, ROWB = 32 * LB, TW = ROWB / 2;
-  constexpr int GW = 3;  // warps sharing one tile: role 0 decodes the box, roles 1..GW-1 split the class rows
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int S = g.stages, nc = g.nc, NCW = g.ncw, NG = NCW / GW;  // NG tile groups
-  const int rows_in = 64 + nc;
-  const int stage_bytes = rows_in * ROWB;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
-  uint64_t* empty = full + TMA_MAX_STAGES;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long total = static_cast<long long>(g.batch) * g.tiles_per_image;
-  const int total32 = static_cast<int>(total);
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == NCW) {
-    if (lane == 0) {
-      int s = 0, fill = 0;
-      for (int t = blockIdx.x; t < total32; t += gridDim.x) {
-        if (fill > 0) mbar_wait(&empty[s], (fill - 1) & 1);
-        const int b = t / g.tiles_per_image, r = t - b * g.tiles_per_image;
-        int l = 0;
-#pragma unroll
-        for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-          if (i < g.num_levels && r >= g.tile_start[i]) l = i;
-        mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
-        tma_load_3d(smem + static_cast<size_t>(s) * stage_bytes, &maps.m[l], (r - g.tile_start[l]) * TW, 0, b, &full[s]);
-        if (++s == S) { s = 0; ++fill; }
-      }
-    }
-    return;
-  }
-  // warp = (group, role): group takes this CTA's tiles number group, group + NG, ...; the GW warps of a group share the stage
-  const int group = warp / GW, role = warp - group * GW;
-  int s = group % S, fill = group / S;
-  const int s_step = NG % S, fill_step = NG / S;
-  for (long long tt = blockIdx.x + static_cast<long long>(group) * gridDim.x; tt < total; tt += static_cast<long long>(NG) * gridDim.x) {
-    const int t = static_cast<int>(tt);
-    const int b = t / g.tiles_per_image, r = t - b * g.tiles_per_image;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < YPB_MAX_LEVELS; ++i)
-      if (i < g.num_levels && r >= g.tile_start[i]) l = i;
-    const int a_local = (r - g.tile_start[l]) * TW + lane * VEC;
-    const bool in_level = a_local < g.level_anchors[l];
-    const int a_glob = g.anchor_start[l] + a_local;
-    mbar_wait(&full[s], fill & 1);
-    const unsigned char* tile = smem + static_cast<size_t>(s) * stage_bytes + lane * LB;
-    auto row = [&](int c) { return *reinterpret_cast<const Pack<T, VEC>*>(tile + static_cast<size_t>(c) * ROWB); };
-    T* out = static_cast<T*>(d.out) + static_cast<long long>(b) * d.osb + a_glob;
-
-    if (role == 0) {
-    // ---- boxes: DFL expectation per side, then dist2bbox / dist2rbox, x stride (same functions as decode_dense_kernel) ----
-    float dist[4][VEC];
-#pragma unroll
-    for (int side = 0; side < 4; ++side) {
-      Pack<T, VEC> raw[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) raw[k] = row(side * 16 + k);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = D::to_f(raw[k].v[i]);
-        dist[side][i] = dfl_expect<16>(v);
-      }
-    }
-    float theta[VEC];
-    if (d.mode == 2 && in_level) {
-      const T* ang = static_cast<const T*>(d.angle) + static_cast<long long>(b) * d.anchors + a_glob;
-      const Pack<T, VEC> pa = *reinterpret_cast<const Pack<T, VEC>*>(ang);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float tv = D::to_f(pa.v[i]);
-        theta[i] = d.angle_is_logit ? D::rnd(activate_angle(tv)) : tv;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) theta[i] = 0.f;
-    }
-    const int W = d.w[l];
-    const float stride = d.stride[l];
-    int gy = a_local / W, gx = a_local - gy * W;
-    Pack<T, VEC> o0, o1, o2, o3;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
-      BoxXYWH bx;
-      if (d.mode == 2) bx = decode_rotated(dist[0][i], dist[1][i], dist[2][i], dist[3][i], theta[i], ax, ay, stride);
-      else bx = decode_axis_aligned(dist[0][i], dist[1][i], dist[2][i], dist[3][i], ax, ay, stride, d.mode == 1);
-      o0.v[i] = D::from_f(bx.cx); o1.v[i] = D::from_f(bx.cy); o2.v[i] = D::from_f(bx.w); o3.v[i] = D::from_f(bx.h);
-      if (++gx == W) { gx = 0; ++gy; }
-    }
-    if (in_level) {
-      store_pack<T, VEC>(out, o0);
-      store_pack<T, VEC>(out + d.osc, o1);
-      store_pack<T, VEC>(out + 2 * d.osc, o2);
-      store_pack<T, VEC>(out + 3 * d.osc, o3);
-    }
-    if (d.mode == 2 && d.append_angle && in_level) {
-      Pack<T, VEC> q;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) q.v[i] = D::from_f(theta[i]);
-      store_pack<T, VEC>(out + static_cast<long long>(4 + nc) * d.osc, q);
-    }
-    } else {
-    // ---- class scores: sigmoid, this role's share of the rows (c = role-1, role-1 + GW-1, ...) from the stage --------------
-    T* cdst = out + 4 * d.osc;
-#pragma unroll 4
-    for (int c = role - 1; c < nc; c += GW - 1) {
-      const Pack<T, VEC> p = row(64 + c);
-      Pack<T, VEC> q;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) q.v[i] = D::from_f(sigmoid_f(D::to_f(p.v[i])));
-      if (in_level) store_pack<T, VEC>(cdst + static_cast<long long>(c) * d.osc, q);
-    }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // GW arrivals complete the phase
-    s += s_step;
-    fill += fill_step;
-    if (s >= S) { s -= S; ++fill; }
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -580,69 +431,6 @@ cudaError_t launch_scan_classes_tma(const HeadGeom& hg, int in_dtype, const Filt
   }
 #undef YPB_TMA
   return cudaErrorInvalidValue;
-}
-
-// 16-bit dense decode through the TMA pipeline; cudaErrorNotSupported = outside its envelope (the LDG kernel runs instead).
-cudaError_t launch_decode_dense_tma(const HeadGeom& hg, int dtype, const void* angle, int angle_is_logit, int append_angle,
-                                    int xyxy, void* out, long long osb, long long osc, int vec, cudaStream_t st) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc || dtype == YPB_F32 || vec != 8 || hg.nc < 1 || 64 + hg.nc > 256 || hg.batch < 1) return cudaErrorNotSupported;
-  if (osb % 4 || osc % 4 || (reinterpret_cast<uintptr_t>(out) & 7u)) return cudaErrorNotSupported;  // 8-byte stores
-  static const int ncw_env = env_int("YPB_DENSE_TMA_NCW", 0);
-  int ncw = ncw_env >= 3 && ncw_env <= TMA_MAX_NCW ? ncw_env / 3 * 3 : 15;  // 3 warps per tile group
-  constexpr int ROWB = 256, TW = 128;
-  const size_t stage_bytes = static_cast<size_t>(64 + hg.nc) * ROWB;
-  int stages = static_cast<int>((200u * 1024u) / stage_bytes);
-  if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
-  if (stages < 2) return cudaErrorNotSupported;
-  TmaScanGeom g{};
-  TmaMaps maps{};
-  DenseTmaArgs d{};
-  g.num_levels = hg.num_levels; g.batch = hg.batch; g.nc = hg.nc; g.stages = stages; g.ncw = ncw;
-  int ts = 0;
-  for (int l = 0; l < hg.num_levels; ++l) {
-    const int hw = hg.h[l] * hg.w[l];
-    if (hw % 4) return cudaErrorNotSupported;
-    g.tile_start[l] = ts;
-    ts += (hw + TW - 1) / TW;
-    g.level_anchors[l] = hw;
-    g.anchor_start[l] = hg.anchor_start[l];
-    d.w[l] = hg.w[l];
-    d.stride[l] = hg.stride[l];
-    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(hw), static_cast<cuuint64_t>(64 + hg.nc), static_cast<cuuint64_t>(hg.batch)};
-    const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(hg.cstride[l]) * 2, static_cast<cuuint64_t>(hg.bstride[l]) * 2};
-    const cuuint32_t box[3] = {static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(64 + hg.nc), 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (gstr[0] % 16 || (hg.batch > 1 && gstr[1] % 16) || gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return cudaErrorNotSupported;
-    const CUresult r = enc(&maps.m[l], dtype == YPB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                           const_cast<void*>(hg.ptr[l]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
-  }
-  for (int l = hg.num_levels; l <= YPB_MAX_LEVELS; ++l) { g.tile_start[l] = ts; g.anchor_start[l] = hg.anchor_start[l]; }
-  g.tiles_per_image = ts;
-  const long long total = static_cast<long long>(hg.batch) * ts;
-  if (total >= (1ll << 31)) return cudaErrorNotSupported;
-  if (angle && (reinterpret_cast<uintptr_t>(angle) & 7u)) return cudaErrorNotSupported;
-  d.angle = angle; d.angle_is_logit = angle_is_logit; d.append_angle = append_angle; d.mode = angle ? 2 : (xyxy ? 1 : 0);
-  d.out = out; d.osb = osb; d.osc = osc; d.anchors = hg.anchors;
-  if (ncw > stages * 3) ncw = stages * 3;  // more groups than stages would only wait
-  g.ncw = ncw;
-  int grid = sm_count();
-  if (grid > total) grid = static_cast<int>(total);
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 2 * TMA_MAX_STAGES * sizeof(uint64_t);
-  const int threads = 32 * (ncw + 1);
-  cudaError_t e;
-  if (dtype == YPB_F16) {
-    e = cudaFuncSetAttribute(decode_dense_tma_kernel<YPB_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    decode_dense_tma_kernel<YPB_F16><<<grid, threads, smem, st>>>(maps, g, d);
-  } else {
-    e = cudaFuncSetAttribute(decode_dense_tma_kernel<YPB_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    decode_dense_tma_kernel<YPB_BF16><<<grid, threads, smem, st>>>(maps, g, d);
-  }
-  return cudaGetLastError();
 }
 
 }  // namespace ypb
