@@ -573,6 +573,14 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         gather_verified = bool(flag.item())
 
+    if os.environ.get("YPB_BENCH_QUICK"):  # diagnostic: only the headline timing
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": total_ms / K, "gather_verified_against_nccl": gather_verified, "quick": True}))
+        sys.stdout.flush()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        os._exit(0)
     # ---- strong scaling (SURVEY 8e / north_star): ONE 64-image batch partitioned over the ranks (data/build.py:171-188) --
     strong = None
     if world > 1:

@@ -2,9 +2,12 @@ run() { echo "== $* $EXTRA"; env "$@" timeout 150 python -m torch.distributed.ru
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('value %.0f us/step %.2f verified %s strong %s' % (d['value'], d['ms_per_step']*1e3, d['gather_verified_against_nccl'], json.dumps(d.get('strong_scaling'))[60:160]))
+        d=json.loads(l); print('value %.0f us/step %.2f verified %s' % (d['value'], d['ms_per_step']*1e3, d['gather_verified_against_nccl']))
     elif 'rror' in l: print(l.strip()[:200])
 "; }
-timeout 200 python -m pytest tests/test_multi_gpu.py -x -q 2>&1 | tail -3
-EXTRA="" run A=1
-EXTRA="" run YPB_PEER_PUSH_SPLIT=1
+EXTRA="" run YPB_BENCH_QUICK=1
+EXTRA="" run YPB_BENCH_QUICK=1 YPB_PEER_DEBUG=1
+EXTRA="" run YPB_BENCH_QUICK=1 YPB_PEER_DEBUG=2
+EXTRA="" run YPB_BENCH_QUICK=1 YPB_PEER_DEBUG=7
+EXTRA="" run YPB_BENCH_QUICK=1 YPB_PEER_DEBUG=7 YPB_BENCH_NO_CONSUME=1
+EXTRA="--gather none" run YPB_BENCH_QUICK=1

@@ -436,6 +436,7 @@ struct SuppressArgs {
   const int32_t* peer_ack;        // local: acknowledgements written by the peers' ypb_peer_wait (or null: no back-pressure)
   int peer_depth;                 // ring entries per rank
   long long peer_entry_stride;    // floats between ring entries
+  int peer_debug;                 // diagnostic bit mask (YPB_PEER_DEBUG): 1 local ring only, 2 no fence, 4 no acknowledgement wait
   long long* dbg;  // diagnostic phase timestamps or null
 };
 void set_phase_buffer(long long* p);

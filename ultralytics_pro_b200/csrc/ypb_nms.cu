@@ -743,7 +743,7 @@ __device__ void peer_push(const SuppressArgs& a, int b, int kept_n, int nthr) {
     if (tid == 0) s_seq = a.peer_state[1] + 1;  // stable during the launch: only its LAST CTA advances peer_state[1]
     __syncthreads();  // also: the local rows of this image are complete
     const int seq = s_seq;
-    if (tid < a.num_peers && a.peer_ack) {
+    if (tid < a.num_peers && a.peer_ack && !(a.peer_debug & 4)) {
       // bounded (~2 s): a consumer that never calls ypb_peer_wait must not hang the GPU - the entry is then overwritten and
       // the overrun is recorded in peer_state[3] for the host to see
       const volatile int32_t* ack = a.peer_ack + tid;
@@ -759,6 +759,7 @@ __device__ void peer_push(const SuppressArgs& a, int b, int kept_n, int nthr) {
     const long long entry = static_cast<long long>(seq % a.peer_depth) * a.peer_entry_stride;
     const float* src = a.out_rows + img_off;
     for (int p = 0; p < a.num_peers; ++p) {
+      if ((a.peer_debug & 1) && p != a.my_rank) continue;  // diagnostic: local ring only
       float* dst = a.peer_rows[p] + entry + img_off;
       if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
         for (int i = tid; i < (nfl >> 2); i += nthr) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
@@ -772,7 +773,7 @@ __device__ void peer_push(const SuppressArgs& a, int b, int kept_n, int nthr) {
     // publishes (fences are cumulative), instead of 512 fences each waiting for its own remote acknowledgements
     __syncthreads();
     if (tid == 0) {
-      __threadfence_system();
+      if (!(a.peer_debug & 2)) __threadfence_system();
       const int prev = atomicAdd(&a.peer_state[0], 1);
       if (prev == a.batch - 1) {  // last image of the launch
         a.peer_state[0] = 0;
@@ -1582,6 +1583,8 @@ cudaError_t launch_sort_suppress(const SuppressArgs& a, cudaStream_t st) {
   if (a.batch <= 0) return cudaSuccess;
   SuppressArgs aa = a;
   aa.dbg = g_phase_buf.load(std::memory_order_relaxed);
+  static const int peer_debug = [] { const char* e = std::getenv("YPB_PEER_DEBUG"); return e ? std::atoi(e) : 0; }();
+  aa.peer_debug = peer_debug;
   static const bool split_push = [] { const char* e = std::getenv("YPB_PEER_PUSH_SPLIT"); return e && e[0] == '1'; }();
   const bool push_after = split_push && a.num_peers > 0 && a.out_rows;
   if (push_after) aa.num_peers = 0;  // the suppression kernel writes the local rows only; peer_push_kernel follows
