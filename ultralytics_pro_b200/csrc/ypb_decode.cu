@@ -212,9 +212,9 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
   // ---- class scores: sigmoid, streamed ---------------------------------------------------------------------------
   const TI* csrc = src + static_cast<long long>(4 * REG) * cs;
   TO* cdst = out + 4 * osc;
-  if constexpr (DT_IN != YPB_F32) {
-    // 16-bit rows carry half the bytes per load: keep the loads of the next 8 rows in flight while the current 8 are
-    // activated and stored (software pipeline), instead of load-batch / compute-batch phases
+  {
+    // keep the loads of the next 8 rows in flight while the current 8 are activated and stored (software pipeline), instead
+    // of load-batch / compute-batch phases: this loop carries no per-anchor state, so the second register buffer is free
     auto act = [&](const Pack<TI, VEC>& p, int c) {
       Pack<TO, VEC> q;
 #pragma unroll
@@ -222,15 +222,6 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
       store_pack<TO, VEC>(cdst + static_cast<long long>(c) * osc, q);
     };
     stream_rows_pipelined<TI, VEC, 8>(csrc, cs, nc, act);
-  } else {
-#pragma unroll 8
-    for (int c = 0; c < nc; ++c) {
-      Pack<TI, VEC> p = load_pack<TI, VEC>(csrc + static_cast<long long>(c) * cs);
-      Pack<TO, VEC> q;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) q.v[i] = DType<DT_OUT>::from_f(sigmoid_f(DType<DT_IN>::to_f(p.v[i])));
-      store_pack<TO, VEC>(cdst + static_cast<long long>(c) * osc, q);
-    }
   }
   if constexpr (MODE == MODE_ROT) {
     if (append_angle) {
