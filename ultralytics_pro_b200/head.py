@@ -209,9 +209,10 @@ def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch
 
     The reference takes the K anchors with the largest class maximum and then the K best pairs among their K*nc scores;
     for tie-free scores that is the global top-K over all pairs (an anchor outside the first set cannot own a pair that
-    beats K anchors' maxima).  Two passes of the filter + sort kernels, no suppression: pass 1 ranks the anchors by their
-    maximum and yields each image's K-th value T; pass 2 emits every pair with score >= T (K*nc at most unless scores tie) and ranks them.
-    Index arithmetic between the passes (picking T, nextafter) is torch plumbing on the device; nothing is read back."""
+    beats K anchors' maxima).  ONE pass over the scores: the filter + sort kernels rank the anchors by their maximum and yield
+    the K best anchors and the K-th value T; a second, tiny call ranks the pairs with score >= T of those K anchors only.
+    Index arithmetic between the two (picking T, nextafter, sorting / gathering B x K anchor rows) is torch plumbing on the
+    device; nothing is read back."""
     _cabi.require_cuda(preds, "detect_postprocess")
     if preds.dim() != 3 or preds.shape[2] != 4 + nc:
         raise ValueError(f"preds must be (B, A, {4 + nc}), got {tuple(preds.shape)}")
@@ -222,16 +223,20 @@ def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch
         return torch.zeros((b, k, 6), dtype=preds.dtype, device=dev)
     dense = preds.transpose(1, 2)  # (B, 4+nc, A) view; the kernels take any strides
     ninf = float("-inf")
+    # pass 1 (the only pass over all the scores): rank the anchors by their class maximum, keep the K best (head.py:208)
     first = engine.make_plan(dev, b, a, nc, 0, ninf, 1.0, k, a, 0.0, False, _cabi.RULE_GREEDY, boxes_xyxy=True)
     engine.run_from_dense(dense, first)
     kth = first.rows[:, k - 1, 4].contiguous()
     thr = torch.nextafter(kth, torch.full_like(kth, ninf))  # score > thr  <=>  score >= K-th anchor maximum
-    # rows_cap stays at the worst case A*nc (like every multi-label call): with TIED scores (16-bit heads, constant inputs,
-    # nc == 1) more than K anchors reach T and more than K*nc pairs pass; a smaller cap would drop whichever rows lost the
-    # race for the last slots.  All of them are ranked (score desc, row asc) and the first K are taken - deterministic.
-    second = engine.make_plan(dev, b, a, nc, 0, 0.0, 1.0, k, a * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
+    # pass 2 reads ONLY those K anchors (head.py:209-211 gathers them too): every pair that can reach the result lives in an
+    # anchor whose maximum is >= T, and among anchors tied at T the lower indices - the ones pass 1 kept - win the flat-index
+    # tie-break, so restricting to the kept anchors is exact.  They are taken in ascending anchor order so that "lower row
+    # first" inside pass 2 is "lower flat index first".  Index plumbing (sort / gather of B x K rows) stays on the device.
+    sel = first.idx[:, :k].clamp(0, a - 1).sort(dim=1).values
+    sub = preds.gather(1, sel.unsqueeze(-1).expand(-1, -1, 4 + nc))  # (B, K, 4+nc)
+    second = engine.make_plan(dev, b, k, nc, 0, 0.0, 1.0, k, k * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
                               conf_per_image=thr)
-    engine.run_from_dense(dense, second)
+    engine.run_from_dense(sub.transpose(1, 2), second)
     return second.rows.to(preds.dtype)
 
 
