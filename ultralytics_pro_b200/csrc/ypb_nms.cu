@@ -399,9 +399,15 @@ __device__ int select_prefix(const uint64_t* __restrict__ keys, int n, int lo, i
     const uint32_t dmask = (1u << w) - 1u;
     for (int i = tid; i < (1 << SEL_BITS); i += NT) hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += NT) {
-      const unsigned long long k = keys[i];
-      if (fixed == 0 || (k >> (64 - fixed)) == prefix) atomicAdd(&hist[static_cast<uint32_t>(k >> shift) & dmask], 1u);
+    for (int i0 = tid; i0 < n; i0 += 4 * NT) {  // 4 independent (L2) loads in flight per thread
+      unsigned long long k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? keys[i0 + u * NT] : 0ull;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned long long k = k4[u];
+        if (i0 + u * NT < n && (fixed == 0 || (k >> (64 - fixed)) == prefix)) atomicAdd(&hist[static_cast<uint32_t>(k >> shift) & dmask], 1u);
+      }
     }
     __syncthreads();
     if (tid < 32) {  // one warp scans the bins in order: first bin whose inclusive cumulative count reaches lo
@@ -703,17 +709,23 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
   const int kc = sm.kcount;
   YPB_MARK(21);
   if (kc > RANK_COUNT_MAX * 2) return -1;  // uniform; more kept rows than the ranking scratch holds - dense walk
-  // rank of a kept row = number of kept rows with a smaller key; the first max_det land in order in out_keys
+  // the kept rows in (score desc, row asc) order; the first max_det are the result.  Few rows: rank by counting (rank =
+  // number of kept rows with a smaller key, all threads in parallel).  Many (val mode: most of a 4096-row prefix survives):
+  // counting is O(kc^2) - 100 us at kc = 2000 - so the keys take the same bitonic network as the candidates.
   uint64_t* out_keys = reinterpret_cast<uint64_t*>(sm.cbox);  // boxes are no longer needed
   __syncthreads();
-  for (int i = tid; i < kc; i += NT) {
-    const uint64_t mine = kkeys[i];
-    int rank = 0;
+  if (kc <= 256) {
+    for (int i = tid; i < kc; i += NT) {
+      const uint64_t mine = kkeys[i];
+      int rank = 0;
 #pragma unroll 4
-    for (int j = 0; j < kc; ++j) rank += kkeys[j] < mine ? 1 : 0;
-    if (rank < a.max_det) out_keys[rank] = mine;
+      for (int j = 0; j < kc; ++j) rank += kkeys[j] < mine ? 1 : 0;
+      if (rank < a.max_det) out_keys[rank] = mine;
+    }
+    __syncthreads();
+  } else {
+    bitonic_sort(out_keys, kkeys, kc, KeyIdentity{});  // ascending keys == rank order; ends with a barrier
   }
-  __syncthreads();
   YPB_MARK(22);
   return min(kc, a.max_det);
 }
