@@ -399,21 +399,14 @@ __device__ int select_prefix(const uint64_t* __restrict__ keys, int n, int lo, i
     const uint32_t dmask = (1u << w) - 1u;
     for (int i = tid; i < (1 << SEL_BITS); i += NT) hist[i] = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 4 * NT) {  // warp-uniform trip count; 4 independent (L2) loads in flight per thread
+    for (int i0 = tid; i0 < n; i0 += 4 * NT) {  // 4 independent (L2) loads in flight per thread
       unsigned long long k4[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) k4[u] = base + u * NT + tid < n ? keys[base + u * NT + tid] : 0ull;
+      for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? keys[i0 + u * NT] : 0ull;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned long long k = k4[u];
-        const bool act = base + u * NT + tid < n && (fixed == 0 || (k >> (64 - fixed)) == prefix);
-        const uint32_t dgt = static_cast<uint32_t>(k >> shift) & dmask;
-        // scores cluster in a few dozen buckets: one shared-memory atomic per (warp, distinct digit), not per key
-        const unsigned am = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          const unsigned peers = __match_any_sync(am, dgt);
-          if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[dgt], static_cast<uint32_t>(__popc(peers)));
-        }
+        if (i0 + u * NT < n && (fixed == 0 || (k >> (64 - fixed)) == prefix)) atomicAdd(&hist[static_cast<uint32_t>(k >> shift) & dmask], 1u);
       }
     }
     __syncthreads();
