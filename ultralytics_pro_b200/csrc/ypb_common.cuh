@@ -84,7 +84,13 @@ __device__ __forceinline__ Pack<T, VEC> load_pack(const T* p) {
   } else if constexpr (sizeof(T) * VEC == 8) {
     Pack<T, VEC> r;
     int2 raw;
+#if defined(YPB_LOAD8_L2_256)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.s32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+#elif defined(YPB_LOAD8_L2_128)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.s32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+#endif
     *reinterpret_cast<int2*>(&r) = raw;
     return r;
   } else if constexpr (sizeof(T) * VEC == 4) {
@@ -106,12 +112,34 @@ __device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& r) {
   if constexpr (sizeof(T) * VEC == 16) {
     __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(&r));
   } else if constexpr (sizeof(T) * VEC == 8) {
+#if defined(YPB_STORE8_PLAIN)
+    *reinterpret_cast<int2*>(p) = *reinterpret_cast<const int2*>(&r);
+#elif defined(YPB_STORE8_WT)
+    __stwt(reinterpret_cast<int2*>(p), *reinterpret_cast<const int2*>(&r));
+#else
     __stcs(reinterpret_cast<int2*>(p), *reinterpret_cast<const int2*>(&r));
+#endif
   } else if constexpr (sizeof(T) * VEC == 4) {
     __stcs(reinterpret_cast<int*>(p), *reinterpret_cast<const int*>(&r));
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+  }
+}
+
+// Element i of a pack, widened to fp32 with ONE instruction: the compiler turns a 16-bit field read followed by
+// __bfloat162float into PRMT + SHL (two issue slots per element in kernels bound by instruction issue); reading the
+// containing 32-bit word and shifting / masking it is the same value in one.
+template <int DT, int VEC>
+__device__ __forceinline__ float pack_elem(const Pack<typename DType<DT>::type, VEC>& p, int i) {
+  if constexpr (DT == YPB_BF16 && VEC % 2 == 0) {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(&p)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  } else if constexpr (DT == YPB_F16 && VEC % 2 == 0) {
+    const __half2 h = reinterpret_cast<const __half2*>(&p)[i >> 1];
+    return (i & 1) ? __high2float(h) : __low2float(h);
+  } else {
+    return DType<DT>::to_f(p.v[i]);
   }
 }
 
@@ -142,9 +170,8 @@ __device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(__fadd_rn(1
 __device__ __forceinline__ float nanmax(float m, float v) { return (v > m || v != v) ? v : m; }
 
 // Expectation of the softmax over 16 bins (DFL, block.py:250-253).  v[k] = logit of bin k.
-// The two sums use a FIXED butterfly association order (k ^ 8, ^ 4, ^ 2, ^ 1) with separately rounded products, so the
-// in-register version (dense kernel, one thread per anchor) and the warp-shuffle version (fused filter, 16 lanes per
-// side) are bit-identical.
+// The sums use a FIXED association order of explicitly rounded operations, so every kernel that inlines them (dense decode,
+// survivor decode of the fused path, stand-alone DFL) produces the same bits.
 __device__ __forceinline__ float tree16(const float (&v)[16]) {
   float a[8], b[4];
 #pragma unroll
@@ -154,12 +181,21 @@ __device__ __forceinline__ float tree16(const float (&v)[16]) {
   return __fadd_rn(__fadd_rn(b[0], b[2]), __fadd_rn(b[1], b[3]));
 }
 
+// YPB_DFL_FORM 1 (default): the shift by the maximum is folded into the exponent's scaling, t_k = fma(v_k, log2 e, -rn(m log2 e)),
+// and the weighted sum runs as four FFMA chains: 91 instead of 134 instructions per (anchor, side) in kernels that are
+// bound by instruction issue.  The constant subtracted is the SAME for the 16 bins, so its rounding cancels in the ratio;
+// every operation is an explicit _rn intrinsic, so all inlining contexts (dense, fused, stand-alone DFL) round alike.
+// YPB_DFL_FORM 0: round 1's form (separate subtract / scale, balanced trees for both sums).
+#ifndef YPB_DFL_FORM
+#define YPB_DFL_FORM 1
+#endif
 template <int REG>
 __device__ __forceinline__ float dfl_expect(const float (&v)[REG]) {
   static_assert(REG == 16, "only reg_max = 16 is built");
   float m = v[0];
 #pragma unroll
   for (int k = 1; k < REG; ++k) m = fmaxf(m, v[k]);
+#if YPB_DFL_FORM == 0
   float e[REG], p[REG];
 #pragma unroll
   for (int k = 0; k < REG; ++k) {
@@ -167,22 +203,24 @@ __device__ __forceinline__ float dfl_expect(const float (&v)[REG]) {
     p[k] = __fmul_rn(static_cast<float>(k), e[k]);
   }
   return __fmul_rn(tree16(p), rcp_ftz(tree16(e)));  // == __fdividef: x * rcp(y), sum of e in [1, 16]
-}
-
-// Same expectation with the 16 bins spread over 16 consecutive lanes (lane & 15 = bin); every lane of the segment
-// returns the result.  Butterfly order matches tree16.
-__device__ __forceinline__ float dfl_expect_lanes16(float v, int bin) {
-  float m = v;
+#else
+  const float L2E = 1.4426950408889634f;
+  const float nm = __fmul_rn(-m, L2E);
+  float e[REG];
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float e = fast_exp(__fsub_rn(v, m));
-  float p = __fmul_rn(static_cast<float>(bin), e);
+  for (int k = 0; k < REG; ++k) e[k] = ex2_ftz(__fmaf_rn(v[k], L2E, nm));
+  float q[4];
+  q[0] = __fmaf_rn(3.f, e[3], __fmaf_rn(2.f, e[2], e[1]));
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    e = __fadd_rn(e, __shfl_xor_sync(0xffffffffu, e, o));
-    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o));
+  for (int j = 1; j < 4; ++j) {
+    const int k = 4 * j;
+    q[j] = __fmaf_rn(static_cast<float>(k + 3), e[k + 3],
+                     __fmaf_rn(static_cast<float>(k + 2), e[k + 2],
+                               __fmaf_rn(static_cast<float>(k + 1), e[k + 1], __fmul_rn(static_cast<float>(k), e[k]))));
   }
-  return __fmul_rn(p, rcp_ftz(e));
+  const float sp = __fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3]));
+  return __fmul_rn(sp, rcp_ftz(tree16(e)));  // sum of e in (0.99, 16]
+#endif
 }
 
 struct BoxXYWH { float cx, cy, w, h; };

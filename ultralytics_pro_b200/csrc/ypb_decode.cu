@@ -234,6 +234,148 @@ decode_dense_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// dense decode of 16-bit heads as ONE uniform row pipeline (round 2; fp32 heads keep decode_dense_kernel, 0.95 of the copy peak)
+//
+//   thread = 4 anchors (64-bit accesses); the 64 + nc channel rows of its anchors are walked in batches of 16 rows: a batch
+//   is exactly one DFL side (16 bins) or 16 class rows.  Two register buffers alternate: the 16 loads of batch k+1 are
+//   issued before batch k is consumed, so every thread keeps 16 independent 8-byte loads in flight through the arithmetic
+//   of BOTH phases (16 warps x 32 lanes x 16 x 8 B = 64 KB per SM; round 1's form had 8 in flight in the class phase and
+//   none across the four sides).  The batch loop is rolled (two bodies, one per buffer) instead of four unrolled sides plus an
+//   unrolled class loop: 1/3 of the code, which matters because the old kernel lost 0.84 warp-stalls per issue to
+//   instruction fetch (ncu, profiles/r02_dense_bf16_raw.csv).  Element unpacking is one instruction (pack_elem).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef YPB_DD16_MIN_BLOCKS
+#define YPB_DD16_MIN_BLOCKS 4
+#endif
+template <int DT, int MODE>
+__global__ void __launch_bounds__(DEC_THREADS, YPB_DD16_MIN_BLOCKS)
+decode_dense16_kernel(const __grid_constant__ HeadGeom g, const void* __restrict__ angle_v, int angle_is_logit,
+                      int append_angle, void* __restrict__ out_v, long long osb, long long osc) {
+  using T = typename DType<DT>::type;
+  using D = DType<DT>;
+  constexpr int VEC = 4, R = 16;
+  using P = Pack<T, VEC>;
+  const int grp = blockIdx.x * DEC_THREADS + threadIdx.x;
+  const int b = blockIdx.y;
+  if (grp >= g.group_start[g.num_levels]) return;
+  const int l = find_level(g, grp);
+  const int a_local = (grp - g.group_start[l]) * VEC;
+  const int a_glob = g.anchor_start[l] + a_local;
+  const long long cs = g.cstride[l];
+  const T* src = static_cast<const T*>(g.ptr[l]) + static_cast<long long>(b) * g.bstride[l] + a_local;
+  T* out = static_cast<T*>(out_v) + static_cast<long long>(b) * osb + a_glob;
+  const int nc = g.nc;
+  const int nb = 4 + nc / R;  // whole batches: 4 sides, then the class rows 16 at a time
+
+  float dl[VEC], dt[VEC], dr[VEC];  // sides 0..2; side 3 is consumed where it is produced
+
+  auto load_batch = [&](P (&buf)[R], int k) {
+    const T* p = src + static_cast<long long>(k * R) * cs;
+#pragma unroll
+    for (int j = 0; j < R; ++j) { buf[j] = load_pack<T, VEC>(p); p += cs; }
+  };
+  auto process = [&](const P (&buf)[R], int k) {
+    if (k < 4) {
+      float d[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float v[R];
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) v[kk] = pack_elem<DT, VEC>(buf[kk], i);
+        d[i] = dfl_expect<R>(v);
+      }
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dl[i] = d[i];
+      } else if (k == 1) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dt[i] = d[i];
+      } else if (k == 2) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dr[i] = d[i];
+      } else {
+        // ---- all four sides known: dist2bbox / dist2rbox, x stride (tal.py:367-403, head.py:168) ----
+        float theta[VEC];
+        if constexpr (MODE == MODE_ROT) {
+          const T* ang = static_cast<const T*>(angle_v) + static_cast<long long>(b) * g.anchors + a_glob;
+          const P pa = load_pack<T, VEC>(ang);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float t = pack_elem<DT, VEC>(pa, i);
+            theta[i] = angle_is_logit ? D::rnd(activate_angle(t)) : t;
+          }
+        }
+        const int W = g.w[l];
+        const float stride = g.stride[l];
+        int gy = a_local / W, gx = a_local - gy * W;
+        P o0, o1, o2, o3;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+          BoxXYWH bx;
+          if constexpr (MODE == MODE_ROT)
+            bx = decode_rotated(dl[i], dt[i], dr[i], d[i], theta[i], ax, ay, stride);
+          else
+            bx = decode_axis_aligned(dl[i], dt[i], dr[i], d[i], ax, ay, stride, MODE == MODE_XYXY);
+          o0.v[i] = D::from_f(bx.cx);
+          o1.v[i] = D::from_f(bx.cy);
+          o2.v[i] = D::from_f(bx.w);
+          o3.v[i] = D::from_f(bx.h);
+          if (++gx == W) { gx = 0; ++gy; }
+        }
+        store_pack<T, VEC>(out, o0);
+        store_pack<T, VEC>(out + osc, o1);
+        store_pack<T, VEC>(out + 2 * osc, o2);
+        store_pack<T, VEC>(out + 3 * osc, o3);
+        if constexpr (MODE == MODE_ROT) {
+          if (append_angle) {
+            P q;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) q.v[i] = D::from_f(theta[i]);
+            store_pack<T, VEC>(out + static_cast<long long>(4 + nc) * osc, q);
+          }
+        }
+      }
+    } else {
+      // ---- 16 class rows: sigmoid (head.py:169), stored where the cat of head.py:169 puts them ----
+      T* q_row = out + static_cast<long long>(4 + (k - 4) * R) * osc;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        P q;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) q.v[i] = D::from_f(sigmoid_f(pack_elem<DT, VEC>(buf[j], i)));
+        store_pack<T, VEC>(q_row, q);
+        q_row += osc;
+      }
+    }
+  };
+
+  P bufa[R], bufb[R];
+  load_batch(bufa, 0);
+#pragma unroll 1
+  for (int k = 0; k < nb; k += 2) {
+    if (k + 1 < nb) load_batch(bufb, k + 1);
+    process(bufa, k);
+    if (k + 1 >= nb) break;
+    if (k + 2 < nb) load_batch(bufa, k + 2);
+    process(bufb, k + 1);
+  }
+  // class rows beyond the last whole batch (nc % 16)
+  const int c0 = (nc / R) * R;
+  if (c0 < nc) {
+    const T* csrc = src + static_cast<long long>(4 * R + c0) * cs;
+    T* cdst = out + static_cast<long long>(4 + c0) * osc;
+    auto act = [&](const P& p, int c) {
+      P q;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) q.v[i] = D::from_f(sigmoid_f(pack_elem<DT, VEC>(p, i)));
+      store_pack<T, VEC>(cdst + static_cast<long long>(c) * osc, q);
+    };
+    stream_rows<T, VEC, 8>(csrc, cs, nc - c0, act);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // fused path, kernel 1: class scan + confidence filter + compaction (nms.py:76-131 evaluated on head.py:169's scores
 // without ever materialising them)
 //
@@ -714,6 +856,17 @@ static cudaError_t decode_dense_dispatch(const HeadGeom& g, const void* angle, i
                                          int xyxy, void* out, long long osb, long long osc, cudaStream_t st) {
   const int groups = g.group_start[g.num_levels];
   dim3 grid((groups + DEC_THREADS - 1) / DEC_THREADS, g.batch);
+#ifndef YPB_DD16_OLD
+  if constexpr (DT_IN != YPB_F32 && DT_IN == DT_OUT && VEC == 4) {
+    if (angle)
+      decode_dense16_kernel<DT_IN, MODE_ROT><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+    else if (xyxy)
+      decode_dense16_kernel<DT_IN, MODE_XYXY><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+    else
+      decode_dense16_kernel<DT_IN, MODE_XYWH><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
+    return cudaGetLastError();
+  }
+#endif
   if (angle)
     decode_dense_kernel<DT_IN, DT_OUT, VEC, 16, MODE_ROT><<<grid, DEC_THREADS, 0, st>>>(g, angle, angle_is_logit, append_angle, out, osb, osc);
   else if (xyxy)
