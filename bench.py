@@ -228,7 +228,9 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
             pp = _post_for(cfg, gather_mode, scan_kernel)
             my_sets = [sets[(ln + nlanes * j) % len(sets)] for j in range(2)]
             pl = pp.enqueue(*my_sets[0])  # builds the plan / result buffers (collective when the peer gather is on)
-            host_counts = torch.empty((pl.count.numel(),), dtype=torch.int32).pin_memory()
+            # the per-image counts reach pinned HOST memory inside every step: written there by the suppression kernel itself
+            # (ypb_nms_out.count_host, mapped memory) - no copy node; a plan without that buffer gets an explicit copy
+            host_counts = pl.count_host if pl.count_host is not None else torch.empty((pl.count.numel(),), dtype=torch.int32).pin_memory()
             gb = None
             if gather_mode in ("nccl", "nccl-eager"):
                 gb = torch.empty((world, pl.packed.numel()), dtype=torch.float32, device=dev)
@@ -245,7 +247,8 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
                         pl.peers.copy_entry(gb)
                 elif gather_mode == "nccl":
                     ypb_dist.gather_packed(pl.packed, gb, group=grp)
-                host_counts.copy_(pl.count, non_blocking=True)
+                if pl.count_host is None:
+                    host_counts.copy_(pl.count, non_blocking=True)
 
             graphs = None
             if use_graph:
@@ -670,7 +673,7 @@ def run_ours(args):
                        "l2": f"inputs {B * in_bytes_img / 1e6:.0f} MB per step > 126 MB L2; {NSETS} rotating input sets",
                        "cuda_graph": use_graph, "lanes": LANES,
                        "timed_region": "per step: class scan, survivor decode, sort+suppress+gather (3 kernels; the plan-owned clean-on-exit counters need no memset), "
-                                       "the per-image counts copied to pinned HOST memory" + (", the gathered results of all ranks copied out of the peer ring" if gather_mode == "peer" else ""),
+                                       "the per-image counts written to pinned HOST memory by the suppression kernel" + (", the gathered results of all ranks copied out of the peer ring" if gather_mode == "peer" else ""),
                        "parallelism": ("images sharded across ranks, no data-path collective; results gathered on every rank each step by "
                                        + {"peer": f"one-sided NVLink peer-memory stores issued by the suppression kernel into a 3-entry ring with consumer acknowledgements + an arrival-flag wait (lag {args.gather_lag} batch per lane; every gathered batch is CONSUMED - copied out - inside the step; drained before the clock stops), all inside the lane's CUDA graph",
                                           "nccl": "one packed NCCL all_gather (one communicator per lane) captured in the lane's CUDA graph",

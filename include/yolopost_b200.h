@@ -35,7 +35,7 @@ extern "C" {
 #define YPB_API
 #endif
 
-#define YPB_ABI_VERSION 10
+#define YPB_ABI_VERSION 11
 #define YPB_MAX_LEVELS 8
 #define YPB_MAX_PEERS 8 /* GPUs of one NVSwitch node */
 
@@ -184,6 +184,11 @@ typedef struct {
   int32_t* peer_state;
   const int32_t* peer_ack;
   int64_t peer_entry_stride;
+  /* count_host: NULL, or the device-accessible address of (B) int32 in pinned (mapped) HOST memory.  The suppression kernel
+   * then stores every per-image count there as well: the one quantity of the call a host needs before it can cut the rows
+   * (nms.py:159-161 returns a list of (n_i, 6+extra) tensors) arrives without a copy node behind the kernels; it is valid
+   * once the stream has been synchronised (or an event recorded behind the call has completed). */
+  int32_t* count_host;
 } ypb_nms_out;
 
 YPB_API int ypb_abi_version(void);

@@ -18,7 +18,7 @@ YPB_F32, YPB_F16, YPB_BF16 = 0, 1, 2
 RULE_GREEDY, RULE_FAST_PROBIOU, RULE_FAST_BOXIOU = 0, 1, 2
 MAX_LEVELS = 8
 MAX_PEERS = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _DTYPES = {torch.float32: YPB_F32, torch.float16: YPB_F16, torch.bfloat16: YPB_BF16}
 
@@ -126,6 +126,7 @@ class NmsOut(C.Structure):
         ("peer_state", C.c_void_p),
         ("peer_ack", C.c_void_p),
         ("peer_entry_stride", C.c_int64),
+        ("count_host", C.c_void_p),
     ]
 
 

@@ -23,12 +23,15 @@ int cuda_fail(cudaError_t e, const char* where) {
   return fail(YPB_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
 }
 
-// Diagnostic switch: YPB_FUSE_DECODE=1 decodes the survivors inside the class-scan kernel instead of the separate
-// GPU-wide decode_tiles_kernel.  Measured slower when batches are pipelined (CTAs holding survivors become the
-// kernel's tail: 53 us vs 39 + 17 us overlappable), so the split form is the default.
-bool split_decode_requested() {
-  static const bool v = [] { const char* e = std::getenv("YPB_FUSE_DECODE"); return !(e && e[0] == '1'); }();
-  return v;
+// Where the survivors' boxes are decoded: inside the class-scan kernel (one kernel boundary less: the latency form) or by the
+// separate GPU-wide decode_tiles_kernel (CTAs holding survivors do not become the scan kernel's tail: the throughput form,
+// 39 + 17 us overlappable vs 53 us at C2 B=64).  Auto: fused when the scan grid is at most two CTAs per SM - measured at
+// C2 B=8 36.8 vs 47.9 us per call, B=1 equal GPU time and 3-5 us less host time.  YPB_FUSE_DECODE=1 / 0 forces either form.
+bool split_decode_requested(const ypb::HeadGeom& g) {
+  static const int forced = [] { const char* e = std::getenv("YPB_FUSE_DECODE"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+  if (forced >= 0) return forced == 0;
+  const long long scan_ctas = static_cast<long long>((g.group_start[g.num_levels] + 127) / 128) * g.batch;
+  return scan_ctas > 2 * 148;
 }
 
 // ypb_nms_params.scan_kernel == YPB_SCAN_AUTO: the one-wave LDG class scan unless YPB_SCAN_TMA=1 asks for the persistent
@@ -128,7 +131,7 @@ ypb::SuppressArgs suppress_args(const ypb_nms_params* p, const ypb_nms_out* out,
   s.row_count = w.row_count; s.keys_a = w.keys_a; s.keys_b = w.keys_b; s.cand_box = w.cand_box;
   s.cand_ang = p->rule == YPB_NMS_FAST_PROBIOU ? w.cand_ang : nullptr;
   s.kept_box = w.kept_box; s.kept_area = w.kept_area; s.kept_key = w.kept_key; s.rec = w.rec;
-  s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_cand = out->cand_count;
+  s.out_rows = out->rows; s.out_idx = reinterpret_cast<long long*>(out->idx); s.out_count = out->count; s.out_count_host = out->count_host; s.out_cand = out->cand_count;
   s.scale_xforms = out->scale_xforms; s.scale_padding = out->scale_padding;
   s.num_peers = out->num_peers; s.my_rank = out->my_rank; s.peer_state = out->peer_state;
   s.peer_ack = out->peer_ack; s.peer_depth = out->peer_depth > 0 ? out->peer_depth : 1; s.peer_entry_stride = out->peer_entry_stride;
@@ -286,7 +289,7 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     }
     ypb::FilterArgs f{};
     f.tile_count = counters + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
-    f.fuse_decode = split_decode_requested() ? 0 : 1;
+    f.fuse_decode = split_decode_requested(g) ? 0 : 1;
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     // the persistent TMA-fed scan when asked for and the geometry fits it (16-byte vectorisable levels, nc <= 256), else the LDG kernel
@@ -302,7 +305,7 @@ static int nms_from_head_impl(const ypb_head_desc* head, const void* angle, int3
     f.conf = p->conf_thres; f.nc = p->nc; f.multi_label = p->multi_label; f.rotated = rotated; f.rows_cap = p->rows_cap;
     f.cls_bits = ypb::bits_for(p->nc); f.class_mask = p->class_mask; f.row_count = counters; f.keys = w.keys_a; f.cand_box = w.cand_box; f.cand_ang = w.cand_ang;
     f.tile_count = counters + head->batch; f.tile_list = w.tile_list; f.tile_flags = w.tile_flags; f.tile_cap = w.tile_cap;
-    f.fuse_decode = split_decode_requested() ? 0 : 1;
+    f.fuse_decode = split_decode_requested(g) ? 0 : 1;
     e = ypb::launch_filter_from_head(g, head->dtype, value_dtype, angle, angle_is_logit, f, vec, 2, st);
     if (e != cudaSuccess) return cuda_fail(e, "decode_candidates");
   }

@@ -450,6 +450,7 @@ struct SuppressArgs {
   float* out_rows;
   long long* out_idx;
   int32_t* out_count;
+  int32_t* out_count_host;  // optional second home of the counts in mapped pinned host memory (ypb_nms_out.count_host)
   int32_t* out_cand;
   int idx_as_row;  // ypb_nms_boxes: write the row id itself
   // riders of the fused path (ypb_riders_desc): per-anchor channels that follow the kept rows as extras

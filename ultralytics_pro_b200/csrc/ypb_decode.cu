@@ -351,14 +351,22 @@ decode_dense16_kernel(const __grid_constant__ HeadGeom g, const void* __restrict
   };
 
   P bufa[R], bufb[R];
-  load_batch(bufa, 0);
+#ifdef YPB_DD16_STAGGER
+  // odd warps walk the class batches first and the four sides last: the two phases differ in their special-function density
+  // (15 % vs 24 % of the instructions), and warps that start together would otherwise load the XU pipe in lockstep
+  const int shift = ((threadIdx.x >> 5) & 1) ? 4 : 0;
+  auto batch_of = [&](int k) { int kk = k + shift; return kk >= nb ? kk - nb : kk; };
+#else
+  auto batch_of = [&](int k) { return k; };
+#endif
+  load_batch(bufa, batch_of(0));
 #pragma unroll 1
   for (int k = 0; k < nb; k += 2) {
-    if (k + 1 < nb) load_batch(bufb, k + 1);
-    process(bufa, k);
+    if (k + 1 < nb) load_batch(bufb, batch_of(k + 1));
+    process(bufa, batch_of(k));
     if (k + 1 >= nb) break;
-    if (k + 2 < nb) load_batch(bufa, k + 2);
-    process(bufb, k + 1);
+    if (k + 2 < nb) load_batch(bufa, batch_of(k + 2));
+    process(bufb, batch_of(k + 1));
   }
   // class rows beyond the last whole batch (nc % 16)
   const int c0 = (nc / R) * R;

@@ -812,7 +812,10 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
   const int cbits = a.cls_bits;
   const uint32_t cmask = (1u << cbits) - 1u;
   const float4* cand_box = a.cand_box + static_cast<long long>(b) * a.anchors;
-  if (tid == 0) a.out_count[b] = kept_n;
+  if (tid == 0) {
+    a.out_count[b] = kept_n;
+    if (a.out_count_host) a.out_count_host[b] = kept_n;  // posted write over PCIe; host-visible once the stream is synchronised
+  }
   const int cols = 6 + a.extra;
   const float* cand_ang3 = a.cand_ang ? a.cand_ang + static_cast<long long>(b) * a.anchors : nullptr;
   for (int k = tid; k < kept_n; k += NT) {

@@ -107,6 +107,7 @@ class NmsPlan:
     peers: object = None         # dist.PeerGather when the kernel also stores the results into every peer's buffer
     scratch_bytes: int = 0
     counters: torch.Tensor = None  # int32[B + 1] clean-on-exit row / octet counters (ypb_nms_params.clean_counters)
+    count_host: torch.Tensor = None  # pinned int32[B]: the suppression kernel stores the counts here too (ypb_nms_out.count_host)
 
 
 _PLAN_CACHE_MAX = 32
@@ -125,10 +126,15 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
               max_nms: int, max_wh: float, multi_label: bool, rule: int, classes=None, with_scale: bool = False,
               scale_padding: bool = True, peer_gather_group=None, nms_box=None, boxes_xyxy: bool = False,
               pad_output: bool = False, conf_per_image: torch.Tensor | None = None, rows_cap: int | None = None,
-              cached: bool = False, scan_kernel: int = 0) -> NmsPlan:
+              cached: bool = False, scan_kernel: int = 0, host_counts: bool | None = None) -> NmsPlan:
     """cached=True: the plan (parameter structs, fixed-stride result buffers) is kept per (thread, stream, geometry,
     parameters) and REUSED by the next call with the same key - only for callers that copy the results out before
-    returning (``split_results`` packs them into fresh tensors); everything is stream-ordered, so reuse is safe."""
+    returning (``split_results`` packs them into fresh tensors); everything is stream-ordered, so reuse is safe.
+    host_counts (default: = cached): the plan owns a pinned host int32[B] that the suppression kernel writes the per-image
+    counts into directly (mapped memory), so reading them needs a stream synchronisation but no copy; only for plans that
+    persist - a pinned allocation per call would cost more than the copy it saves."""
+    if host_counts is None:
+        host_counts = cached
     key = None
     if cached and peer_gather_group is None and conf_per_image is None:
         ckey = None if classes is None else tuple(int(c) for c in (classes.tolist() if isinstance(classes, torch.Tensor) else classes))
@@ -146,7 +152,8 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         # inference_mode may still update them in place (set_transforms)
         with torch.inference_mode(False):
             plan = make_plan(device, batch, anchors, nc, extra, conf_t, iou_eff, max_det, max_nms, max_wh, multi_label, rule,
-                             classes, with_scale, scale_padding, None, nms_box, boxes_xyxy, pad_output, None, rows_cap, False, scan_kernel)
+                             classes, with_scale, scale_padding, None, nms_box, boxes_xyxy, pad_output, None, rows_cap, False, scan_kernel,
+                             host_counts)
         cache = _plan_cache()
         cache[key] = plan
         while len(cache) > _PLAN_CACHE_MAX:
@@ -200,6 +207,9 @@ def make_plan(device, batch: int, anchors: int, nc: int, extra: int, conf_t: flo
         peers.bind(o)
     plan = NmsPlan(p, o, rows, idx, count, cand, packed, scratch, (mask, conf_per_image, counters), xforms, peers)
     plan.counters = counters
+    if host_counts and batch > 0:
+        plan.count_host = torch.zeros((batch,), dtype=torch.int32).pin_memory()
+        o.count_host = plan.count_host.data_ptr()  # unified addressing: the pinned allocation is mapped at the same address
     plan.scratch_bytes = nbytes
     if key is not None:
         cache = _plan_cache()
@@ -253,11 +263,20 @@ def cut_results(out_rows: torch.Tensor, out_idx, counts: list, return_idxs: bool
     return out
 
 
+def plan_counts(plan: NmsPlan) -> list:
+    """Per-image kept counts of the plan's last call on the host: one stream synchronisation; no copy when the kernel wrote
+    them into the plan's mapped host buffer."""
+    if plan.count_host is None:
+        return fetch_counts(plan.count)
+    torch.cuda.current_stream(plan.count.device).synchronize()
+    return plan.count_host.tolist()
+
+
 def split_results(plan: NmsPlan, return_idxs: bool):
     if plan.rows.shape[0] == 0:
         return ([], []) if return_idxs else []
     out_rows, out_idx = compact_results(plan, return_idxs)
-    return cut_results(out_rows, out_idx, fetch_counts(plan.count), return_idxs)
+    return cut_results(out_rows, out_idx, plan_counts(plan), return_idxs)
 
 
 def _check_plan(rc: int, what: str, plan: NmsPlan) -> None:

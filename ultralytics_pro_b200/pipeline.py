@@ -32,9 +32,9 @@ class HeadPostProcessor:
         # multi-GPU: True / a process group = one-sided gather of every rank's results over NVLink peer memory
         # (dist.PeerGather); plans are then created collectively, in the same order on every rank
         self.peer_gather_group = peer_gather_group
-        # use_graph: __call__ replays ONE CUDA graph per distinct set of input tensors (kernels + result packing + the count
-        # copy to pinned memory): a serving loop with static input buffers pays one graph launch and one stream
-        # synchronisation per batch.  The returned views are then valid until the next call on the same inputs.
+        # use_graph: __call__ replays ONE CUDA graph per distinct set of input tensors (kernels + result packing; the counts
+        # land in mapped pinned memory straight from the suppression kernel): a serving loop with static input buffers pays
+        # one graph launch and one stream synchronisation per batch.  The returned views are then valid until the next call on the same inputs.
         self.use_graph = bool(use_graph)
         # class-scan kernel of the fused path: "ldg" (one-wave grid, co-resident with other streams' kernels: multi-stream
         # pipelines), "tma" (persistent TMA-fed ring: fastest single kernel, latency mode / 16-bit heads), "auto" = ldg
@@ -57,7 +57,8 @@ class HeadPostProcessor:
                 plan = engine.make_plan(lv0.device, lv0.shape[0], anchors, self.nc, 1 if self.rotated else 0, conf_t,
                                         iou_eff, self.max_det, self.max_nms, 0.0 if self.agnostic else float(self.max_wh),
                                         self.multi_label, rule, self.classes, with_scale=self.scale_to_original,
-                                        peer_gather_group=self.peer_gather_group, scan_kernel=self.scan_kernel)
+                                        peer_gather_group=self.peer_gather_group, scan_kernel=self.scan_kernel,
+                                        host_counts=True)
                 # a private scratch buffer: the plan outlives the call, the thread-local pool buffer may be regrown
                 nbytes = _cabi.load().ypb_nms_workspace_bytes(lv0.shape[0], anchors, plan.params.rows_cap,
                                                               plan.params.max_det, plan.params.max_nms, plan.params.rule)
@@ -133,21 +134,25 @@ class HeadPostProcessor:
         ent = self._graphs.get(key)
         if ent is None:
             plan = self.enqueue(levels, angle_logits)  # warm-up: plan, scratch and result buffers exist after this
-            with torch.inference_mode(False):
-                out_rows, out_idx = engine.compact_results(plan, True)
-                host = torch.empty((plan.count.numel(),), dtype=torch.int32).pin_memory()
-            host.copy_(plan.count, non_blocking=True)
+            single = plan.rows.shape[0] == 1  # one image: its kept rows already lie back to back - nothing to pack
+            out_rows = out_idx = None
+            if single:
+                out_rows, out_idx = plan.rows[0], plan.idx[0]
+            else:
+                with torch.inference_mode(False):
+                    out_rows, out_idx = engine.compact_results(plan, True)
             cur = torch.cuda.current_stream(dev)
             cur.synchronize()
             graph = torch.cuda.CUDAGraph()
             cap = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(dev)
             with torch.cuda.graph(graph, stream=cap):
                 self.enqueue(levels, angle_logits)
-                engine.compact_results(plan, True, out_rows, out_idx)
-                host.copy_(plan.count, non_blocking=True)
+                if not single:
+                    engine.compact_results(plan, True, out_rows, out_idx)
+                # no count copy: the suppression kernel writes the counts into the plan's mapped host buffer itself
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
-            ent = self._graphs[key] = (graph, plan, out_rows, out_idx, host, list(levels), angle_logits)
+            ent = self._graphs[key] = (graph, plan, out_rows, out_idx, plan.count_host, list(levels), angle_logits)
         graph, plan, out_rows, out_idx, host = ent[:5]
         graph.replay()
         torch.cuda.current_stream(dev).synchronize()
