@@ -238,13 +238,18 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
                 gb = torch.empty((1, world, pl.peers.slot), dtype=torch.float32, device=dev)  # the consumer's copy of the entry
             grp = lane_groups[ln] if lane_groups else None
 
+            beside_mode = gather_mode == "peer" and use_graph and lag == 1 and not os.environ.get("YPB_BENCH_TAIL_CONSUME")
+
+            def consume(pp=pp, pl=pl, gb=gb, want=(-1 if beside_mode else lag)):
+                pp.wait_gather(want)
+                if not os.environ.get("YPB_BENCH_NO_CONSUME"):
+                    # the consumer: one device-side gather of the returned ring entry (measured faster than the single-CTA
+                    # ypb_peer_wait_copy for this 0.9 MB entry: 46.0 vs 50.9 us per step at N=2)
+                    pl.peers.copy_entry(gb)
+
             def tail(pp=pp, pl=pl, gb=gb, host_counts=host_counts, grp=grp):
-                if gather_mode == "peer":
-                    pp.wait_gather(lag)
-                    if not os.environ.get("YPB_BENCH_NO_CONSUME"):
-                        # the consumer: one device-side gather of the returned ring entry (measured faster than the single-CTA
-                        # ypb_peer_wait_copy for this 0.9 MB entry: 46.0 vs 50.9 us per step at N=2)
-                        pl.peers.copy_entry(gb)
+                if gather_mode == "peer" and not beside_mode:
+                    consume()
                 elif gather_mode == "nccl":
                     ypb_dist.gather_packed(pl.packed, gb, group=grp)
                 if pl.count_host is None:
@@ -252,9 +257,11 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
 
             graphs = None
             if use_graph:
-                graphs = [pp.capture(lv, ang, after=tail) for lv, ang in my_sets]
+                # lag 1 + graphs: the consumer of batch q-1 (in-order wait + copy out of the ring) is a FORKED branch of step q's
+                # graph - it runs beside the class scan of step q instead of behind its suppression kernel
+                graphs = [pp.capture(lv, ang, after=tail, beside=consume if beside_mode else None) for lv, ang in my_sets]
         st.synchronize()
-        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": graphs, "plan": pl, "gather": gb, "tail": tail,
+        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": graphs, "plan": pl, "gather": gb, "tail": tail, "beside": beside_mode,
                       "group": grp, "host_counts": host_counts})
     return lanes
 
@@ -274,7 +281,45 @@ def _lane_step(lanes, i, gather_mode):
             ypb_dist.gather_packed(ln["plan"].packed, ln["gather"], group=ln["group"])
 
 
-def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None):
+class _DeviceBarrier:
+    """GPU-side barrier over NVLink peer memory (torch symmetric memory), enqueued on the current stream.  dist.barrier() lines the
+    HOSTS up to within tens of microseconds; a timed region of K = 20 steps lasts under a millisecond, so that skew between the
+    ranks' GPU timelines would be charged to whichever rank started first (its drain waits for the latecomer's last results).
+    This lines the GPUs themselves up before the first event is recorded.  Collective construction."""
+
+    def __init__(self, dev, world):
+        self.handle = None
+        if world <= 1 or os.environ.get("YPB_BENCH_NO_DEVICE_BARRIER"):
+            return
+        ok = 1
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+
+            self.buf = symm.empty(64, dtype=torch.float32, device=dev)
+            try:
+                self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+            except Exception:  # noqa: BLE001
+                symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+                self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+            self.handle.barrier(channel=0)
+            torch.cuda.synchronize(dev)
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"[bench] device-side barrier unavailable ({type(exc).__name__}: {exc})\n")
+            ok = 0
+        import torch.distributed as dist
+
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.handle = None
+
+    def __call__(self):
+        if self.handle is not None:
+            self.handle.barrier(channel=0)
+
+
+def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None, device_barrier=None):
     """W warm-up steps, then EXACTLY K timed steps between a barrier + synchronize on both sides; CUDA events on the stream the
     lanes fork from / join into; max over ranks.  Returns total ms."""
     import torch.distributed as dist
@@ -289,8 +334,10 @@ def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None):
         for ln in lanes:
             main.wait_stream(ln["stream"])
 
-    def drain():
+    def drain(final=True):
         if gather_mode == "peer" and lag > 0:  # every result of every rank has landed before the clock stops
+            if not final and lanes[0].get("beside"):
+                return  # in-order consumers: the warm-up leaves the steady state (one batch in flight per lane) in place
             for ln in lanes:
                 with torch.cuda.stream(ln["stream"]):
                     ln["post"].wait_gather(0)
@@ -298,7 +345,7 @@ def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None):
     fork()
     for i in range(W):
         _lane_step(lanes, i, gather_mode)
-    drain()
+    drain(final=False)
     join()
     torch.cuda.synchronize(dev)
     if sampler is not None:
@@ -307,6 +354,8 @@ def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    if device_barrier is not None:
+        device_barrier()  # the GPUs themselves leave this point together (see _DeviceBarrier)
     ev0.record()
     fork()
     for i in range(K):
@@ -549,7 +598,8 @@ def run_ours(args):
     # everything with a variable host cost (NVML init of the clock sampler, event creation) happens BEFORE the barrier inside
     # _time_lanes, so that the ranks enter the timed region together
     sampler = ClockSampler(local)
-    total_ms = _time_lanes(dev, lanes, K, W, world, gather_mode, args.gather_lag, sampler)
+    dev_barrier = _DeviceBarrier(dev, world)
+    total_ms = _time_lanes(dev, lanes, K, W, world, gather_mode, args.gather_lag, sampler, dev_barrier)
     sys.stderr.write(f"[bench] rank {rank}: {total_ms / K * 1e3:.2f} us/step, kept {int(plan.count.sum())} cand {int(plan.cand.sum())}\n")
     value = world * B * K / (total_ms * 1e-3)
     kept = plan.count.sum().item()
@@ -591,7 +641,7 @@ def run_ours(args):
         if (hi - lo) * world == B:  # equal shards: the peer ring needs the same packed size on every rank
             ssets = [([lv[lo:hi] for lv in s[0]], None) for s in sets]
             slanes = _build_lanes(dev, cfg, ssets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups)
-            sms = _time_lanes(dev, slanes, K, W, world, gather_mode, args.gather_lag)
+            sms = _time_lanes(dev, slanes, K, W, world, gather_mode, args.gather_lag, None, dev_barrier)
             strong = {"global_batch": B, "batch_per_gpu": hi - lo, "value": B * K / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / K,
                       "scaling": "strong", "note": "one 64-image batch per step split contiguously over the ranks; every rank ends "
                                                    "each step holding all 64 images' detections"}

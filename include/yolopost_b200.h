@@ -306,7 +306,10 @@ YPB_API int ypb_match_predictions(const float* preds, int64_t pred_image_stride,
  * number of this rank's own latest launch minus `lag` (state[1]; all ranks run the same launch sequence), i.e. until the
  * results of that launch of every rank have landed here, and (3) writes that entry's index (seq % depth) to *slot_index
  * (device int64, may be NULL) for the consumer's kernels.  lag > 0 is a pipelined gather: the step never stalls on a slower
- * rank; it needs depth >= lag + 2.  The entry stays valid until the NEXT ypb_peer_wait on this lane executes. */
+ * rank; it needs depth >= lag + 2.  lag < 0 = IN ORDER: the launch after the one handed out last (state[2] + 1), whatever this
+ * rank has launched since - the form for a consumer that runs CONCURRENTLY with the next step's kernels (a forked branch of
+ * the step's CUDA graph: the gather of step q-1 is then consumed beside, not behind, the kernels of step q).
+ * The entry stays valid until the NEXT ypb_peer_wait on this lane executes. */
 YPB_API int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth,
                           int32_t* const* peer_ack, int32_t my_rank, int64_t* slot_index, void* stream);
 

@@ -80,6 +80,42 @@ SCRIPT = textwrap.dedent('''
         rr, rc = ypb_dist.split_packed(out[:, : peers.numel].contiguous(), B, md, cols)
         gr, gc = pp.gathered()
         assert torch.equal(rc, gc) and int(gc.sum()) > 0, "wait_copy consumer"
+        # the consumer as a FORKED branch of the NEXT step's graph (in-order wait, lag -1): replay r consumes - beside its own
+        # kernels - the batch the previous launch produced; 9 launches > 3 ring entries, so entries are reused under acknowledgements
+        plain = HeadPostProcessor(cfg.nc, cfg.strides, 0.25, 0.7)
+        refs = []
+        for s_ in range(4):
+            q = plain.enqueue(sets[s_])
+            r_ = torch.empty((world, q.packed.numel()), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(r_, q.packed.clone())
+            refs.append(r_)
+        gb = torch.zeros((1, world, peers.slot), dtype=torch.float32, device=dev)
+        def consume():
+            pp.wait_gather(-1)
+            peers.copy_entry(gb)
+        pp.enqueue(sets[3])  # one batch in flight: the steady state of a lag-1 pipeline
+        snaps, expect = [], []
+        graphs = []
+        for i in (0, 1):
+            graphs.append(pp.capture(sets[i], beside=consume))  # eager warm-up inside: consumes the batch in flight, launches set i
+            snaps.append(gb.clone()); expect.append(3 if i == 0 else 0)
+        last = 1
+        for r_ in range(7):
+            graphs[r_ % 2].replay()
+            snaps.append(gb.clone()); expect.append(last)
+            last = r_ % 2
+        pp.wait_gather(0)
+        torch.cuda.synchronize(dev)
+        for k, (got, e_) in enumerate(zip(snaps, expect)):
+            rr, rc = ypb_dist.split_packed(refs[e_], B, md, cols)
+            gr, gc = ypb_dist.split_packed(got[0][:, : peers.numel].contiguous(), B, md, cols)
+            valid = (torch.arange(md, device=dev)[None, :] < rc[:, None]).unsqueeze(-1)
+            assert torch.equal(rc, gc), ("forked consumer", k, e_, rc.tolist(), gc.tolist())
+            assert torch.equal(rr * valid, gr * valid), ("forked consumer", k)
+        rr, rc = ypb_dist.split_packed(refs[last], B, md, cols)
+        gr, gc = pp.gathered()
+        assert torch.equal(rc, gc) and int(gc.sum()) > 0, "forked consumer drain"
+        assert peers.overrun() == 0, peers.overrun()
     print("ok", rank, flush=True)
     dist.barrier(); torch.cuda.synchronize(dev); os._exit(0)
 ''')

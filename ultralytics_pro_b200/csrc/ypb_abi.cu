@@ -559,8 +559,9 @@ int ypb_match_predictions(const float* preds, int64_t pred_image_stride, int64_t
 
 int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth, int32_t* const* peer_ack,
                   int32_t my_rank, int64_t* slot_index, void* stream) {
-  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
-  if (depth < 1 || (peer_ack && depth < lag + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, lag + 2);
+  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < -1) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
+  // in-order consumption (lag -1) beside the next step behaves like lag 1: the entry being read and the one being filled differ
+  if (depth < 1 || (peer_ack && depth < (lag < 0 ? 1 : lag) + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, (lag < 0 ? 1 : lag) + 2);
   if (my_rank < 0 || my_rank >= world) return fail(YPB_ERR_INVALID_ARGUMENT, "my_rank=%d outside [0,%d)", my_rank, world);
   if (peer_ack)
     for (int i = 0; i < world; ++i)
@@ -573,8 +574,9 @@ int ypb_peer_wait(const int32_t* flags, int32_t world, int32_t* state, int32_t l
 
 int ypb_peer_wait_copy(const int32_t* flags, int32_t world, int32_t* state, int32_t lag, int32_t depth, int32_t* const* peer_ack,
                        int32_t my_rank, int64_t* slot_index, const float* ring, int64_t entry_floats, float* out, void* stream) {
-  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
-  if (depth < 1 || (peer_ack && depth < lag + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, lag + 2);
+  if (!flags || !state || world < 1 || world > YPB_MAX_PEERS || lag < -1) return fail(YPB_ERR_INVALID_ARGUMENT, "flags / state NULL, world=%d or lag=%d invalid", world, lag);
+  // in-order consumption (lag -1) beside the next step behaves like lag 1: the entry being read and the one being filled differ
+  if (depth < 1 || (peer_ack && depth < (lag < 0 ? 1 : lag) + 2)) return fail(YPB_ERR_INVALID_ARGUMENT, "depth=%d: an acknowledged ring needs depth >= lag + 2 = %d", depth, (lag < 0 ? 1 : lag) + 2);
   if (my_rank < 0 || my_rank >= world) return fail(YPB_ERR_INVALID_ARGUMENT, "my_rank=%d outside [0,%d)", my_rank, world);
   if (!ring || !out || entry_floats < 4 || entry_floats % 4 || !aligned(ring, 16) || !aligned(out, 16))
     return fail(YPB_ERR_INVALID_ARGUMENT, "ring / out NULL or not 16-byte aligned, or entry_floats=%lld not a positive multiple of 4", (long long)entry_floats);

@@ -1407,7 +1407,7 @@ __global__ void __launch_bounds__(NT, 1) fast_nms_cluster_kernel(const __grid_co
 struct PeerAckPtrs { int32_t* p[YPB_MAX_PEERS]; };
 __global__ void peer_wait_kernel_byval(const int32_t* flags, int world, int32_t* state, int lag, int depth, PeerAckPtrs acks,
                                        int has_ack, int my_rank, long long* slot_index) {
-  const int want = state[1] - lag;
+  const int want = lag < 0 ? state[2] + 1 : state[1] - lag;  // lag < 0: the batch after the one handed out last (in order)
   const int done = state[2];
   if (has_ack && threadIdx.x < world) *reinterpret_cast<volatile int32_t*>(acks.p[threadIdx.x] + my_rank) = done;
   if (threadIdx.x == 0) {
@@ -1434,7 +1434,7 @@ peer_wait_copy_kernel(const int32_t* flags, int world, int32_t* state, int lag, 
                       int my_rank, long long* slot_index, const float* ring, long long entry_floats, float* out) {
   __shared__ int s_slot;
   if (threadIdx.x < 32) {
-    const int want = state[1] - lag;
+    const int want = lag < 0 ? state[2] + 1 : state[1] - lag;  // lag < 0: the batch after the one handed out last (in order)
     const int done = state[2];
     if (has_ack && threadIdx.x < world) *reinterpret_cast<volatile int32_t*>(acks.p[threadIdx.x] + my_rank) = done;
     if (threadIdx.x == 0) {

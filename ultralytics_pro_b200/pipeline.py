@@ -92,9 +92,14 @@ class HeadPostProcessor:
         self.last = plan
         return plan
 
-    def capture(self, levels, angle_logits=None, after=None) -> "torch.cuda.CUDAGraph":
+    def capture(self, levels, angle_logits=None, after=None, beside=None) -> "torch.cuda.CUDAGraph":
         """Capture one batch's launches into a CUDA graph bound to these input tensors (static addresses).
-        `after()` (optional) is captured behind the kernels, e.g. the NCCL gather of the result buffer."""
+        `after()` (optional) is captured behind the kernels, e.g. the NCCL gather of the result buffer.
+        `beside()` (optional) is captured on a FORKED branch that runs concurrently with the kernels and joins at the end of
+        the graph - e.g. the consumer of the PREVIOUS batch's one-sided gather (``wait_gather(-1)`` + its reads), which then
+        costs the step no latency at all."""
+        if beside is not None:
+            beside()  # eagerly too: the warm-up launch below must find the sequence the replays will continue
         self.enqueue(levels, angle_logits)  # warm: attributes set, plan built, scratch allocated
         if after is not None:
             after()
@@ -104,15 +109,23 @@ class HeadPostProcessor:
         graph = torch.cuda.CUDAGraph()
         # capture needs a non-default stream; keep the caller's stream when it already is one
         cap = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(dev)
+        side = torch.cuda.Stream(dev) if beside is not None else None
         with torch.cuda.graph(graph, stream=cap):
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    beside()
             self.enqueue(levels, angle_logits)
             if after is not None:
                 after()
+            if side is not None:
+                torch.cuda.current_stream(dev).wait_stream(side)
         return graph
 
     def wait_gather(self, lag: int = 0):
         """Enqueue the consumer-side wait of the one-sided gather (graph-capturable): lag=0 for the last enqueued batch,
-        lag=k for the batch k enqueues back on this processor (pipelined: never stalls on a slower rank)."""
+        lag=k for the batch k enqueues back on this processor (pipelined: never stalls on a slower rank), lag=-1 for the batch
+        after the one handed out last (in order - for a consumer running beside the next batch's kernels, ``capture(beside=)``)."""
         if self.last is None or self.last.peers is None:
             raise RuntimeError("no peer gather attached to the last plan")
         self.last.peers.wait(lag)
