@@ -280,9 +280,10 @@ YPB_API int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs,
                              float ratio_w, float ratio_h, uint8_t* out, void* workspace, size_t workspace_bytes,
                              void* stream);
 /* workspace (optional): ypb_process_mask_workspace_bytes(total, out_h, out_w) bytes of device scratch.  With it the call
- * takes its two-step form - cudaMemset of the result, a work list of the (detection, 128x128 tile) pairs that can see their
- * box, and a kernel that computes only those (typically ~15 % of the tiles); without it (NULL) one kernel zero-fills and
- * computes every tile. */
+ * builds a work list of the (detection, 128x128 tile) pairs that can see their box (typically ~15 % of the tiles) and one kernel
+ * computes only those while an extra warp of every CTA zero-fills all other tiles with streaming stores - the write of the
+ * (total, out_h, out_w) result overlaps the arithmetic (out_w % 16 == 0; otherwise: cudaMemset of the result, then the listed
+ * tiles); without it (NULL) one kernel zero-fills and computes every tile. */
 YPB_API size_t ypb_process_mask_workspace_bytes(int32_t total, int32_t out_h, int32_t out_w);
 
 /* Validator matching: engine/validator.py:267-307 match_predictions (non-scipy branch) with, optionally, the pairwise

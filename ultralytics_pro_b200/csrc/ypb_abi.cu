@@ -485,7 +485,9 @@ int ypb_scale_rows(float* rows, int64_t image_stride, int64_t row_stride, int32_
 size_t ypb_process_mask_workspace_bytes(int32_t total, int32_t out_h, int32_t out_w) {
   if (total <= 0 || out_h <= 0 || out_w <= 0) return 0;
   const long long tiles = static_cast<long long>((out_w + 127) / 128) * ((out_h + 127) / 128) * total;
-  return static_cast<size_t>(tiles + 1) * sizeof(int32_t);
+  // the work list (count + (tile, image) per tile), 16-byte rounded, then the fill cursor and one "can see its box" flag byte per
+  // tile (overlapped form)
+  return ((static_cast<size_t>(2 * tiles + 1) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)) + 16 + static_cast<size_t>(tiles);
 }
 
 int ypb_process_mask(const ypb_protos_desc* protos, const float* coeffs, int64_t coef_image_stride, int64_t coef_row_stride,

@@ -521,6 +521,7 @@ struct MaskArgs {  // ypb_process_mask
   float scale_h, scale_w, ratio_w, ratio_h;
   int crop_mode;
   uint8_t* out;
+  int reg_cap, h_cap;  // set by the launcher: floats reserved for the footprint; rows of the pre-interpolated table (0 = off)
 };
 cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

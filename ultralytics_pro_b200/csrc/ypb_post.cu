@@ -7,6 +7,8 @@
 // image, with the reference's rounding (every step a separately rounded fp32 operation, true IEEE division).
 #include "ypb_common.cuh"
 
+#include <cstdlib>
+
 namespace ypb {
 
 namespace {
@@ -140,31 +142,46 @@ __device__ __forceinline__ bool mask_tile_empty(const MaskArgs& a, int b, int k,
 }
 
 // Work list of the two-step form: one thread per (detection, tile); tiles that can see their box are appended (unordered) to
-// list[1..], list[0] = their number.  Everything else of the (total, H, W) result is zero: a plain memset writes it at the
+// list[1..] as (tile id, image) pairs, list[0] = their number.  Everything else of the (total, H, W) result is zero: a plain memset writes it at the
 // write-only ceiling of the memory system and no CTA is spent on it.
 __global__ void __launch_bounds__(256)
-mask_tile_list_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, int32_t* __restrict__ list) {
+mask_tile_list_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, int32_t* __restrict__ list,
+                      uint8_t* __restrict__ tile_live) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per = tiles_x * tiles_y;
   bool live = false;
-  if (t < static_cast<long long>(a.total) * per) {
+  int live_b = 0;
+  const bool in_range = t < static_cast<long long>(a.total) * per;
+  if (in_range) {
     const int d = static_cast<int>(t / per), r = static_cast<int>(t - static_cast<long long>(d) * per);
     const int ty = r / tiles_x, tx = r - ty * tiles_x;
     int b, k;
     mask_locate(a, d, b, k);
     const int X0 = tx * MT_W, Y0 = ty * MT_H;
     live = !mask_tile_empty(a, b, k, X0, Y0, min(X0 + MT_W, a.iw) - 1, min(Y0 + MT_H, a.ih) - 1);
+    live_b = b;
   }
+  if (tile_live && in_range) tile_live[t] = live ? 1 : 0;  // the overlapped form's fill warps skip the listed tiles
+  if (tile_live && t == 0) *reinterpret_cast<int32_t*>(tile_live - 16) = 0;  // cursor of the fill chunks, 16 bytes in front of the flags
   const unsigned m = __ballot_sync(0xffffffffu, live);
   const int lane = threadIdx.x & 31;
   int base = 0;
   if (lane == 0 && m) base = atomicAdd(&list[0], __popc(m));
   base = __shfl_sync(0xffffffffu, base, 0);
-  if (live) list[1 + base + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(t);
+  if (live) {  // entry = (tile id, image): the tile kernel then needs no search through the offsets
+    const int e = base + __popc(m & ((1u << lane) - 1u));
+    list[1 + 2 * e] = static_cast<int32_t>(t);
+    list[2 + 2 * e] = live_b;
+  }
 }
 
+// barrier of the MT_THREADS tile-computing threads only (named barrier 1): the overlapped form runs one more warp per CTA
+// that never joins them
+__device__ __forceinline__ void mt_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MT_THREADS) : "memory"); }
+
 template <int DT>
-__device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s_img, int d, int X0, int Y0, bool fill_empty) {
+__device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s_img, int d, int X0, int Y0, bool fill_empty,
+                                          int b_known = -1) {
   using T = typename DType<DT>::type;
   float* coef = sm_f;                 // [C]
   float4* xtap = reinterpret_cast<float4*>(sm_f + ((a.C + 3) & ~3));  // [MT_W] (x0, x1 as int bits, w0, w1) of every tile column
@@ -175,13 +192,15 @@ __device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s
 
   // detection -> (image, row)
   int b = 0, k = d;
-  if (a.offsets) {
+  if (a.offsets && b_known >= 0) {
+    b = b_known; k = d - a.offsets[b];
+  } else if (a.offsets) {
     if (tid == 0) {
       int lo = 0, hi = a.batch;  // offsets[lo] <= d < offsets[hi]
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.offsets[mid] <= d) lo = mid; else hi = mid; }
       s_img[0] = lo; s_img[1] = d - a.offsets[lo];
     }
-    __syncthreads();
+    mt_sync();
     b = s_img[0]; k = s_img[1];
   }
   const float* bp = a.boxes + static_cast<long long>(b) * a.box_image_stride + static_cast<long long>(k) * a.box_row_stride;
@@ -224,20 +243,42 @@ __device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s
       bilinear_tap(a.scale_h, min(Y0 + tid - MT_W, a.ih - 1), a.win_h, i0, i1, w0, w1);
       ytap[tid - MT_W] = make_float4(__int_as_float(i0), __int_as_float(i1), w0, w1);
     }
-    __syncthreads();
+    mt_sync();
     const T* pr = static_cast<const T*>(a.protos) + static_cast<long long>(b) * a.proto_sb;
-    for (int i = tid; i < rh * rw; i += MT_THREADS) {
-      const int y = i / rw, x = i - y * rw;
-      const int py = ry0 + y + a.win_top, px = rx0 + x + a.win_left;
-      if (a.crop_mode == YPB_MASK_CROP_PROTO) {
-        // ops.py:486 masks * bool: outside the box the product is zero whatever the mask value - skip the dot product
-        const float fx = static_cast<float>(px), fy = static_cast<float>(py);
-        if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) { reg[i] = 0.f; continue; }
+    // the part of the footprint whose values are needed: all of it, or (PROTO crop, ops.py:486 masks * bool: outside the box
+    // the product is zero whatever the mask value) its intersection with the box; the rest is zero.  The needed pixels are
+    // dealt evenly over the threads, and all channel loads of a pixel are in flight together (32 when C is a multiple of 32):
+    // this phase is bound by the latency of its L2 loads, i.e. by round trips per thread.
+    int fx0 = 0, fy0 = 0, fw = rw, fh = rh;
+    if (a.crop_mode == YPB_MASK_CROP_PROTO) {
+      // pixel (px, py) is inside iff bx1 <= px < bx2 and by1 <= py < by2 (floats compared with integers-as-floats)
+      // (bounds clamped before the conversion: infinities must not overflow the integer arithmetic; a NaN bound yields an
+      // empty range, as every comparison with it is false)
+      auto icl = [](float v) { return static_cast<int>(ceilf(fminf(fmaxf(v, -1.0e6f), 1.0e6f))); };
+      const bool box_ok = bx1 == bx1 && bx2 == bx2 && by1 == by1 && by2 == by2;
+      int lx = icl(bx1) - (rx0 + a.win_left), hx = box_ok ? icl(bx2) - (rx0 + a.win_left) : lx;  // [lx, hx)
+      int ly = icl(by1) - (ry0 + a.win_top), hy = box_ok ? icl(by2) - (ry0 + a.win_top) : ly;
+      lx = max(lx, 0); ly = max(ly, 0); hx = min(hx, rw); hy = min(hy, rh);
+      fx0 = lx; fy0 = ly; fw = max(hx - lx, 0); fh = max(hy - ly, 0);
+      for (int i = tid; i < rh * rw; i += MT_THREADS) {
+        const int y = i / rw, x = i - y * rw;
+        if (x < fx0 || x >= fx0 + fw || y < fy0 || y >= fy0 + fh) reg[i] = 0.f;
       }
+    }
+    for (int i = tid; i < fw * fh; i += MT_THREADS) {
+      const int yy = i / fw, y = fy0 + yy, x = fx0 + (i - yy * fw);
+      const int py = ry0 + y + a.win_top, px = rx0 + x + a.win_left;
       const T* p = pr + static_cast<long long>(py) * a.mw + px;
       float acc = 0.f;
       int c = 0;
-      for (; c + 16 <= a.C; c += 16) {  // 16 independent loads in flight, then the sum in channel order
+      for (; c + 32 <= a.C; c += 32) {  // 32 independent loads in flight, then the sum in channel order
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = DType<DT>::to_f(p[static_cast<long long>(c + j) * a.proto_sc]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(coef[c + j], v[j], acc);
+      }
+      for (; c + 16 <= a.C; c += 16) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = DType<DT>::to_f(p[static_cast<long long>(c + j) * a.proto_sc]);
@@ -245,9 +286,26 @@ __device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s
         for (int j = 0; j < 16; ++j) acc = fmaf(coef[c + j], v[j], acc);
       }
       for (; c < a.C; ++c) acc = fmaf(coef[c], DType<DT>::to_f(p[static_cast<long long>(c) * a.proto_sc]), acc);
-      reg[i] = acc;
+      reg[y * rw + x] = acc;
     }
-    __syncthreads();
+    mt_sync();
+    if (a.h_cap > 0) {
+      // horizontally interpolated footprint rows: H[y][c] = w0(c) * reg[y][x0(c)] + w1(c) * reg[y][x1(c)] - the inner sums of
+      // ATen's h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), which depend on (footprint row, output column) only.
+      // Every footprint row serves 1/scale output rows as their upper and as their lower row: computing the sums once per
+      // (row, column) instead of once per output pixel leaves 2 loads + 3 operations per pixel (the same operations on
+      // the same operands in the same order: bit-identical).
+      // (restricting the table to the rows / segments that can see the box was measured: no gain on the C2-like workload, 11 %
+      // slower for whole-image boxes - the test costs what it saves)
+      float* H = reg + a.reg_cap;
+      for (int i = tid; i < rh * MT_W; i += MT_THREADS) {
+        const int y = i / MT_W, c = i - y * MT_W;
+        const float4 tx = xtap[c];
+        const float* r = reg + y * rw - rx0;
+        H[i] = __fadd_rn(__fmul_rn(tx.z, r[__float_as_int(tx.x)]), __fmul_rn(tx.w, r[__float_as_int(tx.y)]));
+      }
+      mt_sync();
+    }
   }
 
   if (XS > X1) return;
@@ -272,7 +330,33 @@ __device__ __forceinline__ void mask_tile(const MaskArgs& a, float* sm_f, int* s
       else
         live = static_cast<float>(Y) >= by1 && static_cast<float>(Y) < by2;
     }
-    if (live) {
+    if (live && a.h_cap > 0) {
+      const float wy0 = ty.z, wy1 = ty.w;
+      const float4* h0 = reinterpret_cast<const float4*>(reg + a.reg_cap + (__float_as_int(ty.x) - ry0) * MT_W + seg * 16);
+      const float4* h1 = reinterpret_cast<const float4*>(reg + a.reg_cap + (__float_as_int(ty.y) - ry0) * MT_W + seg * 16);
+      // the 8 threads of a row read 64-byte apart: thread `seg` starts at 16-byte chunk (seg / 2) of its segment and wraps, so
+      // that a quarter-warp's 128-bit loads cover all 32 banks
+#pragma unroll
+      for (int q0 = 0; q0 < 4; ++q0) {
+        const int q = (q0 + (seg >> 1)) & 3;
+        const float4 t4 = h0[q], b4 = h1[q];
+        const float tv[4] = {t4.x, t4.y, t4.z, t4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int X = XS + 4 * q + e;
+          float v = __fadd_rn(__fmul_rn(wy0, tv[e]), __fmul_rn(wy1, bv[e]));
+          if (a.crop_mode == YPB_MASK_CROP_OUTPUT) {
+            const bool in = static_cast<float>(X) >= bx1 && static_cast<float>(X) < bx2;
+            v = __fmul_rn(v, in ? 1.f : 0.f);
+          }
+          if (v > 0.f && X <= X1) bits |= 1u << (8 * e);  // ops.py:513 masks.gt_(0.0).byte()
+        }
+#pragma unroll
+        for (int z = 0; z < 4; ++z)
+          if (z == q) w4[z] = bits;
+      }
+    } else if (live) {
       const float wy0 = ty.z, wy1 = ty.w;
       const float* r0 = reg + (__float_as_int(ty.x) - ry0) * rw - rx0;
       const float* r1 = reg + (__float_as_int(ty.y) - ry0) * rw - rx0;
@@ -315,7 +399,7 @@ template <int DT>
 __global__ void __launch_bounds__(MT_THREADS, 3)
 process_mask_kernel(const __grid_constant__ MaskArgs a) {
   extern __shared__ __align__(16) float sm_f[];
-  __shared__ int s_img[2];
+  __shared__ int s_img[4];
   mask_tile<DT>(a, sm_f, s_img, blockIdx.z, blockIdx.x * MT_W, blockIdx.y * MT_H, true);
 }
 
@@ -324,15 +408,75 @@ template <int DT>
 __global__ void __launch_bounds__(MT_THREADS, 3)
 process_mask_list_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, const int32_t* __restrict__ list) {
   extern __shared__ __align__(16) float sm_f[];
-  __shared__ int s_img[2];
+  __shared__ int s_img[4];
   const int n = list[0], per = tiles_x * tiles_y;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
-    const int t = list[1 + e];
+    const int t = list[1 + 2 * e], tb = list[2 + 2 * e];
     const int d = t / per, r = t - d * per;
     const int ty = r / tiles_x, tx = r - ty * tiles_x;
-    mask_tile<DT>(a, sm_f, s_img, d, tx * MT_W, ty * MT_H, false);
-    __syncthreads();  // shared memory is reused by the next tile
+    mask_tile<DT>(a, sm_f, s_img, d, tx * MT_W, ty * MT_H, false, tb);
+    mt_sync();  // shared memory is reused by the next tile
   }
+}
+
+// Overlapped form: the zero fill and the tile computation in ONE kernel, on different warps.  Every CTA carries one extra
+// warp (threads MT_THREADS..MT_THREADS+31) that zero-fills the tiles that cannot see their box with 128-bit streaming stores - a
+// posted-store stream that needs next to no issue slots - while the MT_THREADS other threads work through the list of tiles
+// that can (prototype dot products from L2, bilinear taps: bound by instruction issue, L2 latency and shared memory).  The two
+// halves of the two-step form (memset at the write ceiling, then compute) ran one after the other; here the write stream hides
+// under the arithmetic.  The fill is handed out DYNAMICALLY in chunks of 32 consecutive tiles (one atomicAdd, one coalesced
+// read of 32 flag bytes per chunk), so a fill warp whose SM is busy computing simply takes fewer chunks.
+// Needs out_w % 16 == 0 (vector stores); else the two-step form.
+__device__ __forceinline__ void mask_fill_chunks(const MaskArgs& a, int tiles_x, int per, long long ntiles,
+                                                 const uint8_t* __restrict__ tile_live, int32_t* cursor, int lane) {
+  const int rsub = lane >> 3, seg = lane & 7;  // 4 rows x 8 segments of 16 bytes per store instruction
+  for (;;) {
+    int c0 = 0;
+    if (lane == 0) c0 = atomicAdd(cursor, 32);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    if (c0 >= ntiles) break;
+    const long long mine = static_cast<long long>(c0) + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, mine < ntiles && tile_live[mine] == 0);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long t = static_cast<long long>(c0) + j;
+      const int d = static_cast<int>(t / per), r = static_cast<int>(t - static_cast<long long>(d) * per);
+      const int ty = r / tiles_x, tx = r - ty * tiles_x;
+      const int X0 = tx * MT_W, Y0 = ty * MT_H;
+      const int rows = min(MT_H, a.ih - Y0), cols = min(MT_W, a.iw - X0);
+      if (seg * 16 >= cols) continue;  // out_w % 16 == 0: a segment is inside or outside as a whole
+      uint8_t* o = a.out + (static_cast<long long>(d) * a.ih + Y0 + rsub) * a.iw + X0 + seg * 16;
+      const long long step = 4ll * a.iw;
+      for (int y = rsub; y < rows; y += 4, o += step) __stcs(reinterpret_cast<uint4*>(o), make_uint4(0u, 0u, 0u, 0u));
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(MT_THREADS + 32, 3)
+process_mask_overlap_kernel(const __grid_constant__ MaskArgs a, int tiles_x, int tiles_y, const int32_t* __restrict__ list,
+                            const uint8_t* __restrict__ tile_live, int dbg) {
+  extern __shared__ __align__(16) float sm_f[];
+  __shared__ int s_img[4];
+  const int per = tiles_x * tiles_y;
+  const long long ntiles = static_cast<long long>(a.total) * per;
+  int32_t* cursor = reinterpret_cast<int32_t*>(const_cast<uint8_t*>(tile_live) - 16);
+  if (threadIdx.x >= MT_THREADS) {
+    if (dbg != 1) mask_fill_chunks(a, tiles_x, per, ntiles, tile_live, cursor, threadIdx.x - MT_THREADS);
+    return;
+  }
+  if (dbg == 2) return;
+  const int n = list[0];
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int t = list[1 + 2 * e], tb = list[2 + 2 * e];
+    const int d = t / per, r = t - d * per;
+    const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    mask_tile<DT>(a, sm_f, s_img, d, tx * MT_W, ty * MT_H, false, tb);
+    mt_sync();  // shared memory is reused by the next tile
+  }
+  // (letting the computing warps join the fill once their tiles are done was measured: equal on the C2-like workload, SLOWER
+  // when nothing is visible - 0.23 vs 0.16 ms: 27 instead of 3 store streams per SM scatter the DRAM writes)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -410,6 +554,8 @@ cudaError_t launch_match_predictions(const MatchArgs& a, int max_labels, cudaStr
   return cudaGetLastError();
 }
 
+static cudaError_t launch_process_mask_sized(const MaskArgs& a, size_t smem, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (a.total <= 0 || a.ih <= 0 || a.iw <= 0) return cudaSuccess;
   // worst-case footprint of a tile in the prototype grid
@@ -419,26 +565,51 @@ cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t works
     return static_cast<int>(s < in ? s : in);
   };
   const int rh = span(a.scale_h, a.ih, MT_H, a.win_h), rw = span(a.scale_w, a.iw, MT_W, a.win_w);
-  const size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float) + (MT_W + MT_H) * sizeof(float4);
+  size_t smem = (static_cast<size_t>((a.C + 3) & ~3) + static_cast<size_t>(rh) * rw) * sizeof(float) + (MT_W + MT_H) * sizeof(float4);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  // room for the horizontally interpolated rows (rh x MT_W floats) while three CTAs still fit an SM?  (always, for upsampling by
+  // >= 2; a near-1:1 resize keeps the per-pixel form)
+  MaskArgs a2 = a;
+  a2.reg_cap = (rh * rw + 3) & ~3;
+  a2.h_cap = 0;
+  {
+    const size_t with_h = (static_cast<size_t>((a.C + 3) & ~3) + a2.reg_cap + static_cast<size_t>(rh) * MT_W) * sizeof(float) + (MT_W + MT_H) * sizeof(float4);
+    static const bool no_h = [] { const char* e = std::getenv("YPB_MASK_NO_HROWS"); return e && e[0] == '1'; }();
+    if (with_h <= 72 * 1024 && !no_h) { a2.h_cap = rh; smem = with_h; }
+  }
+  return launch_process_mask_sized(a2, smem, workspace, workspace_bytes, st);
+}
+
+static cudaError_t launch_process_mask_sized(const MaskArgs& a, size_t smem, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const int tiles_x = (a.iw + MT_W - 1) / MT_W, tiles_y = (a.ih + MT_H - 1) / MT_H;
   const long long ntiles = static_cast<long long>(a.total) * tiles_x * tiles_y;
   // two-step form when the caller lends a work list: memset the result (the zeros of every tile that cannot see its box are
-  // written at the write-only ceiling, no CTA spent on them), list the tiles that can, compute only those
-  const bool two_step = workspace && workspace_bytes >= (static_cast<size_t>(ntiles) + 1) * sizeof(int32_t) && ntiles < (1ll << 31);
+  // written at the write-only ceiling, no CTA spent on them), list the tiles that can, compute only those.
+  // Overlapped form when the workspace also holds one flag byte per tile and rows are 16-byte multiples: no memset - an
+  // extra warp per CTA writes the zeros of the unlisted tiles WHILE the others compute the listed ones (YPB_MASK_TWO_STEP=1 keeps
+  // the two-step form for comparison).
+  const bool two_step = workspace && workspace_bytes >= (2 * static_cast<size_t>(ntiles) + 1) * sizeof(int32_t) && ntiles < (1ll << 30);
+  static const bool force_two_step = [] { const char* e = std::getenv("YPB_MASK_TWO_STEP"); return e && e[0] == '1'; }();
+  const size_t list_bytes = ((2 * static_cast<size_t>(ntiles) + 1) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15);
+  const bool overlap = two_step && !force_two_step && workspace_bytes >= list_bytes + 16 + static_cast<size_t>(ntiles) && (a.iw & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
   dim3 grid(tiles_x, tiles_y, a.total);
   if (!two_step && (grid.z > 65535u || grid.y > 65535u)) return cudaErrorInvalidConfiguration;
   int32_t* list = static_cast<int32_t*>(workspace);
+  uint8_t* tile_live = overlap ? static_cast<uint8_t*>(workspace) + list_bytes + 16 : nullptr;  // 16 bytes in front: the fill cursor
   if (two_step) {
-    cudaError_t e = cudaMemsetAsync(a.out, 0, static_cast<size_t>(a.total) * a.ih * a.iw, st);
+    cudaError_t e = cudaSuccess;
+    if (!overlap) e = cudaMemsetAsync(a.out, 0, static_cast<size_t>(a.total) * a.ih * a.iw, st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(list, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
-    mask_tile_list_kernel<<<static_cast<unsigned>((ntiles + 255) / 256), 256, 0, st>>>(a, tiles_x, tiles_y, list);
+    mask_tile_list_kernel<<<static_cast<unsigned>((ntiles + 255) / 256), 256, 0, st>>>(a, tiles_x, tiles_y, list, tile_live);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   const unsigned list_grid = static_cast<unsigned>(ntiles < 148 * 6 ? ntiles : 148 * 6);
+  static const int mask_dbg = [] { const char* e = std::getenv("YPB_MASK_DBG"); return e ? std::atoi(e) : 0; }();  // timing diagnostics only
+  const unsigned overlap_grid = static_cast<unsigned>(ntiles < 148 * 3 ? ntiles : 148 * 3);  // all CTAs resident: fill warps on every SM from the start
 #define YPB_PM(DT)                                                                                                  \
   do {                                                                                                              \
     if (smem > 48 * 1024) {                                                                                         \
@@ -446,8 +617,11 @@ cudaError_t launch_process_mask(const MaskArgs& a, void* workspace, size_t works
       if (e != cudaSuccess) return e;                                                                               \
       e = cudaFuncSetAttribute(process_mask_list_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return e;                                                                               \
+      e = cudaFuncSetAttribute(process_mask_overlap_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                               \
     }                                                                                                               \
-    if (two_step) process_mask_list_kernel<DT><<<list_grid, MT_THREADS, smem, st>>>(a, tiles_x, tiles_y, list);     \
+    if (overlap) process_mask_overlap_kernel<DT><<<overlap_grid, MT_THREADS + 32, smem, st>>>(a, tiles_x, tiles_y, list, tile_live, mask_dbg); \
+    else if (two_step) process_mask_list_kernel<DT><<<list_grid, MT_THREADS, smem, st>>>(a, tiles_x, tiles_y, list); \
     else process_mask_kernel<DT><<<grid, MT_THREADS, smem, st>>>(a);                                                \
   } while (0)
   if (a.proto_dtype == YPB_F32) YPB_PM(YPB_F32);
