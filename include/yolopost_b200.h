@@ -82,6 +82,12 @@ typedef struct {
   int32_t channels; /* 4 + nc + extra */
   int32_t anchors;
   int64_t stride_b, stride_c, stride_a; /* elements */
+  /* anchor_subset: NULL, or device (B, subset_len) int64 anchor indices in [0, anchors): ONLY these anchors are candidates (the
+   * second stage of the end2end top-k, head.py:209-211, ranks the pairs of the K anchors kept by the first stage - read where
+   * they lie, no gathered copy).  Row ids, kept indices and the tie order stay those of the full tensor. */
+  const int64_t* anchor_subset;
+  int32_t subset_len;
+  int32_t reserved;
 } ypb_dense_desc;
 
 /* Arguments of non_max_suppression (nms.py:13-29) that reach the device. */
@@ -101,7 +107,8 @@ typedef struct {
    *   nms_box_divisor > 0 : suppression runs on multiplier * (box / divisor) [+ cls * max_wh, with max_wh = multiplier]
    *                         (exporter.py:1437-1452: boxes normalised by the larger image side, class offset in units of 1/nc);
    *   boxes_xyxy          : columns 0..3 of the prediction are already corners (the export decode, head.py:189) - no nms.py:86;
-   *   pad_output          : rows past the kept count are written as zeros (exporter.py:1478-1479 zero padding). */
+   *   pad_output          : rows past the kept count are written as zeros (exporter.py:1478-1479 zero padding), their
+   *                         indices (ypb_nms_out.idx) as -1. */
   float nms_box_divisor;
   float nms_box_multiplier;
   int32_t boxes_xyxy;

@@ -82,6 +82,9 @@ class DenseDesc(C.Structure):
         ("stride_b", C.c_int64),
         ("stride_c", C.c_int64),
         ("stride_a", C.c_int64),
+        ("anchor_subset", C.c_void_p),
+        ("subset_len", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

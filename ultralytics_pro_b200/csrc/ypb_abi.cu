@@ -377,6 +377,7 @@ int ypb_nms_from_dense(const ypb_dense_desc* pred, const ypb_nms_params* p, cons
   if (ypb::bits_for(pred->anchors) + ypb::bits_for(p->nc) > 31)
     return fail(YPB_ERR_UNSUPPORTED, "anchor and class index do not fit the 31-bit row id");
   if (!pred->ptr && pred->batch > 0) return fail(YPB_ERR_INVALID_ARGUMENT, "prediction pointer is NULL");
+  if (pred->anchor_subset && pred->subset_len < 0) return fail(YPB_ERR_INVALID_ARGUMENT, "subset_len=%d invalid", pred->subset_len);
   if (p->nms_box_divisor < 0.f || (p->nms_box_divisor > 0.f && rotated))
     return fail(YPB_ERR_UNSUPPORTED, "normalised NMS boxes (exporter flavour) are built for the axis-aligned rule only");
   ypb::Workspace w = ypb::carve_workspace(workspace, pred->batch, pred->anchors, p->rows_cap, p->max_det, p->max_nms, p->rule);

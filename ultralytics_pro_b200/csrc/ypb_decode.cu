@@ -686,11 +686,22 @@ __global__ void __launch_bounds__(DEC_THREADS)
 filter_from_dense_kernel(const __grid_constant__ ypb_dense_desc d, const __grid_constant__ FilterArgs f) {
   using T = typename DType<DT>::type;
   using D = DType<DT>;
-  const int a = blockIdx.x * DEC_THREADS + threadIdx.x;
+  const int slot_i = blockIdx.x * DEC_THREADS + threadIdx.x;
   const int b = blockIdx.y;
   const int nc = f.nc;
   const float conf = f.conf_per_image ? f.conf_per_image[b] : f.conf;
-  const bool active = a < d.anchors;
+  // one thread per anchor - or per entry of the anchor subset (ypb_dense_desc.anchor_subset): the anchor is then read through
+  // the list; an index outside [0, anchors) (a padding entry) is no candidate
+  int a = slot_i;
+  bool active = slot_i < d.anchors;
+  if (d.anchor_subset) {
+    active = slot_i < d.subset_len;
+    if (active) {
+      const long long v = d.anchor_subset[static_cast<long long>(b) * d.subset_len + slot_i];
+      active = v >= 0 && v < d.anchors;
+      a = active ? static_cast<int>(v) : 0;
+    }
+  }
   const T* p = static_cast<const T*>(d.ptr) + static_cast<long long>(b) * d.stride_b + static_cast<long long>(a) * d.stride_a;
   const T* pc = p + 4 * d.stride_c;
   const long long sc = d.stride_c;
@@ -950,7 +961,12 @@ cudaError_t launch_filter_from_head(const HeadGeom& g, int in_dtype, int value_d
 
 template <int DT>
 static cudaError_t filter_dense_dispatch(const ypb_dense_desc& d, const FilterArgs& f, cudaStream_t st) {
-  dim3 grid((d.anchors + DEC_THREADS - 1) / DEC_THREADS, d.batch);
+  const int lanes = d.anchor_subset ? d.subset_len : d.anchors;
+  if (lanes <= 0) return cudaSuccess;
+  dim3 grid((lanes + DEC_THREADS - 1) / DEC_THREADS, d.batch);
+  // (a form that stages the rows of 128 anchors in shared memory with coalesced loads for channel-contiguous tensors - the
+  // (B, A, 4+nc) layout of the end2end head - was built and measured: no faster than the per-anchor walk, whose sectors are
+  // served by L1 after the first touch; removed)
 #define YPB_FDN(R, M) filter_from_dense_kernel<DT, R, M><<<grid, DEC_THREADS, 0, st>>>(d, f)
   if (f.rotated) { if (f.multi_label) YPB_FDN(true, true); else YPB_FDN(true, false); }
   else           { if (f.multi_label) YPB_FDN(false, true); else YPB_FDN(false, false); }

@@ -851,6 +851,8 @@ __device__ void gather_stage(const SuppressArgs& a, int b, const uint64_t* kk, i
   if (a.pad_zero && a.out_rows) {  // exporter.py:1478-1479: rows past the kept count are zeros
     float* o = a.out_rows + static_cast<long long>(b) * a.max_det * cols;
     for (int i = kept_n * cols + tid; i < a.max_det * cols; i += NT) o[i] = 0.f;
+    if (a.out_idx)  // and their indices are -1 (no anchor): a list a later call may take as its anchor subset
+      for (int i = kept_n + tid; i < a.max_det; i += NT) a.out_idx[static_cast<long long>(b) * a.max_det + i] = -1;
   }
   if (a.rider && a.out_rows) {
     // Segment / Pose riders (head.py:837 mask coefficients, head.py:1252 decoded keypoints): only the kept anchors'
@@ -912,6 +914,16 @@ __device__ int suppress_image(Smem& sm, const SuppressArgs& a, int b, int n, con
       nn = select_prefix(ka, n, min(L, SORT_SMEM_MAX / 2), min(L, SORT_SMEM_MAX), kb, sm);
       kin = kb;
       partial = nn < L;
+    }
+  }
+  if constexpr (RULE == YPB_NMS_GREEDY) {
+    // A threshold >= 1 suppresses nothing (inter / union never exceeds 1): the kept rows are simply the first ranks.  The end2end
+    // top-k (head.py:193-214) runs through here twice; the greedy walk over rows that cannot touch each other was 60 % of it.
+    if (thr >= 1.0f && nn <= SORT_SMEM_MAX && a.box_div == 0.f) {
+      bitonic_sort(sm.u.keys, kin, nn, KeyIdentity{});
+      __syncthreads();
+      *kk_out = sm.u.keys;
+      return min(min(nn, a.max_nms), a.max_det);
     }
   }
   while (true) {

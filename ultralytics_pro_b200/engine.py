@@ -285,11 +285,17 @@ def _check_plan(rc: int, what: str, plan: NmsPlan) -> None:
     _cabi.check(rc, what)
 
 
-def run_from_dense(pred: torch.Tensor, plan: NmsPlan) -> None:
+def run_from_dense(pred: torch.Tensor, plan: NmsPlan, anchor_subset: torch.Tensor | None = None) -> None:
+    """anchor_subset: optional (B, n) int64 device tensor - only these anchors of ``pred`` are candidates (read in place)."""
     d = _cabi.DenseDesc()
     d.ptr, d.dtype = pred.data_ptr(), _cabi.dtype_code(pred.dtype)
     d.batch, d.channels, d.anchors = pred.shape
     d.stride_b, d.stride_c, d.stride_a = pred.stride()
+    if anchor_subset is not None:
+        if anchor_subset.dtype != torch.int64 or anchor_subset.dim() != 2 or anchor_subset.shape[0] != pred.shape[0] \
+                or not anchor_subset.is_contiguous() or anchor_subset.device != pred.device:
+            raise ValueError("anchor_subset must be a contiguous (B, n) int64 tensor on the predictions' device")
+        d.anchor_subset, d.subset_len = anchor_subset.data_ptr(), anchor_subset.shape[1]
     lib = _cabi.load()
     rc = lib.ypb_nms_from_dense(C.byref(d), C.byref(plan.params), C.byref(plan.out), plan.scratch.data_ptr(),
                                 plan.scratch.numel(), _cabi.stream_ptr(pred.device))

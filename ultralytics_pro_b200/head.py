@@ -224,19 +224,20 @@ def detect_postprocess(preds: torch.Tensor, max_det: int, nc: int = 80) -> torch
     dense = preds.transpose(1, 2)  # (B, 4+nc, A) view; the kernels take any strides
     ninf = float("-inf")
     # pass 1 (the only pass over all the scores): rank the anchors by their class maximum, keep the K best (head.py:208)
-    first = engine.make_plan(dev, b, a, nc, 0, ninf, 1.0, k, a, 0.0, False, _cabi.RULE_GREEDY, boxes_xyxy=True)
+    first = engine.make_plan(dev, b, a, nc, 0, ninf, 1.0, k, a, 0.0, False, _cabi.RULE_GREEDY, boxes_xyxy=True,
+                             pad_output=True)  # fewer than K rankable anchors (NaN scores): zero rows, index -1
     engine.run_from_dense(dense, first)
     kth = first.rows[:, k - 1, 4].contiguous()
     thr = torch.nextafter(kth, torch.full_like(kth, ninf))  # score > thr  <=>  score >= K-th anchor maximum
     # pass 2 reads ONLY those K anchors (head.py:209-211 gathers them too): every pair that can reach the result lives in an
     # anchor whose maximum is >= T, and among anchors tied at T the lower indices - the ones pass 1 kept - win the flat-index
-    # tie-break, so restricting to the kept anchors is exact.  They are taken in ascending anchor order so that "lower row
-    # first" inside pass 2 is "lower flat index first".  Index plumbing (sort / gather of B x K rows) stays on the device.
-    sel = first.idx[:, :k].clamp(0, a - 1).sort(dim=1).values
-    sub = preds.gather(1, sel.unsqueeze(-1).expand(-1, -1, 4 + nc))  # (B, K, 4+nc)
-    second = engine.make_plan(dev, b, k, nc, 0, 0.0, 1.0, k, k * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
-                              conf_per_image=thr)
-    engine.run_from_dense(sub.transpose(1, 2), second)
+    # tie-break, so restricting to the kept anchors is exact.  The kernel reads them where they lie, through the index list
+    # pass 1 left on the device (``anchor_subset``): row ids stay those of the full tensor, so "lower row first" is "lower flat
+    # index first" with no sorting or gathering in between.  A threshold of 1 makes both suppression calls pure rankings.
+    sel = first.idx if first.idx.shape[1] == k else first.idx[:, :k].contiguous()
+    second = engine.make_plan(dev, b, a, nc, 0, 0.0, 1.0, k, k * nc, 0.0, True, _cabi.RULE_GREEDY, boxes_xyxy=True,
+                              conf_per_image=thr, rows_cap=k * nc)
+    engine.run_from_dense(dense, second, anchor_subset=sel)
     return second.rows.to(preds.dtype)
 
 
