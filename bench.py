@@ -282,14 +282,16 @@ def _lane_step(lanes, i, gather_mode):
 
 
 class _DeviceBarrier:
-    """GPU-side barrier over NVLink peer memory (torch symmetric memory), enqueued on the current stream.  dist.barrier() lines the
-    HOSTS up to within tens of microseconds; a timed region of K = 20 steps lasts under a millisecond, so that skew between the
-    ranks' GPU timelines would be charged to whichever rank started first (its drain waits for the latecomer's last results).
-    This lines the GPUs themselves up before the first event is recorded.  Collective construction."""
+    """Optional (diagnostic) GPU-side barrier over NVLink peer memory (torch symmetric memory), enqueued on the current stream.
+    dist.barrier() lines the HOSTS up to within tens of microseconds; this lines the GPUs themselves up before the first event
+    is recorded.  Collective construction."""
 
     def __init__(self, dev, world):
         self.handle = None
-        if world <= 1 or os.environ.get("YPB_BENCH_NO_DEVICE_BARRIER"):
+        # OFF unless YPB_BENCH_DEVICE_BARRIER=1.  Measured (profiles/r02_n4_k20.txt, r02_n2_k20.txt): no gain at N=2 (48.1 vs 48.0 us per
+        # step at K=20), a LOSS at N=4 (49.4 vs 47.2) and N=8 (59.9) - GPUs that start in the same microsecond issue their peer stores
+        # and flag writes in the same microseconds for the whole short run; the hosts' natural skew spreads them.
+        if world <= 1 or not os.environ.get("YPB_BENCH_DEVICE_BARRIER"):
             return
         ok = 1
         try:
