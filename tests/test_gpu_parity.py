@@ -529,3 +529,64 @@ def test_head_post_processor_and_graph(cuda_device):
     graph.replay()
     got, got_idx = post.results(return_idxs=True)
     assert_rows_equal(got, got_idx, [w.cpu() for w in want], [w.cpu() for w in want_idx], "graph replay")
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_graphed_post_processor_host_counts(cuda_device, batch):
+    """use_graph=True: the per-image counts come from the plan's mapped host buffer, written by the suppression kernel itself
+    (ypb_nms_out.count_host) - no copy node; a single image skips the packing kernel and returns views of the plan's rows.
+    Replays on changed input contents must follow the contents."""
+    from ultralytics_pro_b200.head import postprocess_from_head
+    from ultralytics_pro_b200.pipeline import HeadPostProcessor
+
+    cfg = CONFIGS["c2_v8x_640_b64"]
+    post = HeadPostProcessor(cfg.nc, cfg.strides, cfg.conf, cfg.iou, use_graph=True)
+    static = [lv.to(cuda_device) for lv in make_head_batch(cfg, batch=batch, seed=60)[0]]
+    for seed in (61, 62, 63):
+        fresh = [lv.to(cuda_device) for lv in make_head_batch(cfg, batch=batch, seed=seed)[0]]
+        for dst, src in zip(static, fresh):
+            dst.copy_(src)
+        want, want_idx = postprocess_from_head(fresh, cfg.strides, cfg.nc, cfg.conf, cfg.iou, return_idxs=True)
+        got, got_idx = post(static, return_idxs=True)
+        assert post.last.count_host is not None
+        assert post.last.count_host.tolist() == [int(w.shape[0]) for w in want]
+        assert_rows_equal([g.cpu() for g in got], [g.cpu() for g in got_idx], [w.cpu() for w in want], [w.cpu() for w in want_idx],
+                          f"graph + host counts, seed {seed}")
+    assert len(post._graphs) == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("mode", ["obb_nc15", "xyxy", "nc20_tail"])
+def test_decode_dense16_modes(cuda_device, dtype, mode):
+    """The 16-bit dense decode kernel (16-row batches): rotated decode with the class rows entirely in the tail loop (nc = 15),
+    the corner form, and a class count with whole batches AND a tail (nc = 20), against fp32 math on the same rounded inputs."""
+    from ultralytics_pro_b200.head import decode_head
+    from ultralytics_pro_b200.synth import HeadConfig
+
+    if mode == "obb_nc15":
+        cfg = CONFIGS["c5_obb_1024_b16"]
+        levels, ang = make_head_batch(cfg, batch=2, seed=71, dtype=dtype)
+        exact = obb_forward_oracle([lv.float() for lv in levels], ang.float(), cfg.strides, cfg.nc)
+        dl, da = _to(cuda_device, levels, ang)
+        got = decode_head(dl, cfg.strides, cfg.nc, angle=da, angle_is_logit=True, append_angle=True).float().cpu()
+    elif mode == "xyxy":
+        cfg = CONFIGS["c1_v8n_640_b1"]
+        levels, _ = make_head_batch(cfg, batch=2, seed=72, dtype=dtype)
+        exact = decode_oracle([lv.float() for lv in levels], cfg.strides, cfg.nc, xyxy=True)
+        got = decode_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc, xyxy=True).float().cpu()
+    else:
+        cfg = HeadConfig("nc20", 320, (8, 16, 32), 20, 2, objects=5)
+        levels, _ = make_head_batch(cfg, batch=2, seed=73, dtype=dtype)
+        exact = decode_oracle([lv.float() for lv in levels], cfg.strides, cfg.nc)
+        got = decode_head(_to(cuda_device, levels)[0], cfg.strides, cfg.nc).float().cpu()
+    assert got.shape == exact.shape
+    tol = 1e-2 * exact.abs() + 1e-2
+    if mode == "obb_nc15":
+        # the angle is rounded to 16 bits before the rotation (as the reference's tensor is): a centre moves by up to
+        # |offset| * 2^-9 * |theta| pixels against fp32 math - allow it on the two centre rows, and require the aggregate error to be
+        # no worse than the reference's own per-op-rounded chain
+        tol[:, :2] += 1.5
+        ref = obb_forward_oracle(levels, ang, cfg.strides, cfg.nc).float()
+        assert float((got - exact).abs().mean()) <= float((ref - exact).abs().mean()) * 1.05 + 1e-6
+    err = (got - exact).abs()
+    assert not bool((err > tol).any()), f"max err {float(err.max())} at {int(err.argmax())}"
