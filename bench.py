@@ -211,7 +211,7 @@ def _post_for(cfg, gather_mode, scan_kernel="auto"):
                              peer_gather_group=True if gather_mode == "peer" else None, scan_kernel=scan_kernel)
 
 
-def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lane_groups=None, scan_kernel="auto"):
+def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lane_groups=None, scan_kernel="auto", consumer="beside"):
     """`nlanes` independent pipelines (own stream, plan, scratch, result buffers, CUDA graphs); lane i owns input sets i and
     i + nlanes.  One step of a lane = [class scan, survivor decode, sort+suppress (+ peer push)], then - all
     inside the lane's CUDA graph - the consumer side: multi-GPU: wait for the gathered batch (`lag` batches back), copy the
@@ -238,7 +238,9 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
                 gb = torch.empty((1, world, pl.peers.slot), dtype=torch.float32, device=dev)  # the consumer's copy of the entry
             grp = lane_groups[ln] if lane_groups else None
 
-            beside_mode = gather_mode == "peer" and use_graph and lag == 1 and not os.environ.get("YPB_BENCH_TAIL_CONSUME")
+            # consumer = "beside": the gathered batch q-1 is consumed on a forked branch of step q's graph; "tail": behind step q-1's
+            # suppression kernel (round 1's placement)
+            beside_mode = gather_mode == "peer" and use_graph and lag == 1 and consumer == "beside"
 
             def consume(pp=pp, pl=pl, gb=gb, want=(-1 if beside_mode else lag)):
                 pp.wait_gather(want)
@@ -261,7 +263,7 @@ def _build_lanes(dev, cfg, sets, nlanes, world, gather_mode, lag, use_graph, lan
                 # graph - it runs beside the class scan of step q instead of behind its suppression kernel
                 graphs = [pp.capture(lv, ang, after=tail, beside=consume if beside_mode else None) for lv, ang in my_sets]
         st.synchronize()
-        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": graphs, "plan": pl, "gather": gb, "tail": tail, "beside": beside_mode,
+        lanes.append({"stream": st, "post": pp, "sets": my_sets, "graphs": graphs, "plan": pl, "gather": gb, "tail": tail, "beside": beside_mode, "primed": True,
                       "group": grp, "host_counts": host_counts})
     return lanes
 
@@ -343,8 +345,15 @@ def _time_lanes(dev, lanes, K, W, world, gather_mode, lag, sampler=None, device_
             for ln in lanes:
                 with torch.cuda.stream(ln["stream"]):
                     ln["post"].wait_gather(0)
+                ln["primed"] = False  # every batch has been handed out: an in-order consumer would now wait for its OWN step's launch
 
     fork()
+    for ln in lanes:
+        if ln.get("beside") and not ln["primed"]:
+            # restore the steady state of the lag-1 pipeline after a drain: one launch in flight that nobody has consumed yet
+            with torch.cuda.stream(ln["stream"]):
+                ln["post"].enqueue(*ln["sets"][0])
+            ln["primed"] = True
     for i in range(W):
         _lane_step(lanes, i, gather_mode)
     drain(final=False)
@@ -594,7 +603,22 @@ def run_ours(args):
     lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager") else None)
     sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B) for s in range(NSETS)]
     use_graph = not args.no_graph
-    lanes = _build_lanes(dev, cfg, sets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups)
+    consumer = os.environ.get("YPB_BENCH_CONSUMER", "beside")  # beside (default, measured best at N=2 and N=4) | tail | auto
+    lanes = _build_lanes(dev, cfg, sets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups,
+                         consumer="tail" if consumer == "tail" else "beside")
+    consumer_pick = None
+    if consumer == "auto" and lanes[0]["beside"]:
+        # Where the consumer of the gathered batch sits (forked beside the next step / behind its own step) is a placement
+        # choice whose effect depends on the number of ranks: try both for a few untimed steps OUTSIDE the timed region and keep the
+        # faster one (all ranks decide on the same max-over-ranks numbers).  Measured at N=2 and N=4 the forked form wins.
+        t_b = _time_lanes(dev, lanes, 40, 5, world, gather_mode, args.gather_lag)
+        lanes_t = _build_lanes(dev, cfg, sets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups, consumer="tail")
+        t_t = _time_lanes(dev, lanes_t, 40, 5, world, gather_mode, args.gather_lag)
+        consumer_pick = {"beside_us_per_step": t_b / 40 * 1e3, "tail_us_per_step": t_t / 40 * 1e3}
+        if t_t < t_b:
+            lanes, lanes_t = lanes_t, lanes
+        consumer_pick["picked"] = "beside" if lanes[0]["beside"] else "tail"
+        del lanes_t
     post, plan = lanes[0]["post"], lanes[0]["plan"]
 
     # everything with a variable host cost (NVML init of the clock sampler, event creation) happens BEFORE the barrier inside
@@ -735,6 +759,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "gpu_launches": (3 + (1 if gather_mode == "peer" else 0)) * K,
             "gather_verified_against_nccl": gather_verified,
+            "gather_consumer": consumer_pick,
             "strong_scaling": strong,
             "e2e": e2e,
             "roofline": roofline,
