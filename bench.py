@@ -603,7 +603,7 @@ def run_ours(args):
     lane_groups = ([dist.new_group(backend="nccl") for _ in range(LANES)] if gather_mode in ("nccl", "nccl-eager") else None)
     sets = [make_head_batch(cfg, batch=B, seed=1000 + s, device=dev, dtype=dtype, first_image=rank * B) for s in range(NSETS)]
     use_graph = not args.no_graph
-    consumer = os.environ.get("YPB_BENCH_CONSUMER", "beside")  # beside (default, measured best at N=2 and N=4) | tail | auto
+    consumer = os.environ.get("YPB_BENCH_CONSUMER", "auto")  # auto (default: a 40-step trial of each placement outside the timed region) | beside | tail
     lanes = _build_lanes(dev, cfg, sets, LANES, world, gather_mode, args.gather_lag, use_graph, lane_groups,
                          consumer="tail" if consumer == "tail" else "beside")
     consumer_pick = None
@@ -654,7 +654,8 @@ def run_ours(args):
 
     if os.environ.get("YPB_BENCH_QUICK"):  # diagnostic: only the headline timing
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": total_ms / K, "gather_verified_against_nccl": gather_verified, "quick": True}))
+            print(json.dumps({"value": value, "ms_per_step": total_ms / K, "gather_verified_against_nccl": gather_verified,
+                              "gather_consumer": consumer_pick, "quick": True}))
         sys.stdout.flush()
         if world > 1:
             dist.barrier()
