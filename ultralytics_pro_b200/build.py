@@ -129,5 +129,44 @@ def _build_locked(force: bool, verbose: bool) -> str:
     return LIB_PATH
 
 
+HARNESS_SRC = os.path.join(PKG_DIR, "..", "tests", "cabi_device_harness.cu")
+HARNESS_PATH = os.path.join(LIB_DIR, "ypb_cabi_harness")
+
+
+def build_harness(force: bool = False) -> str:
+    """Compile tests/cabi_device_harness.cu - the torch-free C++ consumer of the C-ABI that the GPU tests and the
+    compute-sanitizer runs execute - next to the library (rpath $ORIGIN).  Test infrastructure, not part of the product."""
+    lib = build_library()
+    src = os.path.normpath(HARNESS_SRC)
+    h = hashlib.sha256()
+    for name in (src, os.path.join(CSRC, HEADERS[1])):
+        with open(name, "rb") as fh:
+            h.update(fh.read())
+    with open(STAMP) as fh:
+        h.update(fh.read().encode())
+    digest, tag = h.hexdigest(), HARNESS_PATH + ".digest"
+    if not force and os.path.exists(HARNESS_PATH) and os.path.exists(tag) and open(tag).read().strip() == digest:
+        return HARNESS_PATH
+    import fcntl
+
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            tmp = HARNESS_PATH + f".tmp{os.getpid()}"
+            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-lineinfo",
+                   "-I", os.path.join(PKG_DIR, "..", "include"), src, "-o", tmp, "-L", os.path.dirname(lib), "-lyolopost_b200",
+                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-cudart", "shared"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            os.replace(tmp, HARNESS_PATH)
+            with open(tag, "w") as fh:
+                fh.write(digest)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return HARNESS_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_harness(force="--force" in sys.argv))
