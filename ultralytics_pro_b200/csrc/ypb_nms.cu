@@ -679,6 +679,9 @@ __device__ int classwise_greedy(Smem& sm, const SuppressArgs& a, const uint64_t*
       if ((keptw >> lane) & 1u) {
         sm.krank[s + nk + __popc(keptw & lt_mask)] = static_cast<uint16_t>(r0 + lane);
       }
+      // every lane read ckept[cid] at the top of this group: order those reads before lane 0's update (the ballots in between
+      // converge the warp but are not memory barriers; compute-sanitizer racecheck reports the pair without this)
+      __syncwarp();
       if (lane == 0) {
         sm.ckept[cid] = nk + __popc(keptw);
         if (keptw) {
